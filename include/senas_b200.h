@@ -1,0 +1,150 @@
+/*
+ * senas_b200.h -- C ABI of libsenas_b200.so: the SENAS supernet-search hot path on B200 (sm_100a).
+ *
+ * The reference (RayburnChen/senas) has no FFI: its hot path sits behind two Python methods,
+ *     search.cell.MixedOp.forward(x, alpha_normal, alpha_up_dn)            search/cell.py:32-43
+ *     search.cell.Cell.forward(in0, in1, weights_norm, weights_chg, betas) search/cell.py:92-110
+ * (node loop :95-108 and concat :110; preprocess0/1 and post_process are outside this ABI).
+ * The entry points below are what a ctypes binding of those two methods calls; see INTEGRATION.md
+ * for the reference-side stub.  One "edge graph" object covers both granularities:
+ *     a MixedOp  = 1 input state, 1 node, 1 edge, no beta, no ReLU;
+ *     a Cell     = 2 input states, meta_node_num nodes, 2+3+..+(n+1) edges, beta-weighted node
+ *                  sums, ReLU per node, nodes written side by side into one NHWC concat buffer.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor is allocated by the caller (PyTorch's caching
+ *     allocator) and the library keeps no pointer past a call, except the parameter pointers
+ *     recorded in the graph descriptor (they must stay valid and fixed for the graph's lifetime;
+ *     optimizers update parameters in place, so they are).
+ *   - activations are NHWC ("channels_last"), fp32; `*_ld` is the distance in elements between
+ *     consecutive pixels (so a channel slice of a wider buffer can be passed without a copy).
+ *   - every function returns 0 on success, non-zero on failure with a message available from
+ *     senas_last_error() (thread local).  There is no CPU fallback and no multi-backend dispatch:
+ *     a non-sm_100 device or an unsupported shape is an error.
+ *   - all work is enqueued on the caller's stream; nothing synchronises the device.
+ */
+#ifndef SENAS_B200_H_
+#define SENAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SENAS_MAX_CAND 6   /* candidates per MixedOp = alpha columns (utils/operations.py:23-48) */
+#define SENAS_SLOTS 12     /* parameter/buffer slots per candidate, see table below */
+#define SENAS_MAX_EDGES 16
+#define SENAS_MAX_NODES 4
+
+/* OpType ids: the reference's OpType.value['id'] (utils/operations.py:51-54) */
+enum { SENAS_OP_UP = 1, SENAS_OP_DOWN = 2, SENAS_OP_NORM = 3 };
+
+/* candidate kinds (OPS registry, utils/operations.py:8-21) */
+enum {
+  SENAS_KIND_NONE = 0,      /* ZeroOp  -> (1x1 conv) -> BN          :9,155-164  */
+  SENAS_KIND_IDENTITY = 1,  /* Identity-> (1x1 conv) -> BN          :10         */
+  SENAS_KIND_AVG_POOL = 2,  /* AvgPool2d(3,s,1,count_include_pad=False) -> 1x1 -> BN  :62 */
+  SENAS_KIND_UP_SAMPLE = 3, /* Upsample(x2, bilinear, align_corners=False) -> 1x1 -> BN :13 */
+  SENAS_KIND_CONV = 4,      /* ConvBn   (dil_3_conv_5, dil_2_conv_5) :89-95     */
+  SENAS_KIND_SE_CONV = 5,   /* ConvBnSe (se_conv_3)                  :98-104    */
+  SENAS_KIND_DEPSEP = 6     /* DepSepConv (dep_sep_conv_3/5)         :107-115   */
+};
+
+/*
+ * Parameter slots (device pointers to fp32 unless noted; NULL when absent).
+ *   BN group at slot s: s+0 weight(gamma) s+1 bias(beta) s+2 running_mean s+3 running_var
+ *                       s+4 num_batches_tracked (int64)
+ *   NONE/IDENTITY/AVG_POOL/UP_SAMPLE : 0 conv.weight [8,c_in,1,1] (NULL when c_in == 8), BN @1
+ *   CONV                             : 0 conv weight ([8,c_in,k,k], or [c_in,8,k,k] for UP), BN @1
+ *   SE_CONV                          : as CONV, plus 6 excitation.0.weight [1,8], 7 excitation.2.weight [8,1]
+ *   DEPSEP                           : 0 depthwise weight [c_in,1,k,k], BN(c_in) @1,
+ *                                      6 pointwise weight [8,c_in,1,1], BN(8) @7
+ */
+typedef struct {
+  int32_t src;                 /* state read by the edge: 0..n_inputs-1 inputs, n_inputs+i = node i */
+  int32_t dst;                 /* node that accumulates it */
+  int32_t op_type;             /* SENAS_OP_* */
+  int32_t c_in;                /* 8 or 32 */
+  int32_t kind[SENAS_MAX_CAND];
+  int32_t ksize[SENAS_MAX_CAND];    /* 3 or 5 for CONV/SE_CONV/DEPSEP, else 0 */
+  int32_t dilation[SENAS_MAX_CAND]; /* 1, 2 or 3 */
+  void *param[SENAS_MAX_CAND][SENAS_SLOTS];
+  int64_t grad_off[SENAS_MAX_CAND][SENAS_SLOTS]; /* offset (floats) in the flat gradient buffer, -1 = none */
+} senas_edge_desc_t;
+
+typedef struct {
+  int32_t n_inputs;            /* 1 or 2 */
+  int32_t n_nodes;             /* 1..SENAS_MAX_NODES */
+  int32_t n_edges;
+  int32_t c_out;               /* channels per node; only 8 is supported (Cell.k = 4, c = 32) */
+  int32_t node_relu;           /* 1: node = relu(sum), cell.py:107; 0: plain sum (MixedOp) */
+  int32_t reserved;
+  int64_t grad_floats;         /* length of the flat parameter-gradient buffer */
+  senas_edge_desc_t edge[SENAS_MAX_EDGES];
+} senas_graph_desc_t;
+
+typedef struct senas_graph senas_graph_t;
+
+typedef struct {
+  int32_t out_h, out_w;        /* spatial size of the nodes */
+  int64_t saved_bytes;         /* forward -> backward buffer (pre-BN candidate outputs, statistics) */
+  int64_t scratch_bytes;       /* scratch, may be shared by all graphs of one stream */
+} senas_plan_info_t;
+
+typedef struct {
+  int32_t batch;
+  int32_t training;            /* 1: batch statistics + running-stat update; 0: running statistics */
+  int32_t in_h[2], in_w[2];
+  const float *in[2];          /* input states, NHWC */
+  int64_t in_ld[2];
+  const float *alpha;          /* [n_edges][6] softmaxed weights, row already selected by OpType (cell.py:33-36) */
+  const float *beta;           /* [n_edges] per-edge weights (cell.py:104) or NULL for 1 */
+  float *out;                  /* [B, out_h, out_w, n_nodes*c_out] = cat(states[-n:], 1) (cell.py:110) */
+  int64_t out_ld;
+  void *saved;
+  void *scratch;
+  void *stream;                /* cudaStream_t */
+} senas_fwd_args_t;
+
+typedef struct {
+  int32_t batch;
+  int32_t training;
+  int32_t in_h[2], in_w[2];
+  const float *in[2];
+  int64_t in_ld[2];
+  const float *alpha;
+  const float *beta;
+  const float *out;            /* forward result (ReLU mask) */
+  int64_t out_ld;
+  const float *grad_out;       /* dL/d out, same geometry */
+  int64_t grad_out_ld;
+  void *saved;                 /* the buffer forward filled; backward may overwrite it */
+  void *scratch;
+  float *grad_in[2];           /* written (not accumulated); NULL to skip an input */
+  int64_t grad_in_ld[2];
+  float *grad_alpha;           /* [n_edges][6] */
+  float *grad_beta;            /* [n_edges] or NULL */
+  float *grad_params;          /* flat buffer of desc.grad_floats floats, fully written */
+  void *stream;
+} senas_bwd_args_t;
+
+const char *senas_version(void);
+const char *senas_last_error(void);
+/* 0 iff `device` is a compute-capability 10.x GPU this library was built for */
+int senas_device_check(int device);
+
+int senas_graph_create(const senas_graph_desc_t *desc, senas_graph_t **out);
+void senas_graph_destroy(senas_graph_t *g);
+/* geometry + workspace sizes for one batch/input size (cached inside the graph) */
+int senas_graph_plan(senas_graph_t *g, int32_t batch, const int32_t in_h[2], const int32_t in_w[2],
+                     senas_plan_info_t *info);
+int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a);
+int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t senas_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SENAS_B200_H_ */

@@ -1,0 +1,87 @@
+"""ctypes binding of ``libsenas_b200.so`` (C ABI in ``include/senas_b200.h``).
+
+The library is built in-tree by ``senas_b200.build.build()`` (nvcc, sm_100a only) and loaded
+from ``senas_b200/lib/``.  There is no fallback: if the shared object is missing, or the device
+is not sm_100, importing the hot path raises.
+"""
+import ctypes as C
+import os
+
+MAX_CAND, SLOTS, MAX_EDGES, MAX_NODES = 6, 12, 16, 4
+OP_UP, OP_DOWN, OP_NORM = 1, 2, 3
+
+LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libsenas_b200.so')
+
+
+class EdgeDesc(C.Structure):
+    _fields_ = [('src', C.c_int32), ('dst', C.c_int32), ('op_type', C.c_int32), ('c_in', C.c_int32),
+                ('kind', C.c_int32 * MAX_CAND), ('ksize', C.c_int32 * MAX_CAND), ('dilation', C.c_int32 * MAX_CAND),
+                ('param', (C.c_void_p * SLOTS) * MAX_CAND), ('grad_off', (C.c_int64 * SLOTS) * MAX_CAND)]
+
+
+class GraphDesc(C.Structure):
+    _fields_ = [('n_inputs', C.c_int32), ('n_nodes', C.c_int32), ('n_edges', C.c_int32), ('c_out', C.c_int32),
+                ('node_relu', C.c_int32), ('reserved', C.c_int32), ('grad_floats', C.c_int64),
+                ('edge', EdgeDesc * MAX_EDGES)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [('out_h', C.c_int32), ('out_w', C.c_int32), ('saved_bytes', C.c_int64), ('scratch_bytes', C.c_int64)]
+
+
+class FwdArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('training', C.c_int32), ('in_h', C.c_int32 * 2), ('in_w', C.c_int32 * 2),
+                ('in_', C.c_void_p * 2), ('in_ld', C.c_int64 * 2), ('alpha', C.c_void_p), ('beta', C.c_void_p),
+                ('out', C.c_void_p), ('out_ld', C.c_int64), ('saved', C.c_void_p), ('scratch', C.c_void_p),
+                ('stream', C.c_void_p)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('training', C.c_int32), ('in_h', C.c_int32 * 2), ('in_w', C.c_int32 * 2),
+                ('in_', C.c_void_p * 2), ('in_ld', C.c_int64 * 2), ('alpha', C.c_void_p), ('beta', C.c_void_p),
+                ('out', C.c_void_p), ('out_ld', C.c_int64), ('grad_out', C.c_void_p), ('grad_out_ld', C.c_int64),
+                ('saved', C.c_void_p), ('scratch', C.c_void_p), ('grad_in', C.c_void_p * 2),
+                ('grad_in_ld', C.c_int64 * 2), ('grad_alpha', C.c_void_p), ('grad_beta', C.c_void_p),
+                ('grad_params', C.c_void_p), ('stream', C.c_void_p)]
+
+
+EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
+           'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_launch_count']
+
+
+def bind(path):
+    """Load a build of the C ABI and declare its prototypes."""
+    lib = C.CDLL(path)
+    lib.senas_version.restype = C.c_char_p
+    lib.senas_last_error.restype = C.c_char_p
+    lib.senas_device_check.argtypes = [C.c_int]
+    lib.senas_graph_create.argtypes = [C.POINTER(GraphDesc), C.POINTER(C.c_void_p)]
+    lib.senas_graph_destroy.argtypes = [C.c_void_p]
+    lib.senas_graph_destroy.restype = None
+    lib.senas_graph_plan.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(PlanInfo)]
+    lib.senas_graph_forward.argtypes = [C.c_void_p, C.POINTER(FwdArgs)]
+    lib.senas_graph_backward.argtypes = [C.c_void_p, C.POINTER(BwdArgs)]
+    lib.senas_launch_count.restype = C.c_int64
+    return lib
+
+
+_LIB = None
+
+
+def get():
+    """The product library.  Raises if it has not been built -- there is no other code path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a). senas_b200 has no PyTorch/CPU fallback for the MixedOp/Cell path.')
+        _LIB = bind(LIB_PATH)
+    return _LIB
+
+
+def check(lib, rc):
+    if rc != 0:
+        raise RuntimeError('senas_b200: ' + lib.senas_last_error().decode())

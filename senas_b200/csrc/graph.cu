@@ -1,0 +1,897 @@
+// graph.cu -- host side of libsenas_b200.so: edge-graph planning, kernel sequencing and the C ABI
+// declared in include/senas_b200.h.  A graph is either one MixedOp (search/cell.py:32-43 of the
+// reference) or the node loop + concat of one Cell (search/cell.py:95-110).
+#include "../../include/senas_b200.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "kernels.cuh"
+
+#ifdef SENAS_EMU
+static void *dev_upload(const void *h, size_t n) {
+  void *p = malloc(n);
+  memcpy(p, h, n);
+  return p;
+}
+static void dev_free(void *p) { free(p); }
+#else
+static void *dev_upload(const void *h, size_t n) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, n) != cudaSuccess) return nullptr;
+  cudaMemcpy(p, h, n, cudaMemcpyHostToDevice);
+  return p;
+}
+static void dev_free(void *p) { cudaFree(p); }
+#endif
+
+static thread_local std::string g_err;
+#define SENAS_FAIL(...)                           \
+  do {                                            \
+    char buf_[512];                               \
+    snprintf(buf_, sizeof(buf_), __VA_ARGS__);    \
+    g_err = buf_;                                 \
+    return 1;                                     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// tap tables (verified against torch in tests/test_oracle_golden.py)
+// ------------------------------------------------------------------------------------------------
+enum { DIR_FWD = 0, DIR_DGRAD = 1 };
+struct Geo {
+  TapTable taps;
+  int si, so;
+  bool base_is_out;  // base grid = the conv's output grid (else its input grid)
+};
+
+static Geo make_geo(int k, int dil, int op, int dir) {
+  Geo g;
+  memset(&g, 0, sizeof(g));
+  const int pad = (k / 2) * dil;
+  struct Tap {
+    int dy, dx, w, ph;
+  };
+  std::vector<Tap> v;
+  auto axis = [&](int kk, int &d, int &p) {  // per-axis offset and phase of kernel index kk
+    const int off = dil * (kk - k / 2);
+    if (dir == DIR_FWD) {
+      if (op == SENAS_OP_UP) {
+        p = (pad + dil * kk) & 1;
+        d = (p + pad - dil * kk) / 2;
+      } else {
+        p = 0, d = off;
+      }
+    } else {
+      if (op == SENAS_OP_NORM) {
+        p = 0, d = -off;
+      } else if (op == SENAS_OP_DOWN) {
+        p = off & 1;
+        d = (p - off) / 2;
+      } else {
+        p = 0, d = dil * kk - pad;
+      }
+    }
+  };
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      int dy, py, dx, px;
+      axis(ky, dy, py);
+      axis(kx, dx, px);
+      v.push_back({dy, dx, ky * k + kx, py * 2 + px});
+    }
+  const bool phased = (dir == DIR_FWD && op == SENAS_OP_UP) || (dir == DIR_DGRAD && op == SENAS_OP_DOWN);
+  g.taps.n = (int)v.size();
+  g.taps.nphase = phased ? 4 : 1;
+  int idx = 0;
+  g.taps.min_dy = g.taps.min_dx = 1000, g.taps.max_dy = g.taps.max_dx = -1000;
+  for (int ph = 0; ph < 4; ++ph) {
+    g.taps.pstart[ph] = idx;
+    for (auto &t : v)
+      if (t.ph == ph) {
+        g.taps.dy[idx] = (int8_t)t.dy, g.taps.dx[idx] = (int8_t)t.dx, g.taps.widx[idx] = (int8_t)t.w;
+        g.taps.phase[idx] = (int8_t)ph;
+        ++idx;
+        if (t.dy < g.taps.min_dy) g.taps.min_dy = t.dy;
+        if (t.dy > g.taps.max_dy) g.taps.max_dy = t.dy;
+        if (t.dx < g.taps.min_dx) g.taps.min_dx = t.dx;
+        if (t.dx > g.taps.max_dx) g.taps.max_dx = t.dx;
+      }
+  }
+  g.taps.pstart[4] = idx;
+  if (!phased)
+    for (int ph = 1; ph <= 4; ++ph) g.taps.pstart[ph] = idx;
+  if (dir == DIR_FWD) {
+    g.si = op == SENAS_OP_DOWN ? 2 : 1, g.so = op == SENAS_OP_UP ? 2 : 1;
+    g.base_is_out = op != SENAS_OP_UP;
+  } else {
+    g.si = op == SENAS_OP_UP ? 2 : 1, g.so = op == SENAS_OP_DOWN ? 2 : 1;
+    g.base_is_out = op == SENAS_OP_DOWN;  // here "out" = the forward conv's output grid (= gathered dy grid)
+  }
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct TermPlan {
+  int kind = 0, k = 0, dil = 1;
+  bool has_y = false, owns_y = false;
+  int64_t y_off = -1, z_off = -1;
+  int64_t mean_off = -1, istd_off = -1, mean1_off = -1, istd1_off = -1, ysum_off = -1, se_off = -1;
+  int64_t part_off = -1, part1_off = -1;
+  int nblk = 0, nblk1 = 0;
+  int64_t scale_off = -1, coef_off = -1;
+};
+struct EdgePlan {
+  int in_h, in_w;
+  TermPlan t[SENAS_MAX_CAND];
+};
+struct NodePlan {
+  int64_t bias_off, gm_off, dnode_off, bpart_off;
+  int nblk;
+  bool has_consumer;
+};
+struct Plan {
+  int B, in_h[2], in_w[2], out_h, out_w, hw;
+  int64_t saved_floats = 0, scratch_floats = 0, tmp_off = 0, tmp_floats = 0;
+  std::vector<EdgePlan> edges;
+  std::vector<NodePlan> nodes;
+  std::vector<BnDesc *> d_bnA, d_bnB;  // per stage
+  std::vector<int> n_bnA, n_bnB;
+  NodeDesc *d_nodes = nullptr;
+};
+
+struct senas_graph {
+  senas_graph_desc_t d;
+  std::map<std::tuple<int, int, int, int, int>, Plan *> plans;
+};
+
+static int state_stage(const senas_graph_desc_t &d, int s) { return s < d.n_inputs ? 0 : s - d.n_inputs + 1; }
+
+static int out_dim(int op, int v) { return op == SENAS_OP_NORM ? v : (op == SENAS_OP_DOWN ? (v + 1) / 2 : 2 * v); }
+
+static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *iw, Plan **outp) {
+  const senas_graph_desc_t &d = g->d;
+  auto key = std::make_tuple(B, (int)ih[0], (int)iw[0], d.n_inputs > 1 ? (int)ih[1] : 0, d.n_inputs > 1 ? (int)iw[1] : 0);
+  auto it = g->plans.find(key);
+  if (it != g->plans.end()) {
+    *outp = it->second;
+    return 0;
+  }
+  if (B < 1 || B > 128) SENAS_FAIL("batch %d unsupported (1..128 per GPU)", B);
+  Plan *p = new Plan();
+  p->B = B;
+  for (int i = 0; i < 2; ++i) p->in_h[i] = i < d.n_inputs ? ih[i] : 0, p->in_w[i] = i < d.n_inputs ? iw[i] : 0;
+  p->out_h = p->out_w = -1;
+  p->edges.resize(d.n_edges);
+  for (int e = 0; e < d.n_edges; ++e) {  // geometry: resolve in edge order (node edges come after their node's inputs)
+    const senas_edge_desc_t &ed = d.edge[e];
+    int h, w;
+    if (ed.src < d.n_inputs) {
+      h = ih[ed.src], w = iw[ed.src];
+    } else {
+      if (p->out_h < 0) SENAS_FAIL("edge %d reads a node before any input edge defined the node size", e);
+      h = p->out_h, w = p->out_w;
+    }
+    if (h < 1 || w < 1) SENAS_FAIL("edge %d: empty input %dx%d", e, h, w);
+    const int oh = out_dim(ed.op_type, h), ow = out_dim(ed.op_type, w);
+    if (p->out_h < 0) p->out_h = oh, p->out_w = ow;
+    if (oh != p->out_h || ow != p->out_w)
+      SENAS_FAIL("edge %d produces %dx%d but the nodes are %dx%d", e, oh, ow, p->out_h, p->out_w);
+    p->edges[e].in_h = h, p->edges[e].in_w = w;
+  }
+  p->hw = p->out_h * p->out_w;
+  const int HW = p->hw;
+  int64_t sv = 0, sc = 0;
+  auto take = [](int64_t &cur, int64_t n) {
+    int64_t o = cur;
+    cur = align4(cur + n);
+    return o;
+  };
+  const int nblk_px = cdiv(HW, 128);
+  int64_t tmp_need = 0;
+  for (int e = 0; e < d.n_edges; ++e) {
+    const senas_edge_desc_t &ed = d.edge[e];
+    EdgePlan &ep = p->edges[e];
+    const int C = ed.c_in;
+    for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+      TermPlan &t = ep.t[k];
+      t.kind = ed.kind[k], t.k = ed.ksize[k], t.dil = ed.dilation[k];
+      t.mean_off = take(sv, 8), t.istd_off = take(sv, 8);
+      t.scale_off = take(sc, B * 8), t.coef_off = take(sc, 3 * B * 8);
+      const int T = t.k * t.k;
+      switch (t.kind) {
+        case SENAS_KIND_NONE:
+          break;
+        case SENAS_KIND_IDENTITY:
+          t.has_y = true, t.owns_y = (C != 8);
+          t.nblk = nblk_px;
+          if (C != 8) tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * nblk_px * 8 * C);
+          break;
+        case SENAS_KIND_AVG_POOL:
+        case SENAS_KIND_UP_SAMPLE:
+          t.has_y = t.owns_y = true, t.nblk = nblk_px;
+          tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(std::max(HW, ep.in_h * ep.in_w), 128) * 8 * C);
+          break;
+        case SENAS_KIND_CONV:
+        case SENAS_KIND_SE_CONV: {
+          t.has_y = t.owns_y = true;
+          Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
+          const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
+          t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW);
+          tmp_need = std::max<int64_t>(tmp_need, (int64_t)296 * T * C * 8);
+          if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
+          break;
+        }
+        case SENAS_KIND_DEPSEP: {
+          t.has_y = t.owns_y = true;
+          Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
+          const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
+          t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
+          t.nblk = nblk_px;
+          t.z_off = take(sv, (int64_t)B * HW * C);
+          t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
+          t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C);
+          const int64_t pw_tmp = (int64_t)B * nblk_px * 10 * C + 4 * C;
+          const int64_t dw_tmp = (int64_t)B * cdiv(bh * bw, 256) * C * T;
+          tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
+          break;
+        }
+        default:
+          delete p;
+          SENAS_FAIL("edge %d candidate %d: unknown kind %d", e, k, t.kind);
+      }
+      if (t.owns_y) t.y_off = take(sv, (int64_t)B * HW * 8);
+      if (t.has_y) t.part_off = take(sc, (int64_t)B * t.nblk * 16);
+    }
+  }
+  p->nodes.resize(d.n_nodes);
+  for (int i = 0; i < d.n_nodes; ++i) {
+    NodePlan &np = p->nodes[i];
+    int nterms = 0;
+    np.has_consumer = false;
+    for (int e = 0; e < d.n_edges; ++e) {
+      if (d.edge[e].dst == i) nterms += SENAS_MAX_CAND;
+      if (d.edge[e].src == d.n_inputs + i) np.has_consumer = true;
+    }
+    if (nterms > kMaxTerms) {
+      delete p;
+      SENAS_FAIL("node %d has %d terms (max %d)", i, nterms, kMaxTerms);
+    }
+    np.nblk = nblk_px;
+    np.bias_off = take(sc, B * 8);
+    np.gm_off = take(sc, (int64_t)B * HW * 8);
+    np.dnode_off = np.has_consumer ? take(sc, (int64_t)B * HW * 8) : -1;
+    np.bpart_off = take(sc, (int64_t)B * nblk_px * (1 + nterms) * 8);
+  }
+  p->tmp_off = take(sc, tmp_need);
+  p->tmp_floats = tmp_need;
+  p->saved_floats = sv, p->scratch_floats = sc;
+
+  // device descriptor tables
+  const int nstage = d.n_nodes;
+  p->d_bnA.assign(nstage, nullptr), p->d_bnB.assign(nstage, nullptr);
+  p->n_bnA.assign(nstage, 0), p->n_bnB.assign(nstage, 0);
+  for (int s = 0; s < nstage; ++s) {
+    std::vector<BnDesc> A, Bv;
+    for (int e = 0; e < d.n_edges; ++e) {
+      const senas_edge_desc_t &ed = d.edge[e];
+      if (state_stage(d, ed.src) != s) continue;
+      const EdgePlan &ep = p->edges[e];
+      for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+        const TermPlan &t = ep.t[k];
+        BnDesc b;
+        memset(&b, 0, sizeof(b));
+        const bool ds = t.kind == SENAS_KIND_DEPSEP;
+        const int bs = ds ? 7 : 1;  // slot of the final BN group
+        b.C = 8, b.nblk = t.nblk, b.zero_input = t.kind == SENAS_KIND_NONE;
+        b.count_per_sample = (float)HW;
+        b.part_off = t.part_off, b.mean_off = t.mean_off, b.istd_off = t.istd_off, b.ysum_off = t.ysum_off;
+        b.gamma = (float *)ed.param[k][bs], b.beta = (float *)ed.param[k][bs + 1];
+        b.rmean = (float *)ed.param[k][bs + 2], b.rvar = (float *)ed.param[k][bs + 3];
+        b.nbt = (int64_t *)ed.param[k][bs + 4];
+        if (!b.gamma || !b.beta || !b.rmean || !b.rvar || !b.nbt) {
+          delete p;
+          SENAS_FAIL("edge %d candidate %d: missing BatchNorm parameter pointer", e, k);
+        }
+        if (ds) {
+          Bv.push_back(b);
+          BnDesc b1 = b;
+          b1.C = ed.c_in, b1.nblk = t.nblk1, b1.part_off = t.part1_off, b1.mean_off = t.mean1_off;
+          b1.istd_off = t.istd1_off, b1.ysum_off = -1;
+          b1.gamma = (float *)ed.param[k][1], b1.beta = (float *)ed.param[k][2], b1.rmean = (float *)ed.param[k][3];
+          b1.rvar = (float *)ed.param[k][4], b1.nbt = (int64_t *)ed.param[k][5];
+          A.push_back(b1);
+        } else {
+          A.push_back(b);
+        }
+      }
+    }
+    p->n_bnA[s] = (int)A.size(), p->n_bnB[s] = (int)Bv.size();
+    if (!A.empty()) p->d_bnA[s] = (BnDesc *)dev_upload(A.data(), A.size() * sizeof(BnDesc));
+    if (!Bv.empty()) p->d_bnB[s] = (BnDesc *)dev_upload(Bv.data(), Bv.size() * sizeof(BnDesc));
+  }
+  std::vector<NodeDesc> nds(d.n_nodes);
+  for (int i = 0; i < d.n_nodes; ++i) {
+    NodeDesc &nd = nds[i];
+    memset(&nd, 0, sizeof(nd));
+    const NodePlan &np = p->nodes[i];
+    nd.node = i, nd.bias_off = np.bias_off, nd.gm_off = np.gm_off, nd.dnode_off = np.dnode_off;
+    nd.bpart_off = np.bpart_off, nd.nblk = np.nblk, nd.hw = HW;
+    for (int e = 0; e < d.n_edges; ++e) {
+      const senas_edge_desc_t &ed = d.edge[e];
+      if (ed.dst != i) continue;
+      if (nd.nedges >= 4) {
+        delete p;
+        SENAS_FAIL("node %d has more than 4 incoming edges", i);
+      }
+      nd.edges[nd.nedges++] = e;
+      for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+        const TermPlan &t = p->edges[e].t[k];
+        TermDesc &td = nd.t[nd.nterms++];
+        const int bs = t.kind == SENAS_KIND_DEPSEP ? 7 : 1;
+        td.kind = t.kind, td.edge = e, td.cand = k, td.has_y = t.has_y;
+        if (t.owns_y) {
+          td.y = Ref{SP_SAVED, 0, t.y_off, 8};
+        } else if (t.has_y) {  // identity 8->8: y is the edge input itself
+          if (ed.src < d.n_inputs) td.y = Ref{SP_IN0 + ed.src, 0, 0, 0};
+          else td.y = Ref{SP_OUT, 0, (int64_t)(ed.src - d.n_inputs) * 8, 0};
+        } else {
+          td.y = Ref{SP_NULL, 0, 0, 0};
+        }
+        td.mean_off = t.mean_off, td.istd_off = t.istd_off, td.ysum_off = t.ysum_off, td.se_off = t.se_off;
+        td.scale_off = t.scale_off, td.coef_off = t.coef_off;
+        td.gamma = (float *)ed.param[k][bs], td.beta = (float *)ed.param[k][bs + 1];
+        td.w1 = (float *)ed.param[k][6], td.w2 = (float *)ed.param[k][7];
+        td.g_gamma = ed.grad_off[k][bs], td.g_beta = ed.grad_off[k][bs + 1];
+        td.g_w1 = ed.grad_off[k][6], td.g_w2 = ed.grad_off[k][7];
+        td.hw = (float)HW;
+        if (t.kind == SENAS_KIND_SE_CONV && (!td.w1 || !td.w2)) {
+          delete p;
+          SENAS_FAIL("edge %d candidate %d: missing SE weights", e, k);
+        }
+      }
+    }
+  }
+  p->d_nodes = (NodeDesc *)dev_upload(nds.data(), nds.size() * sizeof(NodeDesc));
+  g->plans[key] = p;
+  *outp = p;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static const int kPersistBlocks = 296;
+
+template <typename K>
+static void allow_smem(K kern, size_t bytes) {
+#ifndef SENAS_EMU
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+#else
+  (void)kern, (void)bytes;
+#endif
+}
+
+static size_t gather_smem(const Geo &g, int NC) {
+  const int R = (kTileH - 1) * g.si + (g.taps.max_dy - g.taps.min_dy) + 1;
+  const int Cc = (kTileW - 1) * g.si + (g.taps.max_dx - g.taps.min_dx) + 1;
+  return (size_t)2 * R * Cc * 16 + (size_t)g.taps.n * 8 * NC * 4;
+}
+
+template <int KC, int NC, int NPH>
+static void launch_gather(GatherArgs &a, const Geo &g, int B, void *stream) {
+  auto kern = gather_mac_kernel<KC, NC, NPH>;
+  const size_t smem = gather_smem(g, NC);
+  allow_smem(kern, smem);
+  a.tiles_x = cdiv(a.base_w, kTileW);
+  dim3 grid(a.tiles_x * cdiv(a.base_h, kTileH), B);
+  SENAS_LAUNCH(kern, grid, dim3(kTileThreads), smem, stream, a);
+}
+
+static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream) {
+  const int nph = g.taps.nphase;
+  if (KC == 32 && NC == 8 && nph == 1) launch_gather<32, 8, 1>(a, g, B, stream);
+  else if (KC == 32 && NC == 8 && nph == 4) launch_gather<32, 8, 4>(a, g, B, stream);
+  else if (KC == 8 && NC == 8 && nph == 1) launch_gather<8, 8, 1>(a, g, B, stream);
+  else if (KC == 8 && NC == 8 && nph == 4) launch_gather<8, 8, 4>(a, g, B, stream);
+  else if (KC == 8 && NC == 32 && nph == 1) launch_gather<8, 32, 1>(a, g, B, stream);
+  else if (KC == 8 && NC == 32 && nph == 4) launch_gather<8, 32, 4>(a, g, B, stream);
+  else SENAS_FAIL("no gather kernel for KC=%d NC=%d phases=%d", KC, NC, nph);
+  return 0;
+}
+
+struct Call {  // per-call resolved pointers
+  const senas_graph_desc_t *d;
+  Plan *p;
+  Bases bases;
+  float *saved, *scratch;
+  const float *in[2];
+  int64_t in_ld[2];
+  float *out;
+  int64_t out_ld;
+  void *stream;
+  int B;
+};
+static const float *state_ptr(const Call &c, int s, int64_t *ld) {
+  if (s < c.d->n_inputs) {
+    *ld = c.in_ld[s];
+    return c.in[s];
+  }
+  *ld = c.out_ld;
+  return c.out + (s - c.d->n_inputs) * 8;
+}
+
+static void conv_weight_strides(int op, int c_in, int T, int dir, int *ws_k, int *ws_n) {
+  // forward: k = ci, n = co;  dgrad: k = co, n = ci
+  const int s_ci = op == SENAS_OP_UP ? 8 * T : T, s_co = op == SENAS_OP_UP ? T : c_in * T;
+  if (dir == DIR_FWD) *ws_k = s_ci, *ws_n = s_co;
+  else *ws_k = s_co, *ws_n = s_ci;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_edge(const Call &c, int e, bool second_pass) {
+  const senas_edge_desc_t &ed = c.d->edge[e];
+  const EdgePlan &ep = c.p->edges[e];
+  const Plan &p = *c.p;
+  const int B = c.B, C = ed.c_in;
+  int64_t x_ld;
+  const float *x = state_ptr(c, ed.src, &x_ld);
+  for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+    const TermPlan &t = ep.t[k];
+    float *y = t.owns_y ? c.saved + t.y_off : nullptr;
+    float *part = t.has_y ? c.scratch + t.part_off : nullptr;
+    if (second_pass) {
+      if (t.kind != SENAS_KIND_DEPSEP) continue;
+      PwArgs a;
+      a.z = c.saved + t.z_off, a.hw = p.hw, a.y = y;
+      a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
+      a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
+      a.wpw = (const float *)ed.param[k][6], a.partials = part;
+      dim3 grid(cdiv(p.hw, 128), B);
+      if (C == 32) {
+        auto kern = pw_fwd_kernel<32>;
+        SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+      } else {
+        auto kern = pw_fwd_kernel<8>;
+        SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+      }
+      continue;
+    }
+    switch (t.kind) {
+      case SENAS_KIND_NONE:
+        break;
+      case SENAS_KIND_IDENTITY:
+      case SENAS_KIND_AVG_POOL:
+      case SENAS_KIND_UP_SAMPLE: {
+        AdapterArgs a;
+        a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.y = y, a.o_h = p.out_h, a.o_w = p.out_w;
+        a.w = (const float *)ed.param[k][0], a.partials = part;
+        if ((C != 8) != (a.w != nullptr)) SENAS_FAIL("edge %d candidate %d: 1x1 weight does not match c_in", e, k);
+        dim3 grid(cdiv(p.hw, 128), B);
+#define SENAS_AD_FWD(CC, KK)                                   \
+  {                                                            \
+    auto kern = adapter_fwd_kernel<CC, KK>;                    \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+  }
+        const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
+        if (C == 32 && kk == AD_IDENTITY) SENAS_AD_FWD(32, AD_IDENTITY)
+        else if (C == 32 && kk == AD_POOL) SENAS_AD_FWD(32, AD_POOL)
+        else if (C == 32 && kk == AD_UP) SENAS_AD_FWD(32, AD_UP)
+        else if (C == 8 && kk == AD_IDENTITY) SENAS_AD_FWD(8, AD_IDENTITY)
+        else SENAS_FAIL("edge %d candidate %d: adapter kind %d with c_in %d unsupported", e, k, t.kind, C);
+        break;
+      }
+      case SENAS_KIND_CONV:
+      case SENAS_KIND_SE_CONV: {
+        Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
+        GatherArgs a;
+        memset(&a, 0, sizeof(a));
+        a.src = x, a.src_ld = x_ld, a.src_h = ep.in_h, a.src_w = ep.in_w;
+        a.dst = y, a.dst_ld = 8, a.dst_h = p.out_h, a.dst_w = p.out_w;
+        a.base_h = geo.base_is_out ? p.out_h : ep.in_h, a.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+        a.si = geo.si, a.so = geo.so;
+        a.w = (const float *)ed.param[k][0], a.ws_t = 1;
+        conv_weight_strides(ed.op_type, C, t.k * t.k, DIR_FWD, &a.ws_k, &a.ws_n);
+        a.partials = part, a.taps = geo.taps;
+        if (launch_gather_any(a, geo, C, 8, B, c.stream)) return 1;
+        break;
+      }
+      case SENAS_KIND_DEPSEP: {
+        Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
+        DwArgs a;
+        a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.z = c.saved + t.z_off;
+        a.o_h = p.out_h, a.o_w = p.out_w;
+        a.base_h = geo.base_is_out ? p.out_h : ep.in_h, a.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+        a.si = geo.si, a.so = geo.so, a.w = (const float *)ed.param[k][0], a.partials = c.scratch + t.part1_off;
+        a.taps = geo.taps;
+        dim3 grid(t.nblk1, B);
+        if (C == 32) {
+          auto kern = dw_fwd_kernel<32>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        } else {
+          auto kern = dw_fwd_kernel<8>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        }
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
+static int check_common(senas_graph *g, int batch, const int32_t *ih, const int32_t *iw, Plan **p) {
+  if (!g) SENAS_FAIL("null graph");
+  return build_plan(g, batch, ih, iw, p);
+}
+
+static int check_cuda(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) SENAS_FAIL("%s: CUDA error %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) {
+  Plan *p;
+  if (!a) SENAS_FAIL("null args");
+  if (check_common(g, a->batch, a->in_h, a->in_w, &p)) return 1;
+  const senas_graph_desc_t &d = g->d;
+  if (!a->alpha || !a->out || !a->saved || !a->scratch) SENAS_FAIL("forward: null alpha/out/saved/scratch");
+  for (int i = 0; i < d.n_inputs; ++i)
+    if (!a->in[i] || (a->in_ld[i] & 3) || ((uintptr_t)a->in[i] & 15))
+      SENAS_FAIL("forward: input %d must be non-null, 16-byte aligned, ld multiple of 4", i);
+  if ((a->out_ld & 3) || ((uintptr_t)a->out & 15)) SENAS_FAIL("forward: out must be 16-byte aligned, ld multiple of 4");
+  Call c;
+  c.d = &d, c.p = p, c.B = a->batch, c.stream = a->stream;
+  c.saved = (float *)a->saved, c.scratch = (float *)a->scratch;
+  for (int i = 0; i < 2; ++i) c.in[i] = a->in[i], c.in_ld[i] = a->in_ld[i];
+  c.out = a->out, c.out_ld = a->out_ld;
+  memset(&c.bases, 0, sizeof(c.bases));
+  c.bases.p[SP_SAVED] = c.saved, c.bases.p[SP_SCRATCH] = c.scratch;
+  c.bases.p[SP_IN0] = (float *)a->in[0], c.bases.ld[SP_IN0] = a->in_ld[0];
+  c.bases.p[SP_IN1] = (float *)a->in[1], c.bases.ld[SP_IN1] = a->in_ld[1];
+  c.bases.p[SP_OUT] = a->out, c.bases.ld[SP_OUT] = a->out_ld;
+  for (int s = 0; s < d.n_nodes; ++s) {
+    for (int e = 0; e < d.n_edges; ++e)
+      if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
+    if (p->n_bnA[s]) {
+      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnA[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases,
+                   c.B, a->training);
+    }
+    if (p->n_bnB[s]) {
+      for (int e = 0; e < d.n_edges; ++e)
+        if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, true)) return 1;
+      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnB[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases,
+                   c.B, a->training);
+    }
+    const int thr = std::min(1024, ((c.B * 8 + 31) / 32) * 32);
+    SENAS_LAUNCH(node_coef_kernel, dim3(1), dim3(thr), 0, c.stream, (const NodeDesc *)p->d_nodes, s, c.bases, a->alpha,
+                 a->beta, c.B);
+    SENAS_LAUNCH(node_combine_kernel, dim3(cdiv(p->hw, 128), c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes,
+                 s, c.bases, d.node_relu);
+  }
+  return check_cuda("forward");
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdCall : Call {
+  const senas_bwd_args_t *a;
+  float *dstate[2 + SENAS_MAX_NODES];
+  int64_t dstate_ld[2 + SENAS_MAX_NODES];
+  bool touched[2 + SENAS_MAX_NODES];
+};
+
+static int backward_edge(BwdCall &c, int e) {
+  const senas_edge_desc_t &ed = c.d->edge[e];
+  const EdgePlan &ep = c.p->edges[e];
+  const Plan &p = *c.p;
+  const int B = c.B, C = ed.c_in, HW = p.hw;
+  int64_t x_ld;
+  const float *x = state_ptr(c, ed.src, &x_ld);
+  float *dx = c.dstate[ed.src];
+  const int64_t dx_ld = c.dstate_ld[ed.src];
+  const float *gm = c.scratch + p.nodes[ed.dst].gm_off;
+  float *tmp = c.scratch + p.tmp_off;
+  float *gp = c.a->grad_params;
+  for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+    const TermPlan &t = ep.t[k];
+    if (!t.has_y) continue;
+    int64_t y_ld = 8;
+    const float *y = t.owns_y ? c.saved + t.y_off : x;
+    if (!t.owns_y) y_ld = x_ld;
+    const float *cA = c.scratch + t.coef_off, *cB = cA + B * 8, *cC = cB + B * 8;
+    const int T = t.k * t.k;
+    switch (t.kind) {
+      case SENAS_KIND_IDENTITY:
+      case SENAS_KIND_AVG_POOL:
+      case SENAS_KIND_UP_SAMPLE: {
+        AdapterBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.gm = gm, a.y = y, a.y_ld = y_ld;
+        a.o_h = p.out_h, a.o_w = p.out_w, a.coefA = cA, a.coefB = cB, a.coefC = cC;
+        a.w = (const float *)ed.param[k][0], a.dx = dx, a.dx_ld = dx_ld, a.accumulate = c.touched[ed.src];
+        a.partials = tmp;
+        const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
+        const int in_px = ep.in_h * ep.in_w;
+        if (dx) {
+          dim3 grid(cdiv(in_px, 128), B);
+#define SENAS_AD_DX(CC, KK)                                    \
+  {                                                            \
+    auto kern = adapter_dx_kernel<CC, KK>;                     \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+  }
+          if (C == 32 && kk == AD_IDENTITY) SENAS_AD_DX(32, AD_IDENTITY)
+          else if (C == 32 && kk == AD_POOL) SENAS_AD_DX(32, AD_POOL)
+          else if (C == 32 && kk == AD_UP) SENAS_AD_DX(32, AD_UP)
+          else if (C == 8 && kk == AD_IDENTITY) SENAS_AD_DX(8, AD_IDENTITY)
+          else SENAS_FAIL("adapter dx: unsupported kind/c_in");
+          c.touched[ed.src] = true;
+        }
+        if (a.w != nullptr && ed.grad_off[k][0] >= 0) {
+          const int gpx = kk == AD_POOL ? HW : in_px;
+          dim3 grid(cdiv(gpx, 128), B);
+#define SENAS_AD_DW(CC, KK)                                    \
+  {                                                            \
+    auto kern = adapter_dw_kernel<CC, KK>;                     \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+  }
+          if (kk == AD_IDENTITY) SENAS_AD_DW(32, AD_IDENTITY)
+          else if (kk == AD_POOL) SENAS_AD_DW(32, AD_POOL)
+          else SENAS_AD_DW(32, AD_UP)
+          const int n = 8 * C;
+          SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
+                       (const float *)tmp, (int)(grid.x * B), n);
+        }
+        break;
+      }
+      case SENAS_KIND_CONV:
+      case SENAS_KIND_SE_CONV: {
+        if (dx) {
+          Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_DGRAD);
+          GatherArgs a;
+          memset(&a, 0, sizeof(a));
+          a.src = gm, a.src_ld = 8, a.src_h = p.out_h, a.src_w = p.out_w, a.src2 = y, a.src2_ld = y_ld;
+          a.coefA = cA, a.coefB = cB, a.coefC = cC;
+          a.dst = dx, a.dst_ld = dx_ld, a.dst_h = ep.in_h, a.dst_w = ep.in_w, a.accumulate = c.touched[ed.src];
+          a.base_h = geo.base_is_out ? p.out_h : ep.in_h, a.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+          a.si = geo.si, a.so = geo.so, a.w = (const float *)ed.param[k][0], a.ws_t = 1;
+          conv_weight_strides(ed.op_type, C, T, DIR_DGRAD, &a.ws_k, &a.ws_n);
+          a.partials = nullptr, a.taps = geo.taps;
+          if (launch_gather_any(a, geo, 8, C, B, c.stream)) return 1;
+          c.touched[ed.src] = true;
+        }
+        if (ed.grad_off[k][0] >= 0) {
+          Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
+          WgradArgs a;
+          memset(&a, 0, sizeof(a));
+          a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.gm = gm, a.y = y, a.y_ld = y_ld;
+          a.o_h = p.out_h, a.o_w = p.out_w, a.coefA = cA, a.coefB = cB, a.coefC = cC;
+          a.base_h = geo.base_is_out ? p.out_h : ep.in_h, a.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+          a.si = geo.si, a.so = geo.so, a.tiles_x = cdiv(a.base_w, kTileW), a.tiles_y = cdiv(a.base_h, kTileH);
+          a.batch = B, a.partials = tmp, a.taps = geo.taps;
+          const int items = a.tiles_x * a.tiles_y * B, nblk = std::min(items, kPersistBlocks);
+          const size_t smem = (size_t)2 * (kTileH * geo.so) * (kTileW * geo.so) * 16;
+#define SENAS_WGRAD(KC, TPT)                                                             \
+  {                                                                                      \
+    auto kern = conv_wgrad_kernel<KC, TPT>;                                              \
+    SENAS_LAUNCH(kern, dim3(nblk), dim3(KC * (T / TPT)), smem, c.stream, a);             \
+  }
+          if (C == 32 && t.k == 5) SENAS_WGRAD(32, 5)
+          else if (C == 32 && t.k == 3) SENAS_WGRAD(32, 3)
+          else if (C == 8) SENAS_WGRAD(8, 1)
+          else SENAS_FAIL("conv wgrad: unsupported c_in %d k %d", C, t.k);
+          int ws_ci, ws_co;
+          conv_weight_strides(ed.op_type, C, T, DIR_FWD, &ws_ci, &ws_co);
+          const int n = T * C * 8;
+          SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, (const float *)tmp, nblk, T, C,
+                       gp + ed.grad_off[k][0], 1, ws_ci, ws_co, geo.taps);
+        }
+        break;
+      }
+      case SENAS_KIND_DEPSEP: {
+        PwBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        float *coef1 = tmp + (int64_t)B * cdiv(HW, 128) * 10 * C;
+        a.gm = gm, a.y = y, a.z = c.saved + t.z_off, a.hw = HW, a.batch = B, a.coefA = cA, a.coefB = cB, a.coefC = cC;
+        a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
+        a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
+        a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1;
+        dim3 grid(cdiv(HW, 128), B);
+        if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
+          SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
+        if (C == 32) {
+          auto kern = pw_bwd_stats_kernel<32>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        } else {
+          auto kern = pw_bwd_stats_kernel<8>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        }
+        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)tmp, (int)(grid.x * B), C,
+                     (float)B * (float)HW, a.g1, a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2],
+                     gp + ed.grad_off[k][6]);
+        if (C == 32) {
+          auto kern = pw_bwd_dz_kernel<32>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a, c.a->training);
+        } else {
+          auto kern = pw_bwd_dz_kernel<8>;
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a, c.a->training);
+        }
+        DwBwdArgs w;
+        memset(&w, 0, sizeof(w));
+        w.dz = c.saved + t.z_off, w.z_h = p.out_h, w.z_w = p.out_w, w.x_h = ep.in_h, w.x_w = ep.in_w;
+        w.w = (const float *)ed.param[k][0];
+        if (dx) {
+          Geo geo = make_geo(t.k, 1, ed.op_type, DIR_DGRAD);
+          w.dx = dx, w.dx_ld = dx_ld, w.accumulate = c.touched[ed.src];
+          w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+          w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
+          dim3 g2(cdiv(w.base_h * w.base_w, 128 / (C / 4)), B);
+          if (C == 32) {
+            auto kern = dw_dx_kernel<32>;
+            SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
+          } else {
+            auto kern = dw_dx_kernel<8>;
+            SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
+          }
+          c.touched[ed.src] = true;
+        }
+        {
+          Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
+          w.x = x, w.x_ld = x_ld, w.partials = tmp, w.batch = B, w.chunk = 256;
+          w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
+          w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
+          dim3 g3(cdiv(w.base_h * w.base_w, w.chunk), B);
+          if (C == 32) {
+            auto kern = dw_wgrad_kernel<32>;
+            SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
+          } else {
+            auto kern = dw_wgrad_kernel<8>;
+            SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
+          }
+          const int n = C * T;
+          SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
+                       (const float *)tmp, (int)(g3.x * B), n);
+        }
+        break;
+      }
+      default:
+        break;
+    }
+  }
+  return 0;
+}
+
+extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a) {
+  Plan *p;
+  if (!a) SENAS_FAIL("null args");
+  if (check_common(g, a->batch, a->in_h, a->in_w, &p)) return 1;
+  const senas_graph_desc_t &d = g->d;
+  if (!a->alpha || !a->out || !a->grad_out || !a->saved || !a->scratch || !a->grad_alpha || !a->grad_params)
+    SENAS_FAIL("backward: null pointer argument");
+  if ((a->grad_out_ld & 3) || ((uintptr_t)a->grad_out & 15)) SENAS_FAIL("backward: grad_out alignment");
+  BwdCall c;
+  c.a = a, c.d = &d, c.p = p, c.B = a->batch, c.stream = a->stream;
+  c.saved = (float *)a->saved, c.scratch = (float *)a->scratch;
+  for (int i = 0; i < 2; ++i) c.in[i] = a->in[i], c.in_ld[i] = a->in_ld[i];
+  c.out = (float *)a->out, c.out_ld = a->out_ld;
+  memset(&c.bases, 0, sizeof(c.bases));
+  c.bases.p[SP_SAVED] = c.saved, c.bases.p[SP_SCRATCH] = c.scratch;
+  c.bases.p[SP_IN0] = (float *)a->in[0], c.bases.ld[SP_IN0] = a->in_ld[0];
+  c.bases.p[SP_IN1] = (float *)a->in[1], c.bases.ld[SP_IN1] = a->in_ld[1];
+  c.bases.p[SP_OUT] = (float *)a->out, c.bases.ld[SP_OUT] = a->out_ld;
+  c.bases.p[SP_GOUT] = (float *)a->grad_out, c.bases.ld[SP_GOUT] = a->grad_out_ld;
+  for (int i = 0; i < d.n_inputs; ++i) {
+    c.dstate[i] = a->grad_in[i], c.dstate_ld[i] = a->grad_in_ld[i], c.touched[i] = false;
+    if (a->grad_in[i] && ((a->grad_in_ld[i] & 3) || ((uintptr_t)a->grad_in[i] & 15))) SENAS_FAIL("backward: grad_in alignment");
+  }
+  for (int i = 0; i < d.n_nodes; ++i) {
+    const NodePlan &np = p->nodes[i];
+    c.dstate[d.n_inputs + i] = np.has_consumer ? c.scratch + np.dnode_off : nullptr;
+    c.dstate_ld[d.n_inputs + i] = 8, c.touched[d.n_inputs + i] = false;
+  }
+  cudaMemsetAsync(a->grad_params, 0, sizeof(float) * d.grad_floats, (cudaStream_t)c.stream);
+  const int64_t node_bytes = sizeof(float) * (int64_t)c.B * p->hw * 8;
+  for (int i = d.n_nodes - 1; i >= 0; --i) {
+    const NodePlan &np = p->nodes[i];
+    if (np.has_consumer && !c.touched[d.n_inputs + i])
+      cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
+    SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
+                 d.node_relu);
+    SENAS_LAUNCH(node_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
+                 a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
+    for (int e = 0; e < d.n_edges; ++e)
+      if (d.edge[e].dst == i && backward_edge(c, e)) return 1;
+  }
+  for (int i = 0; i < d.n_inputs; ++i)
+    if (a->grad_in[i] && !c.touched[i]) {
+      if (a->grad_in_ld[i] != d.edge[0].c_in) SENAS_FAIL("backward: cannot zero a strided grad_in");
+      cudaMemsetAsync(a->grad_in[i], 0, sizeof(float) * (int64_t)c.B * p->in_h[i] * p->in_w[i] * a->grad_in_ld[i],
+                      (cudaStream_t)c.stream);
+    }
+  return check_cuda("backward");
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *senas_version(void) { return "senas_b200 0.1 (sm_100a, fp32 exact path)"; }
+extern "C" const char *senas_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t senas_launch_count(void) { return g_launch_count; }
+
+extern "C" int senas_device_check(int device) {
+#ifdef SENAS_EMU
+  (void)device;
+  return 0;
+#else
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) SENAS_FAIL("cannot query CUDA device %d", device);
+  if (prop.major != 10) SENAS_FAIL("device %d is sm_%d%d; libsenas_b200 is built for sm_100a only", device, prop.major, prop.minor);
+  return 0;
+#endif
+}
+
+extern "C" int senas_graph_create(const senas_graph_desc_t *desc, senas_graph_t **out) {
+  if (!desc || !out) SENAS_FAIL("null argument");
+  const senas_graph_desc_t &d = *desc;
+  if (d.n_inputs < 1 || d.n_inputs > 2) SENAS_FAIL("n_inputs must be 1 or 2");
+  if (d.n_nodes < 1 || d.n_nodes > SENAS_MAX_NODES) SENAS_FAIL("n_nodes out of range");
+  if (d.n_edges < 1 || d.n_edges > SENAS_MAX_EDGES) SENAS_FAIL("n_edges out of range");
+  if (d.c_out != 8) SENAS_FAIL("only c_out == 8 (Cell.k = 4 with 32 channels) is supported, got %d", d.c_out);
+  for (int e = 0; e < d.n_edges; ++e) {
+    const senas_edge_desc_t &ed = d.edge[e];
+    if (ed.c_in != 8 && ed.c_in != 32) SENAS_FAIL("edge %d: c_in %d unsupported (8 or 32)", e, ed.c_in);
+    if (ed.op_type < SENAS_OP_UP || ed.op_type > SENAS_OP_NORM) SENAS_FAIL("edge %d: bad op_type", e);
+    if (ed.src < 0 || ed.src >= d.n_inputs + d.n_nodes || ed.dst < 0 || ed.dst >= d.n_nodes) SENAS_FAIL("edge %d: bad src/dst", e);
+    if (ed.src >= d.n_inputs && ed.src - d.n_inputs >= ed.dst) SENAS_FAIL("edge %d: node edges must go forward", e);
+    if (ed.src >= d.n_inputs && (ed.op_type != SENAS_OP_NORM || ed.c_in != 8)) SENAS_FAIL("edge %d: node edges are NORM 8->8", e);
+    for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+      const int kind = ed.kind[k];
+      if ((kind == SENAS_KIND_CONV || kind == SENAS_KIND_SE_CONV || kind == SENAS_KIND_DEPSEP)) {
+        if (ed.ksize[k] != 3 && ed.ksize[k] != 5) SENAS_FAIL("edge %d candidate %d: kernel size %d", e, k, ed.ksize[k]);
+        if (!ed.param[k][0]) SENAS_FAIL("edge %d candidate %d: missing conv weight", e, k);
+      }
+      if (kind == SENAS_KIND_DEPSEP && !ed.param[k][6]) SENAS_FAIL("edge %d candidate %d: missing pointwise weight", e, k);
+      if (kind == SENAS_KIND_AVG_POOL && ed.op_type != SENAS_OP_DOWN) SENAS_FAIL("avg_pool is a DOWN candidate");
+      if (kind == SENAS_KIND_UP_SAMPLE && ed.op_type != SENAS_OP_UP) SENAS_FAIL("up_sample is an UP candidate");
+    }
+  }
+  senas_graph *g = new senas_graph();
+  g->d = d;
+  *out = g;
+  return 0;
+}
+
+extern "C" void senas_graph_destroy(senas_graph_t *g) {
+  if (!g) return;
+  for (auto &kv : g->plans) {
+    Plan *p = kv.second;
+    for (auto q : p->d_bnA) if (q) dev_free(q);
+    for (auto q : p->d_bnB) if (q) dev_free(q);
+    if (p->d_nodes) dev_free(p->d_nodes);
+    delete p;
+  }
+  delete g;
+}
+
+extern "C" int senas_graph_plan(senas_graph_t *g, int32_t batch, const int32_t in_h[2], const int32_t in_w[2],
+                                senas_plan_info_t *info) {
+  Plan *p;
+  if (!info) SENAS_FAIL("null info");
+  if (check_common(g, batch, in_h, in_w, &p)) return 1;
+  info->out_h = p->out_h, info->out_w = p->out_w;
+  info->saved_bytes = p->saved_floats * 4 + 64, info->scratch_bytes = p->scratch_floats * 4 + 64;
+  return 0;
+}

@@ -1,0 +1,1254 @@
+// kernels.cuh -- fp32 (exact-mode) device code of the SENAS MixedOp / Cell hot path.
+//
+// Layout: activations NHWC fp32; `ld` = floats between consecutive pixels.  Every candidate of a
+// MixedOp (utils/operations.py:8-21) produces its *pre-BatchNorm* 8-channel output y_k once, with
+// the per-channel batch statistics reduced in the producer's epilogue (two-stage, fixed order, no
+// float atomics => bit-reproducible).  The BatchNorm affine, the SE gate, the softmax(alpha)
+// weight, the edge beta, the node sum, the ReLU and the concat are then ONE streaming kernel per
+// node (node_combine_kernel) that writes the node's channel slice of the concat buffer; no
+// post-BN / per-candidate weighted tensor ever reaches HBM.  Backward mirrors it: one statistics
+// sweep per node (S1 = sum g, S2_k = sum g*yhat_k, which also yield d alpha and d beta), then the
+// data/weight gradient kernels read dy_k = A*g + B*y_k + C on the fly.
+#pragma once
+#include "platform.h"
+
+#define SENAS_EPS 1e-5f
+#define SENAS_MOMENTUM 0.1f
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+SENAS_DEVFN float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+SENAS_DEVFN void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+SENAS_DEVFN float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+SENAS_DEVFN float warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// Sum NV per-thread values over the whole block (fixed order) and store them to dst[0..NV).
+// Must be called by every thread of the block.  blockDim.x <= 1024, multiple of 32.
+template <int NV>
+SENAS_DEVFN void block_sum_store(const float *v, float *dst) {
+  __shared__ float s_part[32][NV];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  __syncthreads();  // protect s_part against a previous call
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float r = warp_sum(v[i]);
+    if (lane == 0) s_part[warp][i] = r;
+  }
+  __syncthreads();
+  if (tid < NV) {
+    float r = 0.f;
+    for (int w = 0; w < nwarp; ++w) r += s_part[w][tid];
+    dst[tid] = r;
+  }
+}
+
+// Tap table of one convolution variant expressed on a "base grid" (see graph.cu make_taps()):
+//   gathered pixel = base * si + (dy, dx)     produced pixel = base * so + phase
+struct TapTable {
+  int32_t n, nphase;
+  int32_t pstart[5];
+  int32_t min_dy, max_dy, min_dx, max_dx;
+  int8_t dy[25], dx[25], widx[25], phase[25];
+};
+
+// ------------------------------------------------------------------------------------------------
+// gather-MAC: dense / dilated / strided / transposed convolution forward AND data gradient.
+//   dst[b*so+ph][n] (+)= sum_{t in ph} sum_k src[b*si + d_t][k] * W[t][k][n]
+// forward: src = x (KC = c_in), dst = y (NC = 8), statistics epilogue.
+// dgrad  : src = dy = A*gm + B*y + C (KC = 8), dst = dx (NC = c_in), optional accumulate.
+// One thread per base pixel of an 8x16 tile; gathered tile + weights staged in shared memory in
+// 8-channel chunks.
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+  const float *src;
+  int64_t src_ld;
+  int32_t src_h, src_w;
+  const float *src2;  // non-null => affine dy mode (src = gm with ld 8, src2 = y)
+  int64_t src2_ld;
+  const float *coefA, *coefB, *coefC;  // [B][8]
+  float *dst;
+  int64_t dst_ld;
+  int32_t dst_h, dst_w;
+  int32_t accumulate;
+  int32_t base_h, base_w, si, so, tiles_x;
+  const float *w;
+  int32_t ws_t, ws_k, ws_n;
+  float *partials;  // [B][tiles][16] or null
+  TapTable taps;
+};
+
+constexpr int kTileH = 8, kTileW = 16, kTileThreads = 128;
+
+template <int KC, int NC, int NPH>
+__global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) {
+  constexpr int NCH = KC / 8;
+  constexpr bool kPhaseOuter = (NCH == 1);  // single chunk: one live accumulator set
+  constexpr int NLIVE = kPhaseOuter ? 1 : NPH;
+  SENAS_DYN_SMEM(float4, smem);
+  __shared__ float s_coef[24];
+  const int tid = threadIdx.x, n = blockIdx.y, tile = blockIdx.x;
+  const int by0 = (tile / a.tiles_x) * kTileH, bx0 = (tile % a.tiles_x) * kTileW;
+  const int ty = tid / kTileW, tx = tid % kTileW;
+  const int R = (kTileH - 1) * a.si + (a.taps.max_dy - a.taps.min_dy) + 1;
+  const int Cc = (kTileW - 1) * a.si + (a.taps.max_dx - a.taps.min_dx) + 1;
+  const int npx = R * Cc;
+  float4 *s_lo = smem, *s_hi = smem + npx;
+  float *s_w = reinterpret_cast<float *>(smem + 2 * npx);
+  const bool affine = a.src2 != nullptr;
+  if (affine) {
+    if (tid < 24) {
+      const float *t = tid < 8 ? a.coefA : (tid < 16 ? a.coefB : a.coefC);
+      s_coef[tid] = t[n * 8 + (tid & 7)];
+    }
+    __syncthreads();
+  }
+  float acc[NLIVE][NC];
+#pragma unroll
+  for (int p = 0; p < NLIVE; ++p)
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[p][i] = 0.f;
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+
+  const int gy0 = by0 * a.si + a.taps.min_dy, gx0 = bx0 * a.si + a.taps.min_dx;
+  const float *srcn = a.src + (int64_t)n * a.src_h * a.src_w * a.src_ld;
+  const float *src2n = affine ? a.src2 + (int64_t)n * a.src_h * a.src_w * a.src2_ld : nullptr;
+  const int by = by0 + ty, bx = bx0 + tx;
+  const bool base_ok = by < a.base_h && bx < a.base_w;
+  float *dstn = a.dst + (int64_t)n * a.dst_h * a.dst_w * a.dst_ld;
+
+  auto epilogue = [&](int ph, float *r) {
+    const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+    if (base_ok && oy < a.dst_h && ox < a.dst_w) {
+      float *o = dstn + ((int64_t)oy * a.dst_w + ox) * a.dst_ld;
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 v = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        if (a.accumulate) {
+          float4 u = ld4(o + j);
+          v.x += u.x, v.y += u.y, v.z += u.z, v.w += u.w;
+        }
+        st4(o + j, v);
+      }
+      if (NC == 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_s[j] += r[j], st_q[j] += r[j] * r[j];
+      }
+    }
+  };
+
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch > 0) __syncthreads();
+    for (int i = tid; i < npx; i += kTileThreads) {
+      const int r = i / Cc, c = i - r * Cc;
+      const int gy = gy0 + r, gx = gx0 + c;
+      float4 lo = f4zero(), hi = f4zero();
+      if (gy >= 0 && gy < a.src_h && gx >= 0 && gx < a.src_w) {
+        const int64_t pix = (int64_t)gy * a.src_w + gx;
+        const float *p = srcn + pix * a.src_ld + ch * 8;
+        lo = ld4(p), hi = ld4(p + 4);
+        if (affine) {
+          const float *q = src2n + pix * a.src2_ld;
+          const float4 ylo = ld4(q), yhi = ld4(q + 4);
+          lo.x = s_coef[0] * lo.x + s_coef[8] * ylo.x + s_coef[16];
+          lo.y = s_coef[1] * lo.y + s_coef[9] * ylo.y + s_coef[17];
+          lo.z = s_coef[2] * lo.z + s_coef[10] * ylo.z + s_coef[18];
+          lo.w = s_coef[3] * lo.w + s_coef[11] * ylo.w + s_coef[19];
+          hi.x = s_coef[4] * hi.x + s_coef[12] * yhi.x + s_coef[20];
+          hi.y = s_coef[5] * hi.y + s_coef[13] * yhi.y + s_coef[21];
+          hi.z = s_coef[6] * hi.z + s_coef[14] * yhi.z + s_coef[22];
+          hi.w = s_coef[7] * hi.w + s_coef[15] * yhi.w + s_coef[23];
+        }
+      }
+      s_lo[i] = lo, s_hi[i] = hi;
+    }
+    for (int i = tid; i < a.taps.n * 8 * NC; i += kTileThreads) {
+      const int nn = i % NC, kk = (i / NC) & 7, t = i / (NC * 8);
+      s_w[i] = __ldg(a.w + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)(ch * 8 + kk) * a.ws_k + (int64_t)nn * a.ws_n);
+    }
+    __syncthreads();
+    for (int ph = 0; ph < NPH; ++ph) {
+      float *r = acc[kPhaseOuter ? 0 : ph];
+      if (kPhaseOuter && NPH > 1) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) r[i] = 0.f;
+      }
+      for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
+        const int idx = (ty * a.si + a.taps.dy[t] - a.taps.min_dy) * Cc + (tx * a.si + a.taps.dx[t] - a.taps.min_dx);
+        const float4 lo = s_lo[idx], hi = s_hi[idx];
+        const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const float *wt = s_w + t * 8 * NC;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+          for (int j = 0; j < NC; j += 4) {
+            const float4 w4 = ld4(wt + kk * NC + j);
+            r[j] = fmaf(xv[kk], w4.x, r[j]);
+            r[j + 1] = fmaf(xv[kk], w4.y, r[j + 1]);
+            r[j + 2] = fmaf(xv[kk], w4.z, r[j + 2]);
+            r[j + 3] = fmaf(xv[kk], w4.w, r[j + 3]);
+          }
+        }
+      }
+      if (kPhaseOuter) epilogue(ph, r);
+    }
+  }
+  if (!kPhaseOuter) {
+#pragma unroll
+    for (int ph = 0; ph < NPH; ++ph) epilogue(ph, acc[ph]);
+  }
+  if (a.partials != nullptr) {  // uniform
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = st_s[j], v[8 + j] = st_q[j];
+    block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// convolution weight gradient: dW[t][ci][co] = sum_b x[b*si + d_t][ci] * dy[b*so + phase_t][co]
+// thread = (ci, tap group); x read straight from global/L1 (32 consecutive ci = one 128 B line),
+// dy = A*gm + B*y + C staged per tile in shared memory.  Persistent blocks loop over (sample, tile)
+// and write one partial per block; wgrad_reduce_kernel sums them in fixed order.
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float *x;
+  int64_t x_ld;
+  int32_t x_h, x_w;
+  const float *gm, *y;
+  int64_t y_ld;
+  int32_t o_h, o_w;
+  const float *coefA, *coefB, *coefC;
+  int32_t base_h, base_w, si, so, tiles_x, tiles_y, batch;
+  float *partials;  // [gridDim.x][T][KC][8]
+  TapTable taps;
+};
+
+template <int KC, int TPT>
+__global__ void conv_wgrad_kernel(WgradArgs a) {
+  SENAS_DYN_SMEM(float4, smem);  // dy tile: 2 planes of (kTileH*so)*(kTileW*so) float4
+  const int tid = threadIdx.x, ci = tid % KC, tg = tid / KC;
+  const int oth = kTileH * a.so, otw = kTileW * a.so, onpx = oth * otw;
+  float4 *s_lo = smem, *s_hi = smem + onpx;
+  float acc[TPT][8];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  const int tiles = a.tiles_x * a.tiles_y, total = tiles * a.batch;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int n = item / tiles, tile = item - n * tiles;
+    const int by0 = (tile / a.tiles_x) * kTileH, bx0 = (tile % a.tiles_x) * kTileW;
+    const float *gmn = a.gm + (int64_t)n * a.o_h * a.o_w * 8;
+    const float *yn = a.y + (int64_t)n * a.o_h * a.o_w * a.y_ld;
+    const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld;
+    __syncthreads();
+    for (int i = tid; i < onpx; i += blockDim.x) {
+      const int r = i / otw, c = i - r * otw;
+      const int oy = by0 * a.so + r, ox = bx0 * a.so + c;
+      float4 lo = f4zero(), hi = f4zero();
+      if (oy < a.o_h && ox < a.o_w) {
+        const int64_t pix = (int64_t)oy * a.o_w + ox;
+        const float4 glo = ld4(gmn + pix * 8), ghi = ld4(gmn + pix * 8 + 4);
+        const float4 ylo = ld4(yn + pix * a.y_ld), yhi = ld4(yn + pix * a.y_ld + 4);
+        const float *A = a.coefA + n * 8, *B = a.coefB + n * 8, *C = a.coefC + n * 8;
+        lo.x = A[0] * glo.x + B[0] * ylo.x + C[0];
+        lo.y = A[1] * glo.y + B[1] * ylo.y + C[1];
+        lo.z = A[2] * glo.z + B[2] * ylo.z + C[2];
+        lo.w = A[3] * glo.w + B[3] * ylo.w + C[3];
+        hi.x = A[4] * ghi.x + B[4] * yhi.x + C[4];
+        hi.y = A[5] * ghi.y + B[5] * yhi.y + C[5];
+        hi.z = A[6] * ghi.z + B[6] * yhi.z + C[6];
+        hi.w = A[7] * ghi.w + B[7] * yhi.w + C[7];
+      }
+      s_lo[i] = lo, s_hi[i] = hi;
+    }
+    __syncthreads();
+    for (int b = 0; b < kTileH * kTileW; ++b) {
+      const int ty = b / kTileW, tx = b - ty * kTileW;
+      const int by = by0 + ty, bx = bx0 + tx;
+      if (by >= a.base_h || bx >= a.base_w) continue;
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {
+        const int t = tg * TPT + j;
+        const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t];
+        if (iy < 0 || iy >= a.x_h || ix < 0 || ix >= a.x_w) continue;
+        const float xv = __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld + ci);
+        const int ph = a.taps.phase[t];
+        const int idx = (ty * a.so + (ph >> 1)) * otw + tx * a.so + (ph & 1);
+        const float4 lo = s_lo[idx], hi = s_hi[idx];
+        acc[j][0] = fmaf(xv, lo.x, acc[j][0]);
+        acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
+        acc[j][2] = fmaf(xv, lo.z, acc[j][2]);
+        acc[j][3] = fmaf(xv, lo.w, acc[j][3]);
+        acc[j][4] = fmaf(xv, hi.x, acc[j][4]);
+        acc[j][5] = fmaf(xv, hi.y, acc[j][5]);
+        acc[j][6] = fmaf(xv, hi.z, acc[j][6]);
+        acc[j][7] = fmaf(xv, hi.w, acc[j][7]);
+      }
+    }
+  }
+  float *out = a.partials + (int64_t)blockIdx.x * a.taps.n * KC * 8;
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    const int t = tg * TPT + j;
+    float *o = out + ((int64_t)t * KC + ci) * 8;
+    st4(o, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+    st4(o + 4, make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]));
+  }
+}
+
+// dst[widx_t*ws_t + ci*ws_k + co*ws_n] = sum_blk partials[blk][t][ci][co]
+__global__ void wgrad_reduce_kernel(const float *partials, int nblk, int T, int KC, float *dst, int ws_t, int ws_k,
+                                    int ws_n, TapTable taps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, total = T * KC * 8;
+  if (i >= total) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partials[(int64_t)b * total + i];
+  const int co = i & 7, ci = (i >> 3) % KC, t = i / (8 * KC);
+  dst[(int64_t)taps.widx[t] * ws_t + (int64_t)ci * ws_k + (int64_t)co * ws_n] = s;
+}
+
+// dst[i] = sum_blk src[blk*n + i]
+__global__ void reduce_partials_kernel(float *dst, const float *src, int nblk, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += src[(int64_t)b * n + i];
+  dst[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise convolution (dep_sep_conv_*, first half): z = dw(x), statistics of z.
+// thread = (base pixel, channel quad); x through L1 (a pixel's C floats are one or a quarter line).
+// ------------------------------------------------------------------------------------------------
+struct DwArgs {
+  const float *x;
+  int64_t x_ld;
+  int32_t x_h, x_w;
+  float *z;  // [B][o_h][o_w][C]
+  int32_t o_h, o_w, base_h, base_w, si, so;
+  const float *w;   // [C][T] (PyTorch [C,1,k,k])
+  float *partials;  // [B][gridDim.x][2C]
+  TapTable taps;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) dw_fwd_kernel(DwArgs a) {
+  constexpr int Q = C / 4, PPB = 128 / Q;
+  __shared__ float s_w[25 * C];
+  __shared__ float s_red[128][8];
+  const int tid = threadIdx.x, n = blockIdx.y, pl = tid / Q, q = tid % Q;
+  const int T = a.taps.n;
+  for (int i = tid; i < T * C; i += 128) {
+    const int c = i % C, t = i / C;
+    s_w[i] = __ldg(a.w + c * T + a.taps.widx[t]);
+  }
+  __syncthreads();
+  const int b = blockIdx.x * PPB + pl;
+  const bool ok = b < a.base_h * a.base_w;
+  const int by = ok ? b / a.base_w : 0, bx = ok ? b - by * a.base_w : 0;
+  const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld + q * 4;
+  float *zn = a.z + (int64_t)n * a.o_h * a.o_w * C + q * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ok) {
+    for (int ph = 0; ph < a.taps.nphase; ++ph) {
+      float4 r = f4zero();
+      for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
+        const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t];
+        if (iy < 0 || iy >= a.x_h || ix < 0 || ix >= a.x_w) continue;
+        const float4 xv = ld4(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld);
+        const float4 wv = ld4(s_w + t * C + q * 4);
+        r.x = fmaf(xv.x, wv.x, r.x), r.y = fmaf(xv.y, wv.y, r.y), r.z = fmaf(xv.z, wv.z, r.z), r.w = fmaf(xv.w, wv.w, r.w);
+      }
+      const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+      if (oy < a.o_h && ox < a.o_w) {
+        st4(zn + ((int64_t)oy * a.o_w + ox) * C, r);
+        s[0] += r.x, s[1] += r.y, s[2] += r.z, s[3] += r.w;
+        sq[0] += r.x * r.x, sq[1] += r.y * r.y, sq[2] += r.z * r.z, sq[3] += r.w * r.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s_red[tid][j] = s[j], s_red[tid][4 + j] = sq[j];
+  __syncthreads();
+  if (tid < 2 * C) {
+    const int c = tid % C, which = tid / C;
+    float r = 0.f;
+    for (int p = 0; p < PPB; ++p) r += s_red[p * Q + c / 4][which * 4 + (c & 3)];
+    a.partials[((int64_t)n * gridDim.x + blockIdx.x) * 2 * C + tid] = r;
+  }
+}
+
+// pointwise half: y = W_pw . relu(BN1(z)), statistics of y.  thread = pixel.
+struct PwArgs {
+  const float *z;
+  int32_t hw;
+  float *y;  // [B][hw][8]
+  const float *mean1, *istd1, *g1, *b1;
+  const float *wpw;  // [8][C]
+  float *partials;   // [B][gridDim.x][16]
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) pw_fwd_kernel(PwArgs a) {
+  __shared__ float s_sc[C], s_sh[C];
+  __shared__ float s_w[C * 8];  // [ci][co]
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (tid < C) {
+    const float sc = a.g1[tid] * a.istd1[tid];
+    s_sc[tid] = sc, s_sh[tid] = a.b1[tid] - a.mean1[tid] * sc;
+  }
+  for (int i = tid; i < C * 8; i += 128) s_w[i] = __ldg(a.wpw + (i & 7) * C + (i >> 3));
+  __syncthreads();
+  const int p = blockIdx.x * 128 + tid;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (p < a.hw) {
+    const float *zp = a.z + ((int64_t)n * a.hw + p) * C;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c4 = 0; c4 < C; c4 += 4) {
+      const float4 zv = ld4(zp + c4);
+      const float r[4] = {fmaxf(fmaf(zv.x, s_sc[c4], s_sh[c4]), 0.f), fmaxf(fmaf(zv.y, s_sc[c4 + 1], s_sh[c4 + 1]), 0.f),
+                          fmaxf(fmaf(zv.z, s_sc[c4 + 2], s_sh[c4 + 2]), 0.f),
+                          fmaxf(fmaf(zv.w, s_sc[c4 + 3], s_sh[c4 + 3]), 0.f)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w0 = ld4(s_w + (c4 + k) * 8), w1 = ld4(s_w + (c4 + k) * 8 + 4);
+        acc[0] = fmaf(r[k], w0.x, acc[0]), acc[1] = fmaf(r[k], w0.y, acc[1]);
+        acc[2] = fmaf(r[k], w0.z, acc[2]), acc[3] = fmaf(r[k], w0.w, acc[3]);
+        acc[4] = fmaf(r[k], w1.x, acc[4]), acc[5] = fmaf(r[k], w1.y, acc[5]);
+        acc[6] = fmaf(r[k], w1.z, acc[6]), acc[7] = fmaf(r[k], w1.w, acc[7]);
+      }
+    }
+    float *yp = a.y + ((int64_t)n * a.hw + p) * 8;
+    st4(yp, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(yp + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j], v[8 + j] = acc[j] * acc[j];
+  }
+  block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// adapters (AdapterBlock, operations.py:167-183): identity / avg_pool / up_sample -> 1x1 -> y
+// ------------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=False: src = max((o + 0.5)/2 - 0.5, 0)
+SENAS_DEVFN void up_src(int o, int n_in, int &i0, int &i1, float &lam) {
+  float s = (o + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  lam = s - (float)i0;
+}
+// weight with which input index i contributes to bilinear output o (0 if it does not)
+SENAS_DEVFN float up_weight(int o, int i, int n_in) {
+  if (o < 0 || o >= 2 * n_in) return 0.f;
+  int i0, i1;
+  float lam;
+  up_src(o, n_in, i0, i1, lam);
+  float w = 0.f;
+  if (i0 == i) w += 1.f - lam;
+  if (i1 == i) w += lam;
+  return w;
+}
+// AvgPool2d(3, stride 2, pad 1, count_include_pad=False): number of valid taps along one axis
+SENAS_DEVFN int pool_cnt(int o, int n_in) {
+  const int lo = 2 * o - 1 < 0 ? 0 : 2 * o - 1, hi = 2 * o + 1 > n_in - 1 ? n_in - 1 : 2 * o + 1;
+  return hi - lo + 1;
+}
+
+enum { AD_IDENTITY = 1, AD_POOL = 2, AD_UP = 3 };
+
+struct AdapterArgs {
+  const float *x;
+  int64_t x_ld;
+  int32_t x_h, x_w;
+  float *y;  // [B][o_h][o_w][8]; null for stats-only (identity 8->8)
+  int32_t o_h, o_w;
+  const float *w;  // [8][C] 1x1 weight, null when C == 8 identity
+  float *partials;
+};
+
+// 32-channel (or 8-channel) "adapter input" a[c] at output pixel (oy, ox)
+template <int C, int KIND>
+SENAS_DEVFN void adapter_input(const float *xn, int64_t x_ld, int x_h, int x_w, int oy, int ox, float *av) {
+  if (KIND == AD_IDENTITY) {
+    const float *p = xn + ((int64_t)oy * x_w + ox) * x_ld;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 v = ld4(p + c);
+      av[c] = v.x, av[c + 1] = v.y, av[c + 2] = v.z, av[c + 3] = v.w;
+    }
+  } else if (KIND == AD_POOL) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) av[c] = 0.f;
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+        if (iy < 0 || iy >= x_h || ix < 0 || ix >= x_w) continue;
+        ++cnt;
+        const float *p = xn + ((int64_t)iy * x_w + ix) * x_ld;
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+          const float4 v = ld4(p + c);
+          av[c] += v.x, av[c + 1] += v.y, av[c + 2] += v.z, av[c + 3] += v.w;
+        }
+      }
+    const float inv = 1.f / (float)cnt;
+#pragma unroll
+    for (int c = 0; c < C; ++c) av[c] *= inv;
+  } else {  // AD_UP
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up_src(oy, x_h, y0, y1, ly);
+    up_src(ox, x_w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float *p00 = xn + ((int64_t)y0 * x_w + x0) * x_ld, *p01 = xn + ((int64_t)y0 * x_w + x1) * x_ld;
+    const float *p10 = xn + ((int64_t)y1 * x_w + x0) * x_ld, *p11 = xn + ((int64_t)y1 * x_w + x1) * x_ld;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 a = ld4(p00 + c), b = ld4(p01 + c), d = ld4(p10 + c), e = ld4(p11 + c);
+      av[c] = w00 * a.x + w01 * b.x + w10 * d.x + w11 * e.x;
+      av[c + 1] = w00 * a.y + w01 * b.y + w10 * d.y + w11 * e.y;
+      av[c + 2] = w00 * a.z + w01 * b.z + w10 * d.z + w11 * e.z;
+      av[c + 3] = w00 * a.w + w01 * b.w + w10 * d.w + w11 * e.w;
+    }
+  }
+}
+
+template <int C, int KIND>
+__global__ void __launch_bounds__(128) adapter_fwd_kernel(AdapterArgs a) {
+  __shared__ float s_w[C * 8];  // [ci][co]
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (a.w != nullptr)
+    for (int i = tid; i < C * 8; i += 128) s_w[i] = __ldg(a.w + (i & 7) * C + (i >> 3));
+  __syncthreads();
+  const int p = blockIdx.x * 128 + tid, hw = a.o_h * a.o_w;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (p < hw) {
+    const int oy = p / a.o_w, ox = p - oy * a.o_w;
+    float av[C];
+    adapter_input<C, KIND>(a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld, a.x_ld, a.x_h, a.x_w, oy, ox, av);
+    float acc[8];
+    if (a.w != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float4 w0 = ld4(s_w + c * 8), w1 = ld4(s_w + c * 8 + 4);
+        acc[0] = fmaf(av[c], w0.x, acc[0]), acc[1] = fmaf(av[c], w0.y, acc[1]);
+        acc[2] = fmaf(av[c], w0.z, acc[2]), acc[3] = fmaf(av[c], w0.w, acc[3]);
+        acc[4] = fmaf(av[c], w1.x, acc[4]), acc[5] = fmaf(av[c], w1.y, acc[5]);
+        acc[6] = fmaf(av[c], w1.z, acc[6]), acc[7] = fmaf(av[c], w1.w, acc[7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = av[j];  // C == 8 identity: y aliases x
+    }
+    if (a.y != nullptr) {
+      float *yp = a.y + ((int64_t)n * hw + p) * 8;
+      st4(yp, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      st4(yp + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j], v[8 + j] = acc[j] * acc[j];
+  }
+  block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+}
+
+// adapter backward, data gradient.  thread = input pixel: s[8] = gather of dy (kind specific), then
+// dx[ci] (+)= sum_co s[co] * W[co][ci]  (or dx (+)= s when there is no 1x1).
+struct AdapterBwdArgs {
+  const float *x;  // forward input (dW only)
+  int64_t x_ld;
+  int32_t x_h, x_w;
+  const float *gm, *y;  // dy = A*gm + B*y + C on the output grid
+  int64_t y_ld;
+  int32_t o_h, o_w;
+  const float *coefA, *coefB, *coefC;
+  const float *w;  // [8][C] or null
+  float *dx;
+  int64_t dx_ld;
+  int32_t accumulate;
+  float *partials;  // dW partials [B*gridDim.x][8*C]
+};
+
+SENAS_DEVFN void load_dy8(const AdapterBwdArgs &a, int n, int oy, int ox, float *d) {
+  const int64_t pix = ((int64_t)n * a.o_h + oy) * a.o_w + ox;
+  const float4 glo = ld4(a.gm + pix * 8), ghi = ld4(a.gm + pix * 8 + 4);
+  const float4 ylo = ld4(a.y + pix * a.y_ld), yhi = ld4(a.y + pix * a.y_ld + 4);
+  const float *A = a.coefA + n * 8, *B = a.coefB + n * 8, *C = a.coefC + n * 8;
+  d[0] = A[0] * glo.x + B[0] * ylo.x + C[0], d[1] = A[1] * glo.y + B[1] * ylo.y + C[1];
+  d[2] = A[2] * glo.z + B[2] * ylo.z + C[2], d[3] = A[3] * glo.w + B[3] * ylo.w + C[3];
+  d[4] = A[4] * ghi.x + B[4] * yhi.x + C[4], d[5] = A[5] * ghi.y + B[5] * yhi.y + C[5];
+  d[6] = A[6] * ghi.z + B[6] * yhi.z + C[6], d[7] = A[7] * ghi.w + B[7] * yhi.w + C[7];
+}
+
+// s[8] = d(1x1 output) gathered onto input pixel (iy, ix)
+template <int KIND>
+SENAS_DEVFN void adapter_gather_dy(const AdapterBwdArgs &a, int n, int iy, int ix, float *s) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (KIND == AD_IDENTITY) {
+    load_dy8(a, n, iy, ix, s);
+  } else if (KIND == AD_POOL) {
+    // output windows containing i: o in [ceil((i-1)/2), floor((i+1)/2)]
+    for (int oy = iy >> 1; oy <= (iy + 1) >> 1; ++oy) {
+      if (oy >= a.o_h) continue;
+      for (int ox = ix >> 1; ox <= (ix + 1) >> 1; ++ox) {
+        if (ox >= a.o_w) continue;
+        float d[8];
+        load_dy8(a, n, oy, ox, d);
+        const float inv = 1.f / (float)(pool_cnt(oy, a.x_h) * pool_cnt(ox, a.x_w));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += d[j] * inv;
+      }
+    }
+  } else {  // AD_UP: outputs 2i-1 .. 2i+2 per axis
+    for (int oy = 2 * iy - 1; oy <= 2 * iy + 2; ++oy) {
+      const float wy = up_weight(oy, iy, a.x_h);
+      if (wy == 0.f) continue;
+      for (int ox = 2 * ix - 1; ox <= 2 * ix + 2; ++ox) {
+        const float wx = up_weight(ox, ix, a.x_w);
+        if (wx == 0.f) continue;
+        float d[8];
+        load_dy8(a, n, oy, ox, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += d[j] * (wy * wx);
+      }
+    }
+  }
+}
+
+template <int C, int KIND>
+__global__ void __launch_bounds__(128) adapter_dx_kernel(AdapterBwdArgs a) {
+  __shared__ float s_w[C * 8];  // [co][ci]
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (a.w != nullptr)
+    for (int i = tid; i < C * 8; i += 128) s_w[i] = __ldg(a.w + i);
+  __syncthreads();
+  const int p = blockIdx.x * 128 + tid;
+  if (p >= a.x_h * a.x_w) return;
+  const int iy = p / a.x_w, ix = p - iy * a.x_w;
+  float s[8];
+  adapter_gather_dy<KIND>(a, n, iy, ix, s);
+  float *o = a.dx + ((int64_t)n * a.x_h * a.x_w + p) * a.dx_ld;
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    float4 r;
+    if (a.w != nullptr) {
+      r = f4zero();
+#pragma unroll
+      for (int co = 0; co < 8; ++co) {
+        const float4 w4 = ld4(s_w + co * C + c);
+        r.x = fmaf(s[co], w4.x, r.x), r.y = fmaf(s[co], w4.y, r.y), r.z = fmaf(s[co], w4.z, r.z), r.w = fmaf(s[co], w4.w, r.w);
+      }
+    } else {
+      r = make_float4(s[c], s[c + 1], s[c + 2], s[c + 3]);
+    }
+    if (a.accumulate) {
+      const float4 u = ld4(o + c);
+      r.x += u.x, r.y += u.y, r.z += u.z, r.w += u.w;
+    }
+    st4(o + c, r);
+  }
+}
+
+// adapter / pointwise weight gradient: dW[co][ci] = sum_p s[p][co] * a[p][ci] over a 128-pixel tile,
+// both staged in shared memory; one partial per block.
+//   AD_IDENTITY: p over x grid, a = x,        s = dy
+//   AD_POOL    : p over output grid, a = pooled(x), s = dy
+//   AD_UP      : p over x (low-res) grid, a = x, s = bilinear^T(dy)
+template <int C, int KIND>
+__global__ void __launch_bounds__(128) adapter_dw_kernel(AdapterBwdArgs a) {
+  __shared__ float s_a[128][C + 1];
+  __shared__ float s_s[128][9];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  const int gh = (KIND == AD_POOL) ? a.o_h : a.x_h, gw = (KIND == AD_POOL) ? a.o_w : a.x_w;
+  const int p = blockIdx.x * 128 + tid;
+  float av[C], s[8];
+#pragma unroll
+  for (int c = 0; c < C; ++c) av[c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (p < gh * gw) {
+    const int py = p / gw, px = p - py * gw;
+    const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld;
+    if (KIND == AD_POOL) {
+      adapter_input<C, AD_POOL>(xn, a.x_ld, a.x_h, a.x_w, py, px, av);
+      load_dy8(a, n, py, px, s);
+    } else {
+      adapter_input<C, AD_IDENTITY>(xn, a.x_ld, a.x_h, a.x_w, py, px, av);
+      adapter_gather_dy<KIND>(a, n, py, px, s);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) s_a[tid][c] = av[c];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_s[tid][j] = s[j];
+  __syncthreads();
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 8 * C;
+  for (int o = tid; o < 8 * C; o += 128) {
+    const int co = o / C, ci = o - co * C;
+    float r = 0.f;
+    for (int q = 0; q < 128; ++q) r = fmaf(s_s[q][co], s_a[q][ci], r);
+    out[o] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics finalize (one block per BN instance)
+// ------------------------------------------------------------------------------------------------
+struct Bases {
+  float *p[8];
+  int64_t ld[8];
+};
+enum { SP_SAVED = 0, SP_SCRATCH = 1, SP_IN0 = 2, SP_IN1 = 3, SP_OUT = 4, SP_GOUT = 5, SP_NULL = 7 };
+struct Ref {
+  int32_t space, pad;
+  int64_t off, ld;  // ld == 0: take the space's ld
+};
+SENAS_DEVFN float *ref_ptr(const Ref &r, const Bases &b) { return r.space == SP_NULL ? nullptr : b.p[r.space] + r.off; }
+SENAS_DEVFN int64_t ref_ld(const Ref &r, const Bases &b) { return r.ld ? r.ld : b.ld[r.space]; }
+
+struct BnDesc {
+  int32_t C, nblk, zero_input, pad;  // zero_input: the 'none' candidate (no partials, y == 0)
+  float count_per_sample;
+  float pad2;
+  int64_t part_off;                   // scratch: [B][nblk][2C]
+  int64_t mean_off, istd_off;         // saved
+  int64_t ysum_off;                   // saved [B][C], -1 when not needed
+  float *gamma, *beta, *rmean, *rvar;
+  int64_t *nbt;
+};
+
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const BnDesc *descs, Bases bases, int batch, int training) {
+  const BnDesc d = descs[blockIdx.x];
+  float *saved = bases.p[SP_SAVED], *scratch = bases.p[SP_SCRATCH];
+  __shared__ double s_tot[64];
+  __shared__ float s_grp[128];
+  const int tid = threadIdx.x, V = 2 * d.C, G = 128 / V, j = tid % V, g = tid / V;
+  if (tid < V) s_tot[tid] = 0.0;
+  __syncthreads();
+  if (!d.zero_input) {
+    const float *part = scratch + d.part_off;
+    for (int n = 0; n < batch; ++n) {
+      float r = 0.f;
+      if (g < G)
+        for (int b = g; b < d.nblk; b += G) r += part[((int64_t)n * d.nblk + b) * V + j];
+      s_grp[tid] = r;
+      __syncthreads();
+      if (tid < V) {
+        float t = 0.f;
+        for (int gg = 0; gg < G; ++gg) t += s_grp[gg * V + tid];
+        s_tot[tid] += (double)t;
+        if (d.ysum_off >= 0 && tid < d.C) saved[d.ysum_off + (int64_t)n * d.C + tid] = t;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < d.C) {
+    const double cnt = (double)d.count_per_sample * batch;
+    const double mean = s_tot[tid] / cnt;
+    double var = s_tot[d.C + tid] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float m_use, v_use;
+    if (training) {
+      m_use = (float)mean, v_use = (float)var;
+      const double unb = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+      d.rmean[tid] = (1.f - SENAS_MOMENTUM) * d.rmean[tid] + SENAS_MOMENTUM * (float)mean;
+      d.rvar[tid] = (1.f - SENAS_MOMENTUM) * d.rvar[tid] + SENAS_MOMENTUM * (float)unb;
+      if (tid == 0) *d.nbt += 1;
+    } else {
+      m_use = d.rmean[tid], v_use = d.rvar[tid];
+    }
+    saved[d.mean_off + tid] = m_use;
+    saved[d.istd_off + tid] = 1.0f / sqrtf(v_use + SENAS_EPS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// node coefficients + SE gate, node combine
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTerms = 24;
+struct TermDesc {
+  int32_t kind, edge, cand, has_y;
+  Ref y;                                 // pre-BN candidate output (8 channels)
+  int64_t mean_off, istd_off, ysum_off;  // saved
+  int64_t se_off;                        // saved: s[B][8], q[B][8], h[B]
+  int64_t scale_off;                     // scratch [B][8]   (forward)
+  int64_t coef_off;                      // scratch [3][B][8] (backward A, B, C)
+  float *gamma, *beta, *w1, *w2;
+  int64_t g_gamma, g_beta, g_w1, g_w2;  // offsets in the flat gradient buffer
+  float hw, pad;
+};
+struct NodeDesc {
+  int32_t nterms, node, nedges, pad;
+  int32_t edges[4];
+  int64_t bias_off;     // scratch [B][8]
+  int64_t gm_off;       // scratch [B][HW][8]
+  int64_t dnode_off;    // scratch [B][HW][8], -1 when the node feeds no edge
+  int64_t bpart_off;    // scratch [B][nblk][(1+nterms)*8]
+  int32_t nblk, hw;
+  TermDesc t[kMaxTerms];
+};
+
+__global__ void node_coef_kernel(const NodeDesc *nodes, int node, Bases bases, const float *alpha, const float *beta,
+                                 int batch) {
+  const NodeDesc &nd = nodes[node];
+  float *saved = bases.p[SP_SAVED], *scratch = bases.p[SP_SCRATCH];
+  const int total = batch * 8, rounded = (total + 31) & ~31;
+  for (int i = threadIdx.x; i < rounded; i += blockDim.x) {
+    const bool ok = i < total;
+    const int n = ok ? i >> 3 : 0, c = i & 7;
+    float bias = 0.f;
+    for (int ti = 0; ti < nd.nterms; ++ti) {
+      const TermDesc &t = nd.t[ti];
+      const float kappa = alpha[t.edge * 6 + t.cand] * (beta ? beta[t.edge] : 1.f);
+      const float g = t.gamma[c], b = t.beta[c], mean = saved[t.mean_off + c], istd = saved[t.istd_off + c];
+      float s = 1.f;
+      if (t.kind == 5) {  // SE_CONV: gate from the per-sample mean of BN(y)
+        const float q = g * (saved[t.ysum_off + n * 8 + c] / t.hw - mean) * istd + b;
+        float h = q * t.w1[c];
+        h += __shfl_xor_sync(0xffffffffu, h, 1);
+        h += __shfl_xor_sync(0xffffffffu, h, 2);
+        h += __shfl_xor_sync(0xffffffffu, h, 4);
+        const float a = fmaxf(h, 0.f);
+        s = 1.f / (1.f + expf(-t.w2[c] * a));
+        if (ok) {
+          saved[t.se_off + n * 8 + c] = s;
+          saved[t.se_off + batch * 8 + n * 8 + c] = q;
+          if (c == 0) saved[t.se_off + batch * 16 + n] = h;
+        }
+      }
+      if (ok && t.has_y) scratch[t.scale_off + n * 8 + c] = kappa * g * istd * s;
+      bias += kappa * (b - g * mean * istd) * s;
+    }
+    if (ok) scratch[nd.bias_off + n * 8 + c] = bias;
+  }
+}
+
+__global__ void __launch_bounds__(128) node_combine_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+  const NodeDesc &nd = nodes[node];
+  const float *scratch = bases.p[SP_SCRATCH];
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= nd.hw) return;
+  const int64_t pix = (int64_t)n * nd.hw + p;
+  const float *bias = scratch + nd.bias_off + n * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+  for (int ti = 0; ti < nd.nterms; ++ti) {
+    const TermDesc &t = nd.t[ti];
+    if (!t.has_y) continue;
+    const float *y = ref_ptr(t.y, bases) + pix * ref_ld(t.y, bases);
+    const float *sc = scratch + t.scale_off + n * 8;
+    const float4 lo = ld4(y), hi = ld4(y + 4);
+    acc[0] = fmaf(sc[0], lo.x, acc[0]), acc[1] = fmaf(sc[1], lo.y, acc[1]);
+    acc[2] = fmaf(sc[2], lo.z, acc[2]), acc[3] = fmaf(sc[3], lo.w, acc[3]);
+    acc[4] = fmaf(sc[4], hi.x, acc[4]), acc[5] = fmaf(sc[5], hi.y, acc[5]);
+    acc[6] = fmaf(sc[6], hi.z, acc[6]), acc[7] = fmaf(sc[7], hi.w, acc[7]);
+  }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+  }
+  float *o = bases.p[SP_OUT] + pix * bases.ld[SP_OUT] + nd.node * 8;
+  st4(o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  st4(o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: node statistics sweep
+//   gm = (g_out[node] + d_node) * relu'  ->  scratch;  per block: S1 = sum gm, S2_t = sum gm * yhat_t
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+  const NodeDesc &nd = nodes[node];
+  float *scratch = bases.p[SP_SCRATCH];
+  const float *saved = bases.p[SP_SAVED];
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  const bool ok = p < nd.hw;
+  const int64_t pix = (int64_t)n * nd.hw + (ok ? p : 0);
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (ok) {
+    const float *gp = bases.p[SP_GOUT] + pix * bases.ld[SP_GOUT] + nd.node * 8;
+    float4 lo = ld4(gp), hi = ld4(gp + 4);
+    if (nd.dnode_off >= 0) {
+      const float4 a = ld4(scratch + nd.dnode_off + pix * 8), b = ld4(scratch + nd.dnode_off + pix * 8 + 4);
+      lo.x += a.x, lo.y += a.y, lo.z += a.z, lo.w += a.w, hi.x += b.x, hi.y += b.y, hi.z += b.z, hi.w += b.w;
+    }
+    if (relu) {
+      const float *op = bases.p[SP_OUT] + pix * bases.ld[SP_OUT] + nd.node * 8;
+      const float4 a = ld4(op), b = ld4(op + 4);
+      lo.x = a.x > 0.f ? lo.x : 0.f, lo.y = a.y > 0.f ? lo.y : 0.f, lo.z = a.z > 0.f ? lo.z : 0.f;
+      lo.w = a.w > 0.f ? lo.w : 0.f, hi.x = b.x > 0.f ? hi.x : 0.f, hi.y = b.y > 0.f ? hi.y : 0.f;
+      hi.z = b.z > 0.f ? hi.z : 0.f, hi.w = b.w > 0.f ? hi.w : 0.f;
+    }
+    st4(scratch + nd.gm_off + pix * 8, lo);
+    st4(scratch + nd.gm_off + pix * 8 + 4, hi);
+    g[0] = lo.x, g[1] = lo.y, g[2] = lo.z, g[3] = lo.w, g[4] = hi.x, g[5] = hi.y, g[6] = hi.z, g[7] = hi.w;
+  }
+  float *part = scratch + nd.bpart_off + ((int64_t)n * nd.nblk + blockIdx.x) * (1 + nd.nterms) * 8;
+  block_sum_store<8>(g, part);
+  for (int ti = 0; ti < nd.nterms; ++ti) {
+    const TermDesc &t = nd.t[ti];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (t.has_y && ok) {
+      const float *y = ref_ptr(t.y, bases) + pix * ref_ld(t.y, bases);
+      const float4 lo = ld4(y), hi = ld4(y + 4);
+      const float yv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = g[j] * (yv[j] - saved[t.mean_off + j]) * saved[t.istd_off + j];
+    }
+    if (t.has_y) block_sum_store<8>(v, part + (1 + ti) * 8);  // uniform branch
+  }
+}
+
+// backward finalize for one node: reductions, parameter / alpha / beta gradients, dy coefficient tables
+__global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, int node, Bases bases, const float *alpha,
+                                                        const float *beta, float *g_alpha, float *g_beta, float *g_params,
+                                                        int batch, int training) {
+  const NodeDesc &nd = nodes[node];
+  float *scratch = bases.p[SP_SCRATCH];
+  const float *saved = bases.p[SP_SAVED];
+  __shared__ float s_S1[128 * 8], s_S2[128 * 8];  // [n][c], batch <= 128
+  __shared__ float s_u[128 * 8], s_dh[128];
+  __shared__ float s_T[8], s_dg[8], s_db[8];
+  __shared__ float s_gbeta[4];
+  const int tid = threadIdx.x, total = batch * 8, V = (1 + nd.nterms) * 8;
+  const float *part = scratch + nd.bpart_off;
+  const float M = (float)batch * (float)nd.hw;
+  if (tid < 4) s_gbeta[tid] = 0.f;
+  for (int i = tid; i < total; i += 128) {
+    const int n = i >> 3, c = i & 7;
+    float r = 0.f;
+    for (int b = 0; b < nd.nblk; ++b) r += part[((int64_t)n * nd.nblk + b) * V + c];
+    s_S1[i] = r;
+  }
+  __syncthreads();
+  for (int ti = 0; ti < nd.nterms; ++ti) {
+    const TermDesc &t = nd.t[ti];
+    const float w = alpha[t.edge * 6 + t.cand], be = beta ? beta[t.edge] : 1.f, kappa = w * be;
+    const bool se = t.kind == 5;
+    for (int i = tid; i < total; i += 128) {
+      const int n = i >> 3, c = i & 7;
+      float r = 0.f;
+      if (t.has_y)
+        for (int b = 0; b < nd.nblk; ++b) r += part[((int64_t)n * nd.nblk + b) * V + (1 + ti) * 8 + c];
+      s_S2[i] = r;
+    }
+    __syncthreads();
+    if (se) {  // through the gate: u = ds * s(1-s), dh = relu'(h) * sum_c u*W2
+      for (int n = tid; n < batch; n += 128) {
+        float da = 0.f;
+        for (int c = 0; c < 8; ++c) {
+          const float s = saved[t.se_off + n * 8 + c];
+          const float ds = kappa * (t.gamma[c] * s_S2[n * 8 + c] + t.beta[c] * s_S1[n * 8 + c]);
+          const float u = ds * s * (1.f - s);
+          s_u[n * 8 + c] = u;
+          da += u * t.w2[c];
+        }
+        s_dh[n] = saved[t.se_off + batch * 16 + n] > 0.f ? da : 0.f;
+      }
+      __syncthreads();
+    }
+    if (tid < 8) {
+      const int c = tid;
+      const float g = t.gamma[c], b = t.beta[c], mean = saved[t.mean_off + c], istd = saved[t.istd_off + c];
+      float dg = 0.f, db = 0.f, T = 0.f, dw1 = 0.f, dw2 = 0.f;
+      for (int n = 0; n < batch; ++n) {
+        const float S1 = s_S1[n * 8 + c], S2 = s_S2[n * 8 + c];
+        float s = 1.f, dq = 0.f, Yh = 0.f;
+        if (se) {
+          s = saved[t.se_off + n * 8 + c];
+          dq = s_dh[n] * t.w1[c];
+          Yh = (saved[t.ysum_off + n * 8 + c] - t.hw * mean) * istd;
+          const float h = saved[t.se_off + batch * 16 + n];
+          dw2 += s_u[n * 8 + c] * fmaxf(h, 0.f);
+          dw1 += s_dh[n] * saved[t.se_off + batch * 8 + n * 8 + c];
+        }
+        dg += kappa * s * S2 + dq / t.hw * Yh;
+        db += kappa * s * S1 + dq;
+        T += s * (g * S2 + b * S1);
+      }
+      s_T[c] = T, s_dg[c] = dg, s_db[c] = db;
+      if (t.g_gamma >= 0) g_params[t.g_gamma + c] = dg;
+      if (t.g_beta >= 0) g_params[t.g_beta + c] = db;
+      if (se) {
+        if (t.g_w1 >= 0) g_params[t.g_w1 + c] = dw1;
+        if (t.g_w2 >= 0) g_params[t.g_w2 + c] = dw2;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float Ts = 0.f;
+      for (int c = 0; c < 8; ++c) Ts += s_T[c];
+      g_alpha[t.edge * 6 + t.cand] = be * Ts;
+      for (int k = 0; k < nd.nedges; ++k)
+        if (nd.edges[k] == t.edge) s_gbeta[k] += w * Ts;
+    }
+    if (t.has_y) {
+      float *cf = scratch + t.coef_off;
+      for (int i = tid; i < total; i += 128) {
+        const int n = i >> 3, c = i & 7;
+        const float g = t.gamma[c], mean = saved[t.mean_off + c], istd = saved[t.istd_off + c];
+        float s = 1.f, dq = 0.f;
+        if (se) s = saved[t.se_off + n * 8 + c], dq = s_dh[n] * t.w1[c];
+        const float gi = g * istd;
+        const float m1 = training ? s_db[c] / M : 0.f, m2 = training ? s_dg[c] / M : 0.f;
+        cf[i] = gi * kappa * s;
+        cf[total + i] = -gi * istd * m2;
+        cf[2 * total + i] = gi * (dq / t.hw - m1 + mean * istd * m2);
+      }
+    }
+    __syncthreads();
+  }
+  if (g_beta != nullptr && tid < nd.nedges) g_beta[nd.edges[tid]] = s_gbeta[tid];
+}
+
+// ------------------------------------------------------------------------------------------------
+// dep-sep backward
+// ------------------------------------------------------------------------------------------------
+struct PwBwdArgs {
+  const float *gm, *y;  // y ld = 8
+  float *z;             // [B][hw][C]; dz kernel overwrites it with dz
+  int32_t hw, batch;
+  const float *coefA, *coefB, *coefC;
+  const float *mean1, *istd1, *g1, *b1;
+  const float *wpw;       // [8][C]
+  float *partials;        // pass 1: [B][gridDim.x][10C] = du sums (C), du*zhat sums (C), dWpw (8C)
+  const float *bn1_coef;  // pass 2: [3][C] = a1, dbeta1/M, dgamma1/M
+};
+
+// du (gradient at the BN1 output, after the ReLU mask) and side values for one pixel
+template <int C>
+SENAS_DEVFN void pw_pixel_backward(const PwBwdArgs &a, const float *s_w /*[co][ci]*/, const float *s_sc, const float *s_sh,
+                                   int n, int p, float *dy, float *zhat_or_r, float *du, bool want_r) {
+  const int64_t pix = (int64_t)n * a.hw + p;
+  const float4 glo = ld4(a.gm + pix * 8), ghi = ld4(a.gm + pix * 8 + 4);
+  const float4 ylo = ld4(a.y + pix * 8), yhi = ld4(a.y + pix * 8 + 4);
+  const float *A = a.coefA + n * 8, *B = a.coefB + n * 8, *Cc = a.coefC + n * 8;
+  dy[0] = A[0] * glo.x + B[0] * ylo.x + Cc[0], dy[1] = A[1] * glo.y + B[1] * ylo.y + Cc[1];
+  dy[2] = A[2] * glo.z + B[2] * ylo.z + Cc[2], dy[3] = A[3] * glo.w + B[3] * ylo.w + Cc[3];
+  dy[4] = A[4] * ghi.x + B[4] * yhi.x + Cc[4], dy[5] = A[5] * ghi.y + B[5] * yhi.y + Cc[5];
+  dy[6] = A[6] * ghi.z + B[6] * yhi.z + Cc[6], dy[7] = A[7] * ghi.w + B[7] * yhi.w + Cc[7];
+  const float *zp = a.z + pix * C;
+#pragma unroll
+  for (int c4 = 0; c4 < C; c4 += 4) {
+    const float4 zv = ld4(zp + c4);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c4 + k;
+      const float u = fmaf(zz[k], s_sc[c], s_sh[c]);
+      float dr = 0.f;
+#pragma unroll
+      for (int co = 0; co < 8; ++co) dr = fmaf(dy[co], s_w[co * C + c], dr);
+      du[c] = u > 0.f ? dr : 0.f;
+      zhat_or_r[c] = want_r ? fmaxf(u, 0.f) : (zz[k] - a.mean1[c]) * a.istd1[c];
+    }
+  }
+}
+
+// pass 1: statistics of du and the pointwise weight gradient
+template <int C>
+__global__ void __launch_bounds__(128) pw_bwd_stats_kernel(PwBwdArgs a) {
+  __shared__ float s_w[8 * C], s_sc[C], s_sh[C];
+  __shared__ float s_r[128][C + 1];
+  __shared__ float s_dy[128][9];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  for (int i = tid; i < 8 * C; i += 128) s_w[i] = __ldg(a.wpw + i);
+  if (tid < C) {
+    const float sc = a.g1[tid] * a.istd1[tid];
+    s_sc[tid] = sc, s_sh[tid] = a.b1[tid] - a.mean1[tid] * sc;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 128 + tid;
+  float dy[8], r[C], du[C];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dy[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) r[c] = du[c] = 0.f;
+  if (p < a.hw) pw_pixel_backward<C>(a, s_w, s_sc, s_sh, n, p, dy, r, du, true);
+#pragma unroll
+  for (int c = 0; c < C; ++c) s_r[tid][c] = r[c];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_dy[tid][j] = dy[j];
+  __syncthreads();
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
+  for (int o = tid; o < 8 * C; o += 128) {
+    const int co = o / C, ci = o - co * C;
+    float acc = 0.f;
+    for (int q = 0; q < 128; ++q) acc = fmaf(s_dy[q][co], s_r[q][ci], acc);
+    out[2 * C + o] = acc;
+  }
+  __syncthreads();
+  // du and du*zhat: zhat = (r>0 ? (u - b1)/g1 ...) is not recoverable from r; recompute from z
+#pragma unroll
+  for (int c = 0; c < C; ++c) s_r[tid][c] = du[c];
+  __syncthreads();
+  if (tid < C) {
+    float acc = 0.f;
+    for (int q = 0; q < 128; ++q) acc += s_r[q][tid];
+    out[tid] = acc;
+  }
+  __syncthreads();
+  if (p < a.hw) {
+    const float *zp = a.z + ((int64_t)n * a.hw + p) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_r[tid][c] = du[c] * (zp[c] - a.mean1[c]) * a.istd1[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) s_r[tid][c] = 0.f;
+  }
+  __syncthreads();
+  if (tid < C) {
+    float acc = 0.f;
+    for (int q = 0; q < 128; ++q) acc += s_r[q][tid];
+    out[C + tid] = acc;
+  }
+}
+
+// BN1 backward finalize (one block): reduce pass-1 partials, write d gamma1 / d beta1 / dW_pw, coefficient table
+__global__ void __launch_bounds__(128) pw_bfin_kernel(const float *partials, int nblk_total, int C, float M, const float *g1,
+                                                      const float *istd1, float *coef /*[3][C]*/, float *g_gamma1,
+                                                      float *g_beta1, float *g_wpw) {
+  const int V = 10 * C;
+  for (int i = threadIdx.x; i < V; i += 128) {
+    float s = 0.f;
+    for (int b = 0; b < nblk_total; ++b) s += partials[(int64_t)b * V + i];
+    if (i < C) {
+      g_beta1[i] = s;
+      coef[C + i] = s / M;
+      coef[i] = g1[i] * istd1[i];
+    } else if (i < 2 * C) {
+      g_gamma1[i - C] = s;
+      coef[2 * C + i - C] = s / M;
+    } else {
+      g_wpw[i - 2 * C] = s;
+    }
+  }
+}
+
+// pass 2: dz = a1 * (du - dbeta1/M - zhat * dgamma1/M), in place over z
+template <int C>
+__global__ void __launch_bounds__(128) pw_bwd_dz_kernel(PwBwdArgs a, int training) {
+  __shared__ float s_w[8 * C], s_sc[C], s_sh[C], s_k[3 * C];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  for (int i = tid; i < 8 * C; i += 128) s_w[i] = __ldg(a.wpw + i);
+  for (int i = tid; i < 3 * C; i += 128) s_k[i] = a.bn1_coef[i];
+  if (tid < C) {
+    const float sc = a.g1[tid] * a.istd1[tid];
+    s_sc[tid] = sc, s_sh[tid] = a.b1[tid] - a.mean1[tid] * sc;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 128 + tid;
+  if (p >= a.hw) return;
+  float dy[8], zh[C], du[C];
+  pw_pixel_backward<C>(a, s_w, s_sc, s_sh, n, p, dy, zh, du, false);
+  float *zp = a.z + ((int64_t)n * a.hw + p) * C;
+#pragma unroll
+  for (int c = 0; c < C; c += 4) {
+    float4 r;
+    float *rr = &r.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      rr[k] = training ? s_k[c + k] * (du[c + k] - s_k[C + c + k] - zh[c + k] * s_k[2 * C + c + k]) : s_k[c + k] * du[c + k];
+    st4(zp + c, r);
+  }
+}
+
+// depthwise data gradient: dx[i][c] (+)= sum_t dz[b(i,t)*so' ...][c] * w[c][t], with the mirrored
+// tap table (same base-grid convention as gather_mac dgrad).  thread = (base pixel, channel quad).
+struct DwBwdArgs {
+  const float *dz;
+  int32_t z_h, z_w;
+  float *dx;
+  int64_t dx_ld;
+  int32_t x_h, x_w;
+  int32_t accumulate, base_h, base_w, si, so;
+  const float *w;  // [C][T]
+  TapTable taps;   // mirrored (dgrad) table
+  // wgrad
+  const float *x;
+  int64_t x_ld;
+  float *partials;
+  int32_t batch, chunk;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) dw_dx_kernel(DwBwdArgs a) {
+  constexpr int Q = C / 4, PPB = 128 / Q;
+  __shared__ float s_w[25 * C];
+  const int tid = threadIdx.x, n = blockIdx.y, pl = tid / Q, q = tid % Q;
+  const int T = a.taps.n;
+  for (int i = tid; i < T * C; i += 128) {
+    const int c = i % C, t = i / C;
+    s_w[i] = __ldg(a.w + c * T + a.taps.widx[t]);
+  }
+  __syncthreads();
+  const int b = blockIdx.x * PPB + pl;
+  if (b >= a.base_h * a.base_w) return;
+  const int by = b / a.base_w, bx = b - by * a.base_w;
+  const float *zn = a.dz + (int64_t)n * a.z_h * a.z_w * C + q * 4;
+  float *xn = a.dx + (int64_t)n * a.x_h * a.x_w * a.dx_ld + q * 4;
+  for (int ph = 0; ph < a.taps.nphase; ++ph) {
+    const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+    if (oy >= a.x_h || ox >= a.x_w) continue;
+    float4 r = f4zero();
+    for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
+      const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t];
+      if (iy < 0 || iy >= a.z_h || ix < 0 || ix >= a.z_w) continue;
+      const float4 zv = ld4(zn + ((int64_t)iy * a.z_w + ix) * C);
+      const float4 wv = ld4(s_w + t * C + q * 4);
+      r.x = fmaf(zv.x, wv.x, r.x), r.y = fmaf(zv.y, wv.y, r.y), r.z = fmaf(zv.z, wv.z, r.z), r.w = fmaf(zv.w, wv.w, r.w);
+    }
+    float *o = xn + ((int64_t)oy * a.x_w + ox) * a.dx_ld;
+    if (a.accumulate) {
+      const float4 u = ld4(o);
+      r.x += u.x, r.y += u.y, r.z += u.z, r.w += u.w;
+    }
+    st4(o, r);
+  }
+}
+
+// depthwise weight gradient: dW[c][t] = sum_b x[b*si + d_t][c] * dz[b*so + phase_t][c]; forward tap table.
+// thread = (c, t); each block walks `chunk` base pixels of one sample.
+template <int C>
+__global__ void dw_wgrad_kernel(DwBwdArgs a) {
+  const int tid = threadIdx.x, c = tid % C, t = tid / C, n = blockIdx.y;
+  const int npix = a.base_h * a.base_w;
+  const int b0 = blockIdx.x * a.chunk, b1 = b0 + a.chunk < npix ? b0 + a.chunk : npix;
+  const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld + c;
+  const float *zn = a.dz + (int64_t)n * a.z_h * a.z_w * C + c;
+  const int dy = a.taps.dy[t], dx = a.taps.dx[t], ph = a.taps.phase[t];
+  float acc = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const int by = b / a.base_w, bx = b - by * a.base_w;
+    const int iy = by * a.si + dy, ix = bx * a.si + dx;
+    const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+    if (iy < 0 || iy >= a.x_h || ix < 0 || ix >= a.x_w || oy >= a.z_h || ox >= a.z_w) continue;
+    acc = fmaf(__ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld), zn[((int64_t)oy * a.z_w + ox) * C], acc);
+  }
+  a.partials[((int64_t)n * gridDim.x + blockIdx.x) * C * a.taps.n + c * a.taps.n + a.taps.widx[t]] = acc;
+}

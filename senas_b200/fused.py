@@ -1,0 +1,218 @@
+"""Host driver of one edge graph (a MixedOp, or the node loop + concat of a Cell).
+
+Builds the C-ABI descriptor from the parameter modules, owns the opaque graph handle, and wraps
+``senas_graph_forward`` / ``senas_graph_backward`` in a ``torch.autograd.Function``.  PyTorch
+is used for device memory, streams and autograd plumbing only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ops import (KIND_AVG_POOL, KIND_CONV, KIND_DEPSEP, KIND_IDENTITY, KIND_NONE, KIND_SE_CONV, KIND_UP_SAMPLE,
+                  AdapterBlock, ConvBn, ConvBnSe, DepSepConv)
+
+
+def _bn_slots(bn):
+    return [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked]
+
+
+def candidate_slots(op):
+    """(kind, ksize, dilation, [12 slot tensors or None]) for one candidate block, in the slot order
+    documented in include/senas_b200.h."""
+    slots = [None] * _lib.SLOTS
+    if isinstance(op, AdapterBlock):
+        slots[0] = op.conv.weight if hasattr(op, 'conv') else None
+        slots[1:6] = _bn_slots(op.norm)
+        return op.kind, 0, 1, slots
+    if isinstance(op, ConvBnSe):
+        slots[0] = op[0].weight
+        slots[1:6] = _bn_slots(op[1])
+        slots[6], slots[7] = op[2].excitation[0].weight, op[2].excitation[2].weight
+        return KIND_SE_CONV, op.k, op.dilation, slots
+    if isinstance(op, ConvBn):
+        slots[0] = op[0].weight
+        slots[1:6] = _bn_slots(op[1])
+        return KIND_CONV, op.k, op.dilation, slots
+    if isinstance(op, DepSepConv):
+        slots[0] = op[0].weight
+        slots[1:6] = _bn_slots(op[1])
+        slots[6] = op[3].weight
+        slots[7:12] = _bn_slots(op[4])
+        return KIND_DEPSEP, op.k, 1, slots
+    raise TypeError(f'not a MixedOp candidate: {type(op).__name__}')
+
+
+_scratch = {}
+
+
+def scratch_for(device, nbytes):
+    """One grow-only scratch buffer per device, shared by every graph on the stream."""
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _scratch[device] = buf
+    return buf
+
+
+def _nhwc(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+class GraphRunner:
+    """``edges``: list of (candidate module list, src state, dst node, op_type id, c_in)."""
+
+    def __init__(self, edges, n_inputs, n_nodes, node_relu, lib=None):
+        self.lib = lib if lib is not None else _lib.get()
+        self.edges, self.n_inputs, self.n_nodes, self.node_relu = edges, n_inputs, n_nodes, node_relu
+        self.handle = None
+        self._plans = {}
+        self._build()
+
+    def _build(self):
+        lib = self.lib
+        desc = _lib.GraphDesc()
+        desc.n_inputs, desc.n_nodes, desc.n_edges = self.n_inputs, self.n_nodes, len(self.edges)
+        desc.c_out, desc.node_relu = 8, int(self.node_relu)
+        self.params, self.sizes, self.shapes = [], [], []
+        off = 0
+        for e, (cands, src, dst, op_type, c_in) in enumerate(self.edges):
+            ed = desc.edge[e]
+            ed.src, ed.dst, ed.op_type, ed.c_in = src, dst, op_type, c_in
+            for k, op in enumerate(cands):
+                kind, ks, dil, slots = candidate_slots(op)
+                ed.kind[k], ed.ksize[k], ed.dilation[k] = kind, ks, dil
+                for s, t in enumerate(slots):
+                    ed.grad_off[k][s] = -1
+                    if t is None:
+                        ed.param[k][s] = None
+                        continue
+                    if not t.is_contiguous():
+                        raise RuntimeError('senas_b200: parameters must be contiguous')
+                    ed.param[k][s] = t.data_ptr()
+                    if t.is_floating_point() and isinstance(t, torch.nn.Parameter):
+                        ed.grad_off[k][s] = off
+                        self.params.append(t)
+                        self.sizes.append(t.numel())
+                        self.shapes.append(t.shape)
+                        off += t.numel()
+        desc.grad_floats = off
+        self.grad_floats = off
+        self.device = self.params[0].device
+        self._fingerprint = (self.params[0].data_ptr(), self.params[-1].data_ptr(), self.device)
+        h = C.c_void_p()
+        _lib.check(lib, lib.senas_graph_create(C.byref(desc), C.byref(h)))
+        if self.handle is not None:
+            lib.senas_graph_destroy(self.handle)
+        self.handle, self._plans, self._desc = h, {}, desc
+
+    def refresh(self):
+        """Re-read parameter pointers if the module was moved (``.to()``) since the graph was built."""
+        fp = (self.params[0].data_ptr(), self.params[-1].data_ptr(), self.params[0].device)
+        if fp != self._fingerprint:
+            self._build()
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.lib.senas_graph_destroy(self.handle)
+        except Exception:
+            pass
+
+    def plan(self, batch, hs, ws):
+        key = (batch, tuple(hs), tuple(ws))
+        info = self._plans.get(key)
+        if info is None:
+            info = _lib.PlanInfo()
+            ih, iw = (C.c_int32 * 2)(*(list(hs) + [0])[:2]), (C.c_int32 * 2)(*(list(ws) + [0])[:2])
+            _lib.check(self.lib, self.lib.senas_graph_plan(self.handle, batch, ih, iw, C.byref(info)))
+            self._plans[key] = info
+        return info
+
+    # -- raw calls (tensors already NHWC fp32 on self.device) ---------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
+
+    def forward(self, ins, alpha, beta, training):
+        B = ins[0].shape[0]
+        hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
+        info = self.plan(B, hs, ws)
+        out = torch.empty((B, 8 * self.n_nodes, info.out_h, info.out_w), dtype=torch.float32, device=self.device,
+                          memory_format=torch.channels_last)
+        saved = torch.empty(info.saved_bytes, dtype=torch.uint8, device=self.device)
+        scratch = scratch_for(self.device, info.scratch_bytes)
+        a = _lib.FwdArgs()
+        a.batch, a.training = B, int(training)
+        for i, t in enumerate(ins):
+            a.in_h[i], a.in_w[i], a.in_[i], a.in_ld[i] = t.shape[2], t.shape[3], t.data_ptr(), t.shape[1]
+        a.alpha, a.beta = alpha.data_ptr(), (beta.data_ptr() if beta is not None else None)
+        a.out, a.out_ld = out.data_ptr(), out.shape[1]
+        a.saved, a.scratch, a.stream = saved.data_ptr(), scratch.data_ptr(), self._stream()
+        _lib.check(self.lib, self.lib.senas_graph_forward(self.handle, C.byref(a)))
+        return out, saved
+
+    def backward(self, ins, alpha, beta, out, grad_out, saved, training, need_in):
+        B = ins[0].shape[0]
+        hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
+        info = self.plan(B, hs, ws)
+        scratch = scratch_for(self.device, info.scratch_bytes)
+        n_edges = len(self.edges)
+        g_alpha = torch.empty((n_edges, 6), dtype=torch.float32, device=self.device)
+        g_beta = torch.empty((n_edges,), dtype=torch.float32, device=self.device) if beta is not None else None
+        g_params = torch.empty((self.grad_floats,), dtype=torch.float32, device=self.device)
+        g_ins = [torch.empty_like(t, memory_format=torch.channels_last) if need else None
+                 for t, need in zip(ins, need_in)]
+        a = _lib.BwdArgs()
+        a.batch, a.training = B, int(training)
+        for i, t in enumerate(ins):
+            a.in_h[i], a.in_w[i], a.in_[i], a.in_ld[i] = t.shape[2], t.shape[3], t.data_ptr(), t.shape[1]
+            if g_ins[i] is not None:
+                a.grad_in[i], a.grad_in_ld[i] = g_ins[i].data_ptr(), t.shape[1]
+        a.alpha, a.beta = alpha.data_ptr(), (beta.data_ptr() if beta is not None else None)
+        a.out, a.out_ld = out.data_ptr(), out.shape[1]
+        a.grad_out, a.grad_out_ld = grad_out.data_ptr(), grad_out.shape[1]
+        a.saved, a.scratch = saved.data_ptr(), scratch.data_ptr()
+        a.grad_alpha = g_alpha.data_ptr()
+        a.grad_beta = g_beta.data_ptr() if g_beta is not None else None
+        a.grad_params, a.stream = g_params.data_ptr(), self._stream()
+        _lib.check(self.lib, self.lib.senas_graph_backward(self.handle, C.byref(a)))
+        return g_ins, g_alpha, g_beta, g_params
+
+    # -- autograd entry ------------------------------------------------------------------------
+    def apply(self, ins, alpha, beta, training):
+        """ins: list of [B,C,H,W] fp32 tensors; alpha [E,6]; beta [E] or None -> [B,8*nodes,Ho,Wo]."""
+        self.refresh()
+        ins = [_nhwc(t.float()) for t in ins]
+        alpha = alpha.float().contiguous()
+        beta = beta.float().contiguous() if beta is not None else None
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in ins) or alpha.requires_grad or
+                                        any(p.requires_grad for p in self.params)):
+            in1 = ins[1] if len(ins) > 1 else None
+            return _GraphFn.apply(self, training, alpha, beta, ins[0], in1, *self.params)
+        out, _ = self.forward(ins, alpha, beta, training)
+        return out
+
+
+class _GraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, training, alpha, beta, in0, in1, *params):
+        ins = [in0] if in1 is None else [in0, in1]
+        out, saved = runner.forward(ins, alpha, beta, training)
+        ctx.runner, ctx.training, ctx.saved_buf, ctx.has_in1 = runner, training, saved, in1 is not None
+        ctx.has_beta = beta is not None
+        ctx.save_for_backward(alpha, beta, in0, in1, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        alpha, beta, in0, in1, out = ctx.saved_tensors
+        runner = ctx.runner
+        if ctx.saved_buf is None:
+            raise RuntimeError('senas_b200: backward through the same fused graph twice is not supported')
+        ins = [in0] if in1 is None else [in0, in1]
+        need_in = [ctx.needs_input_grad[4]] + ([ctx.needs_input_grad[5]] if in1 is not None else [])
+        g_ins, g_alpha, g_beta, g_params = runner.backward(ins, alpha, beta, out, _nhwc(grad_out.float()),
+                                                           ctx.saved_buf, ctx.training, need_in)
+        ctx.saved_buf = None  # the library overwrote parts of it (dz in place of z)
+        grads = [g.view(s) for g, s in zip(torch.split(g_params, runner.sizes), runner.shapes)]
+        return (None, None, g_alpha, g_beta, g_ins[0], g_ins[1] if in1 is not None else None, *grads)

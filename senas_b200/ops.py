@@ -1,0 +1,237 @@
+"""Candidate-operation zoo of the SENAS supernet: parameter containers only.
+
+Mirrors the public surface of the reference's ``utils/operations.py`` (``OPS`` registry
+``:8-21``, candidate lists ``:23-48``, ``OpType`` ``:51-54``, ``build_ops`` ``:57-78``) so that
+``state_dict`` keys, parameter order and fixed-seed initialisation are identical, but the
+candidate blocks here own **no arithmetic**: the hot path (every candidate inside a
+``MixedOp``) is evaluated by the sm_100a kernels behind ``libsenas_b200.so``.  Calling a
+candidate block directly raises -- there is deliberately no PyTorch fallback.
+
+The blocks that are *outside* the hot path (``ShrinkBlock``, ``RectifyBlock``, ``ReLUConv``,
+the stem ``BasicBlock``) are ordinary ``torch.nn`` modules.
+"""
+from enum import Enum
+
+import torch
+import torch.nn as nn
+
+DownOps = ['avg_pool', 'se_conv_3', 'dil_3_conv_5', 'dil_2_conv_5', 'dep_sep_conv_3', 'dep_sep_conv_5']
+UpOps = ['up_sample', 'se_conv_3', 'dil_3_conv_5', 'dil_2_conv_5', 'dep_sep_conv_3', 'dep_sep_conv_5']
+NormOps = ['identity', 'none', 'dil_3_conv_5', 'dil_2_conv_5', 'dep_sep_conv_3', 'dep_sep_conv_5']
+
+
+class OpType(Enum):
+    """Same member names and ``value`` payloads as the reference enum (operations.py:51-54)."""
+    UP = {'id': 1, 'ops': UpOps}
+    DOWN = {'id': 2, 'ops': DownOps}
+    NORM = {'id': 3, 'ops': NormOps}
+
+
+# candidate "kind" ids shared with the C-ABI (include/senas_b200.h, SENAS_KIND_*)
+KIND_NONE, KIND_IDENTITY, KIND_AVG_POOL, KIND_UP_SAMPLE = 0, 1, 2, 3
+KIND_CONV, KIND_SE_CONV, KIND_DEPSEP = 4, 5, 6
+
+
+def same_padding(kernel_size, dilation=1):
+    """``get_same_padding`` (utils/utils.py:21-29) times dilation (operations.py:119-120)."""
+    if kernel_size % 2 == 0:
+        raise AssertionError('kernel size should be odd number')
+    return (kernel_size // 2) * dilation
+
+
+def _geometry(op_type):
+    stride = 1 if op_type == OpType.NORM else 2
+    transposed = op_type == OpType.UP
+    return stride, transposed, (1 if transposed else 0)
+
+
+def _weight(c_in, c_ot, k, stride, dilation, transposed, out_pad, groups=1):
+    pad = same_padding(k, dilation)
+    if transposed:
+        return nn.ConvTranspose2d(c_in, c_ot, k, stride=stride, padding=pad, dilation=dilation, bias=False,
+                                  output_padding=out_pad, groups=groups)
+    return nn.Conv2d(c_in, c_ot, k, stride=stride, padding=pad, dilation=dilation, bias=False, groups=groups)
+
+
+class _KernelOnly:
+    """Mixin: the block is a parameter store for the CUDA path, not a callable."""
+
+    def forward(self, *a, **k):  # noqa: D401
+        raise RuntimeError(
+            f'{type(self).__name__} is evaluated inside the fused senas_b200 MixedOp kernels; '
+            'it has no standalone (PyTorch) forward')
+
+
+class ZeroOp(_KernelOnly, nn.Module):
+    def __init__(self, stride=1):
+        super().__init__()
+        self.stride = stride
+
+
+class SEBlock(_KernelOnly, nn.Module):
+    """Squeeze-excite parameter store; ``mid = 1`` for c = 8 (operations.py:186-203)."""
+
+    def __init__(self, c, r=16):
+        super().__init__()
+        self.mid = c // r if c > r else 1
+        self.squeeze = nn.AdaptiveAvgPool2d(1)
+        self.excitation = nn.Sequential(nn.Linear(c, self.mid, bias=False), nn.ReLU(inplace=True),
+                                        nn.Linear(self.mid, c, bias=False), nn.Sigmoid())
+
+
+class AdapterBlock(_KernelOnly, nn.Module):
+    """pool / upsample / identity / zero -> optional 1x1 conv -> BN (operations.py:167-183)."""
+
+    def __init__(self, c_in, c_ot, module, kind):
+        super().__init__()
+        self.c_in, self.c_ot, self.kind = c_in, c_ot, kind
+        self.module = module
+        if c_in != c_ot:
+            self.conv = nn.Conv2d(c_in, c_ot, kernel_size=1, bias=False)
+        self.norm = nn.BatchNorm2d(c_ot, affine=True)
+
+
+class ConvBn(_KernelOnly, nn.Sequential):
+    kind = KIND_CONV
+
+    def __init__(self, c_in, c_ot, k, op_type, dilation=1):
+        stride, tr, op = _geometry(op_type)
+        super().__init__(_weight(c_in, c_ot, k, stride, dilation, tr, op), nn.BatchNorm2d(c_ot))
+        self.k, self.dilation = k, dilation
+
+
+class ConvBnSe(_KernelOnly, nn.Sequential):
+    kind = KIND_SE_CONV
+
+    def __init__(self, c_in, c_ot, k, op_type, dilation=1):
+        stride, tr, op = _geometry(op_type)
+        super().__init__(_weight(c_in, c_ot, k, stride, dilation, tr, op), nn.BatchNorm2d(c_ot), SEBlock(c_ot))
+        self.k, self.dilation = k, dilation
+
+
+class DepSepConv(_KernelOnly, nn.Sequential):
+    kind = KIND_DEPSEP
+
+    def __init__(self, c_in, c_ot, k, op_type):
+        stride, tr, op = _geometry(op_type)
+        super().__init__(_weight(c_in, c_in, k, stride, 1, tr, op, groups=c_in), nn.BatchNorm2d(c_in),
+                         nn.ReLU(inplace=True), _weight(c_in, c_ot, 1, 1, 1, False, 0), nn.BatchNorm2d(c_ot))
+        self.k, self.dilation = k, 1
+
+
+def build_ops(op_name, op_type, c_in=None, c_ot=None, dp=0):
+    """Candidate factory; same names / argument meaning / error as operations.py:57-78."""
+    if dp:
+        raise NotImplementedError('dropout inside candidates is not part of the search path (dp=0 at cell.py:29)')
+    stride = 1 if op_type == OpType.NORM else 2
+    if op_name == 'avg_pool':
+        return AdapterBlock(c_in, c_ot, nn.AvgPool2d(3, stride=stride, padding=1, count_include_pad=False),
+                            KIND_AVG_POOL)
+    if op_name == 'se_conv_3':
+        return ConvBnSe(c_in, c_ot, 3, op_type)
+    if op_name == 'dil_3_conv_5':
+        return ConvBn(c_in, c_ot, 5, op_type, dilation=3)
+    if op_name == 'dil_2_conv_5':
+        return ConvBn(c_in, c_ot, 5, op_type, dilation=2)
+    if op_name == 'dep_sep_conv_3':
+        return DepSepConv(c_in, c_ot, 3, op_type)
+    if op_name == 'dep_sep_conv_5':
+        return DepSepConv(c_in, c_ot, 5, op_type)
+    raise NotImplementedError()
+
+
+OPS = {
+    'none': lambda c_in, c_ot, op_type, dp: AdapterBlock(c_in, c_ot, ZeroOp(stride=1), KIND_NONE),
+    'identity': lambda c_in, c_ot, op_type, dp: AdapterBlock(c_in, c_ot, nn.Identity(), KIND_IDENTITY),
+    'avg_pool': lambda c_in, c_ot, op_type, dp: build_ops('avg_pool', op_type, c_in, c_ot),
+    'up_sample': lambda c_in, c_ot, op_type, dp: AdapterBlock(
+        c_in, c_ot, nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), KIND_UP_SAMPLE),
+    'se_conv_3': lambda c_in, c_ot, op_type, dp: build_ops('se_conv_3', op_type, c_in, c_ot, dp=dp),
+    'dil_3_conv_5': lambda c_in, c_ot, op_type, dp: build_ops('dil_3_conv_5', op_type, c_in, c_ot, dp=dp),
+    'dil_2_conv_5': lambda c_in, c_ot, op_type, dp: build_ops('dil_2_conv_5', op_type, c_in, c_ot, dp=dp),
+    'dep_sep_conv_3': lambda c_in, c_ot, op_type, dp: build_ops('dep_sep_conv_3', op_type, c_in, c_ot, dp=dp),
+    'dep_sep_conv_5': lambda c_in, c_ot, op_type, dp: build_ops('dep_sep_conv_5', op_type, c_in, c_ot, dp=dp),
+}
+
+
+# ------------------------------------------------------------------------------------------
+# Blocks around the hot path (rows f1/f3 of SURVEY.md section 8: stock PyTorch for now)
+# ------------------------------------------------------------------------------------------
+class ReLUConv(nn.Sequential):
+    def __init__(self, c_in, c_ot, kernel_size=3):
+        super().__init__(nn.ReLU(inplace=False), _weight(c_in, c_ot, kernel_size, 1, 1, False, 0))
+
+
+class StemConvBn(nn.Sequential):
+    """The 7x7 stem (``ConvBn(in_channels, c, kernel_size=7)``, senas_search.py:30)."""
+
+    def __init__(self, c_in, c_ot, kernel_size):
+        super().__init__(_weight(c_in, c_ot, kernel_size, 1, 1, False, 0), nn.BatchNorm2d(c_ot))
+
+
+class ShrinkBlock(nn.Module):
+    def __init__(self, c_in, c_ot):
+        super().__init__()
+        self.act = nn.ReLU(inplace=False)
+        self.conv = nn.Conv2d(c_in, c_ot, kernel_size=3, padding=1, bias=False)
+        self.norm = nn.BatchNorm2d(c_ot)
+
+    def forward(self, x):
+        return self.norm(self.conv(self.act(x)))
+
+
+class RectifyBlock(nn.Module):
+    def __init__(self, c_in, c_ot, cell_type='down'):
+        super().__init__()
+        self.cell_type = cell_type
+        self.conv = nn.Conv2d(c_in, c_ot, kernel_size=3, padding=1, bias=False)
+        self.norm = nn.BatchNorm2d(c_ot)
+
+    def forward(self, x):
+        return self.norm(self.conv(x))
+
+
+def build_rectify(c_in, c_ot, cell_type):
+    act = nn.ReLU(inplace=False)
+    if cell_type == 'up':
+        if c_in == c_ot:
+            return nn.Sequential(act, nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False),
+                                 nn.BatchNorm2d(c_ot))
+        return nn.Sequential(act, nn.ConvTranspose2d(c_in, c_ot, kernel_size=1, stride=2, output_padding=1,
+                                                     bias=False), nn.BatchNorm2d(c_ot))
+    if c_in == c_ot:
+        return nn.Sequential(act, nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False),
+                             nn.BatchNorm2d(c_ot))
+    return nn.Sequential(act, nn.Conv2d(c_in, c_ot, kernel_size=1, stride=2, bias=False), nn.BatchNorm2d(c_ot))
+
+
+class BasicBlock(nn.Module):
+    """ResNet basic block of ``stem1`` (operations.py:235-268); out of the hot path."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+
+    def forward(self, x):
+        out = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        out += x
+        return out
+
+
+def weights_init(m):
+    """Same initialisation rule as utils/utils.py:240-250."""
+    if isinstance(m, nn.Linear):
+        nn.init.xavier_normal_(m.weight)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+        nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+    elif isinstance(m, nn.BatchNorm2d):
+        nn.init.constant_(m.weight, 1)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)

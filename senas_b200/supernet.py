@@ -1,0 +1,190 @@
+"""Search network and controller around the fused cells: API mirror of the reference's
+``search/senas_search.py`` (``Head`` :5-13, ``SenasSearch`` :16-112, ``NAS`` :115-279,
+``Architecture`` :282-303).  Constructor signatures, attribute names, ``state_dict`` keys,
+``parameters()`` order and fixed-seed initial values are identical to the reference; the
+``Cell`` objects it builds run the sm_100a kernels (``senas_b200.cell``).
+
+Everything outside the cells (stems, gamma-mixed skip concat, head conv) is stock PyTorch --
+rows f1/f3 of SURVEY.md section 8 ("next").  Activations travel in ``channels_last`` (NHWC)
+memory so the cells read and write them without layout conversion.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .cell import Cell
+from .genotype import GenoParser, Genotype
+from .ops import (BasicBlock, DownOps, NormOps, ReLUConv, StemConvBn, UpOps, weights_init)
+
+
+class Head(nn.Module):
+    def __init__(self, meta_node_num, double_down, c_in0, c_in1, nclass):
+        super().__init__()
+        self.up_cell = Cell(meta_node_num, double_down, c_in0, c_in1, c_in1, cell_type='up')
+        self.segmentation_head = ReLUConv(c_in1, nclass, kernel_size=3)
+
+    def forward(self, s0, ot, weights_up_norm, weights_up, betas_up):
+        return self.segmentation_head(self.up_cell(s0, ot, weights_up_norm, weights_up, betas_up))
+
+
+class SenasSearch(nn.Module):
+    """UNet++-shaped supernet: ``depth-1`` down cells, a nested triangle of up cells, one head."""
+
+    def __init__(self, in_channels, c, nclass, depth, meta_node_num=3, double_down_channel=False,
+                 supervision=False):
+        super().__init__()
+        assert depth >= 2, 'depth must >= 2'
+        self._depth, self._double_down_channel = depth, double_down_channel
+        self._supervision, self._meta_node_num = supervision, meta_node_num
+        dd = 2 if double_down_channel else 1
+        c_in0 = c_in1 = c_curr = c
+
+        self.blocks = nn.ModuleList()
+        self.stem0 = StemConvBn(in_channels, c_in0, kernel_size=7)
+        self.stem1 = nn.Sequential(nn.ReLU(inplace=False), nn.MaxPool2d(3, stride=2, padding=1),
+                                   BasicBlock(c_in0, c_in1))
+        widths = [[c_in1]]  # widths[i][j] = channels produced by blocks[i][j]
+        down = nn.ModuleList([self.stem1])
+        for _ in range(1, depth):
+            c_curr = int(dd * c_curr)
+            down.append(Cell(meta_node_num, dd, c_in0, c_in1, c_curr, cell_type='down'))
+            widths[0].append(c_curr)
+            c_in0, c_in1 = c_in1, c_curr
+        self.blocks.append(down)
+        for i in range(1, depth):
+            row, row_w = nn.ModuleList(), []
+            for j in range(depth - i):
+                head_in0 = sum(widths[k][j] for k in range(i))
+                row.append(Cell(meta_node_num, dd, head_in0, widths[i - 1][j + 1], widths[0][j], cell_type='up'))
+                row_w.append(widths[0][j])
+            widths.append(row_w)
+            self.blocks.append(row)
+        self.head_block = nn.ModuleList([Head(meta_node_num, dd, c, widths[-1][0], nclass)])
+
+    def forward(self, x, alpha_dn_nm, alpha_up_nm, alpha_dn, alpha_up, beta_dn, beta_up, gamma):
+        if x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        s0 = self.stem0(x)
+        cell_out = [self.stem1(s0)]
+        for j in range(1, self._depth):
+            prev = s0 if j == 1 else cell_out[-2]
+            cell_out.append(self.blocks[0][j](prev, cell_out[-1], alpha_dn_nm, alpha_dn, beta_dn))
+        for j in reversed(range(self._depth - 1)):
+            for i in range(1, self._depth - j):
+                ides = list(range(j, i + j))
+                gidx = [sum(range(k + j)) + j for k in range(1, i)]
+                parts = [cell_out[ides[0]]]
+                for k, g in enumerate(gidx):
+                    parts.append(cell_out[ides[k]] * gamma[g][0] + cell_out[ides[k + 1]] * gamma[g][1])
+                in0 = torch.cat(parts, dim=1)
+                cell_out[i + j] = self.blocks[i][j](in0, cell_out[i + j], alpha_up_nm, alpha_up, beta_up)
+        head = self.head_block[-1]
+        if self._supervision:
+            return [head(s0, ot, alpha_up_nm, alpha_up, beta_up) for ot in cell_out]
+        return [head(s0, cell_out[-1], alpha_up_nm, alpha_up, beta_up)]
+
+
+class NAS(nn.Module):
+    """Owner of the architecture parameters; same constructor as senas_search.py:117-120.
+
+    ``multi_gpus`` is accepted for signature compatibility only: the reference's in-process
+    replica path (:262-279) is broken as shipped; data parallelism here is one process per GPU
+    (``senas_b200.dp``), so ``device_ids`` is always ``[0]``.
+    """
+
+    def __init__(self, input_c, c, num_classes, depth, meta_node_num=4, use_sharing=True,
+                 double_down_channel=True, use_softmax_head=False, supervision=False, multi_gpus=False,
+                 device='cuda'):
+        super().__init__()
+        self._use_sharing, self._meta_node_num, self._depth = use_sharing, meta_node_num, depth
+        self.net = SenasSearch(input_c, c, num_classes, depth, meta_node_num, double_down_channel, supervision)
+        self.net.apply(weights_init)
+        self.device_ids = [0]
+        self._init_alphas()
+
+    def _init_alphas(self):
+        k = sum(2 + i for i in range(self._meta_node_num))
+        self.alphas_dn = nn.Parameter(1e-3 * torch.randn(k, len(DownOps)))
+        self.alphas_up = nn.Parameter(1e-3 * torch.randn(k, len(UpOps)))
+        self.alphas_dn_nm = nn.Parameter(1e-3 * torch.randn(k, len(NormOps)))
+        self.alphas_up_nm = self.alphas_dn_nm if self._use_sharing else nn.Parameter(
+            1e-3 * torch.randn(k, len(NormOps)))
+        self.betas_dn = nn.Parameter(1e-3 * torch.randn(k))
+        self.betas_up = nn.Parameter(1e-3 * torch.randn(k))
+        self.gamma = nn.Parameter(1e-3 * torch.randn(sum(range(self._depth - 1)), 2))
+        self._arch_parameters = [self.alphas_dn, self.alphas_up, self.alphas_dn_nm, self.alphas_up_nm,
+                                 self.betas_dn, self.betas_up, self.gamma]
+
+    def alphas_dict(self):
+        return {'alphas_dn': self.alphas_dn, 'alphas_dn_nm': self.alphas_dn_nm, 'alphas_up': self.alphas_up,
+                'alphas_up_nm': self.alphas_up_nm}
+
+    def betas_dict(self):
+        return {'betas_dn': self.betas_dn, 'betas_up': self.betas_up}
+
+    def load_params(self, alphas_dict, betas_dict):
+        """Key names as read by the reference (senas_search.py:170-176), including its quirk of
+        dropping ``gamma`` from the arch-parameter list."""
+        self.alphas_dn = alphas_dict['alphas_down']
+        self.alphas_up = alphas_dict['alphas_up']
+        self.alphas_dn_nm = alphas_dict['alphas_normal_down']
+        self.alphas_up_nm = alphas_dict['alphas_normal_up']
+        self.betas_dn = betas_dict['betas_down']
+        self.betas_up = betas_dict['betas_up']
+        self._arch_parameters = [self.alphas_dn, self.alphas_up, self.alphas_dn_nm, self.alphas_up_nm,
+                                 self.betas_dn, self.betas_up]
+
+    def arch_parameters(self):
+        return self._arch_parameters
+
+    def _beta_softmax(self, betas, detach=False):
+        """Per-node softmax segments exactly as the reference takes them (senas_search.py:212-216,
+        253-257): ``offset = len(list_of_segments)`` there, i.e. segment ``i`` is
+        ``betas[i : 2*i + 2]`` (overlapping windows), *not* the cumulative edge offset."""
+        segs = []
+        for i in range(self._meta_node_num):
+            off = len(segs)
+            s = F.softmax(betas[off:off + 2 + i], dim=-1)
+            segs.append(s.detach().cpu() if detach else s)
+        return torch.cat(segs, dim=0)
+
+    def genotype(self):
+        """senas_search.py:203-244 -- CPU index work on the softmaxed tables."""
+        sm = lambda t: F.softmax(t, dim=-1).detach().cpu()
+        a_dn_nm, a_dn, a_up_nm, a_up = sm(self.alphas_dn_nm), sm(self.alphas_dn), sm(self.alphas_up_nm), sm(
+            self.alphas_up)
+        b_dn, b_up = self._beta_softmax(self.betas_dn, True), self._beta_softmax(self.betas_up, True)
+        for j in range(a_dn.shape[0]):
+            a_dn_nm[j, :] = a_dn_nm[j, :] * b_dn[j].item()
+            a_dn[j, :] = a_dn[j, :] * b_dn[j].item()
+            a_up_nm[j, :] = a_up_nm[j, :] * b_up[j].item()
+            a_up[j, :] = a_up[j, :] * b_up[j].item()
+        parser = GenoParser(self._meta_node_num)
+        gene_down = parser.parse(a_dn_nm.numpy(), a_dn.numpy(), cell_type='down')
+        gene_up = parser.parse(a_up_nm.numpy(), a_up.numpy(), cell_type='up')
+        concat = range(2, self._meta_node_num + 2)
+        gamma = sm(self.gamma)
+        idx = torch.topk(gamma[:, 1], len(gamma) // 2, largest=False).indices
+        g = gamma.argmax(1).tolist()
+        g = [v if i not in idx else 0 for i, v in enumerate(g)]
+        path = [g[sum(range(i)): sum(range(i)) + i] for i in range(1, self._depth - 1)]
+        path = sum([(v[:v.index(1)] + [1] * len(v[v.index(1):])) if (1 in v) else v for v in path], [])
+        return Genotype(down=gene_down, down_concat=concat, up=gene_up, up_concat=concat, gamma=path)
+
+    def forward(self, x):
+        sm = lambda t: F.softmax(t, dim=-1)
+        return self.net(x, sm(self.alphas_dn_nm), sm(self.alphas_up_nm), sm(self.alphas_dn), sm(self.alphas_up),
+                        self._beta_softmax(self.betas_dn), self._beta_softmax(self.betas_up), sm(self.gamma))
+
+
+class Architecture(object):
+    """First-order DARTS step on the architecture parameters (senas_search.py:282-303)."""
+
+    def __init__(self, model, arch_optimizer, criterion):
+        self.model, self.optimizer, self.criterion = model, arch_optimizer, criterion
+
+    def step(self, input_valid, target_valid):
+        self.optimizer.zero_grad()
+        loss = self.criterion(self.model(input_valid), target_valid)
+        loss.backward()
+        self.optimizer.step()
