@@ -143,6 +143,11 @@ int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a);
 int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t senas_launch_count(void);
+/* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
+ * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
+ * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */
+int senas_profile(int on);
+int64_t senas_profile_dump(char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,8 @@ class BwdArgs(C.Structure):
 
 
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
-           'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_launch_count']
+           'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_launch_count', 'senas_profile',
+           'senas_profile_dump']
 
 
 def bind(path):
@@ -64,6 +65,9 @@ def bind(path):
     lib.senas_graph_forward.argtypes = [C.c_void_p, C.POINTER(FwdArgs)]
     lib.senas_graph_backward.argtypes = [C.c_void_p, C.POINTER(BwdArgs)]
     lib.senas_launch_count.restype = C.c_int64
+    lib.senas_profile.argtypes = [C.c_int]
+    lib.senas_profile_dump.argtypes = [C.c_char_p, C.c_int64]
+    lib.senas_profile_dump.restype = C.c_int64
     return lib
 
 
@@ -80,6 +84,19 @@ def get():
                 '(nvcc, sm_100a). senas_b200 has no PyTorch/CPU fallback for the MixedOp/Cell path.')
         _LIB = bind(LIB_PATH)
     return _LIB
+
+
+def profile_dump(lib=None):
+    """{family: dict(launches, ms, flops, bytes)} of the last senas_profile recording."""
+    lib = lib or get()
+    n = lib.senas_profile_dump(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.senas_profile_dump(buf, n + 1)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, fl, by = line.split()
+        out[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out
 
 
 def check(lib, rc):

@@ -460,6 +460,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
       a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
       a.wpw = (const float *)ed.param[k][6], a.partials = part;
       dim3 grid(cdiv(p.hw, 128), B);
+      SENAS_TAG("pw_fwd", 2.0 * B * p.hw * C * 8, 4.0 * B * p.hw * (C + 8));
       if (C == 32) {
         auto kern = pw_fwd_kernel<32>;
         SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
@@ -483,6 +484,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
 #define SENAS_AD_FWD(CC, KK)                                   \
   {                                                            \
     auto kern = adapter_fwd_kernel<CC, KK>;                    \
+    SENAS_TAG("adapter_fwd", 2.0 * B * p.hw * CC * 8, 4.0 * B * (ep.in_h * ep.in_w * CC + p.hw * 8)); \
     SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
   }
         const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
@@ -505,6 +507,8 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         a.w = (const float *)ed.param[k][0], a.ws_t = 1;
         conv_weight_strides(ed.op_type, C, t.k * t.k, DIR_FWD, &a.ws_k, &a.ws_n);
         a.partials = part, a.taps = geo.taps;
+        SENAS_TAG("conv_fwd", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
+                  4.0 * B * (ep.in_h * ep.in_w * C + p.hw * 8));
         if (launch_gather_any(a, geo, C, 8, B, c.stream)) return 1;
         break;
       }
@@ -517,6 +521,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         a.si = geo.si, a.so = geo.so, a.w = (const float *)ed.param[k][0], a.partials = c.scratch + t.part1_off;
         a.taps = geo.taps;
         dim3 grid(t.nblk1, B);
+        SENAS_TAG("dw_fwd", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C, 4.0 * B * (ep.in_h * ep.in_w * C + p.hw * C));
         if (C == 32) {
           auto kern = dw_fwd_kernel<32>;
           SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
@@ -566,18 +571,22 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
     if (p->n_bnA[s]) {
+      SENAS_TAG("bn_finalize", 0, 0);
       SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnA[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases,
                    c.B, a->training);
     }
     if (p->n_bnB[s]) {
       for (int e = 0; e < d.n_edges; ++e)
         if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, true)) return 1;
+      SENAS_TAG("bn_finalize", 0, 0);
       SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnB[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases,
                    c.B, a->training);
     }
     const int thr = std::min(1024, ((c.B * 8 + 31) / 32) * 32);
+    SENAS_TAG("node_coef", 0, 0);
     SENAS_LAUNCH(node_coef_kernel, dim3(1), dim3(thr), 0, c.stream, (const NodeDesc *)p->d_nodes, s, c.bases, a->alpha,
                  a->beta, c.B);
+    SENAS_TAG("node_combine", 0, 4.0 * c.B * p->hw * 8 * (1 + 5 * (s + 2)));
     SENAS_LAUNCH(node_combine_kernel, dim3(cdiv(p->hw, 128), c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes,
                  s, c.bases, d.node_relu);
   }
@@ -631,6 +640,7 @@ static int backward_edge(BwdCall &c, int e) {
 #define SENAS_AD_DX(CC, KK)                                    \
   {                                                            \
     auto kern = adapter_dx_kernel<CC, KK>;                     \
+    SENAS_TAG("adapter_dx", 2.0 * B * in_px * CC * 8, 4.0 * B * (in_px * CC + HW * 16)); \
     SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
   }
           if (C == 32 && kk == AD_IDENTITY) SENAS_AD_DX(32, AD_IDENTITY)
@@ -646,12 +656,14 @@ static int backward_edge(BwdCall &c, int e) {
 #define SENAS_AD_DW(CC, KK)                                    \
   {                                                            \
     auto kern = adapter_dw_kernel<CC, KK>;                     \
+    SENAS_TAG("adapter_dw", 2.0 * B * gpx * CC * 8, 4.0 * B * (in_px * CC + HW * 16)); \
     SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
   }
           if (kk == AD_IDENTITY) SENAS_AD_DW(32, AD_IDENTITY)
           else if (kk == AD_POOL) SENAS_AD_DW(32, AD_POOL)
           else SENAS_AD_DW(32, AD_UP)
           const int n = 8 * C;
+          SENAS_TAG("reduce", 0, 0);
           SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
                        (const float *)tmp, (int)(grid.x * B), n);
         }
@@ -670,6 +682,8 @@ static int backward_edge(BwdCall &c, int e) {
           a.si = geo.si, a.so = geo.so, a.w = (const float *)ed.param[k][0], a.ws_t = 1;
           conv_weight_strides(ed.op_type, C, T, DIR_DGRAD, &a.ws_k, &a.ws_n);
           a.partials = nullptr, a.taps = geo.taps;
+          SENAS_TAG("conv_dgrad", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
+                    4.0 * B * (ep.in_h * ep.in_w * C + HW * 16));
           if (launch_gather_any(a, geo, 8, C, B, c.stream)) return 1;
           c.touched[ed.src] = true;
         }
@@ -687,6 +701,7 @@ static int backward_edge(BwdCall &c, int e) {
 #define SENAS_WGRAD(KC, TPT)                                                             \
   {                                                                                      \
     auto kern = conv_wgrad_kernel<KC, TPT>;                                              \
+    SENAS_TAG("conv_wgrad", 2.0 * B * a.base_h * a.base_w * T * KC * 8, 4.0 * B * (ep.in_h * ep.in_w * KC + HW * 16)); \
     SENAS_LAUNCH(kern, dim3(nblk), dim3(KC * (T / TPT)), smem, c.stream, a);             \
   }
           if (C == 32 && t.k == 5) SENAS_WGRAD(32, 5)
@@ -696,6 +711,7 @@ static int backward_edge(BwdCall &c, int e) {
           int ws_ci, ws_co;
           conv_weight_strides(ed.op_type, C, T, DIR_FWD, &ws_ci, &ws_co);
           const int n = T * C * 8;
+          SENAS_TAG("reduce", 0, 0);
           SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, (const float *)tmp, nblk, T, C,
                        gp + ed.grad_off[k][0], 1, ws_ci, ws_co, geo.taps);
         }
@@ -712,6 +728,7 @@ static int backward_edge(BwdCall &c, int e) {
         dim3 grid(cdiv(HW, 128), B);
         if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
           SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
+        SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
         if (C == 32) {
           auto kern = pw_bwd_stats_kernel<32>;
           SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
@@ -719,9 +736,11 @@ static int backward_edge(BwdCall &c, int e) {
           auto kern = pw_bwd_stats_kernel<8>;
           SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
         }
+        SENAS_TAG("pw_bfin", 0, 0);
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)tmp, (int)(grid.x * B), C,
                      (float)B * (float)HW, a.g1, a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2],
                      gp + ed.grad_off[k][6]);
+        SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
         if (C == 32) {
           auto kern = pw_bwd_dz_kernel<32>;
           SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a, c.a->training);
@@ -739,6 +758,7 @@ static int backward_edge(BwdCall &c, int e) {
           w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g2(cdiv(w.base_h * w.base_w, 128 / (C / 4)), B);
+          SENAS_TAG("dw_dx", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + 2 * ep.in_h * ep.in_w * C));
           if (C == 32) {
             auto kern = dw_dx_kernel<32>;
             SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
@@ -754,6 +774,7 @@ static int backward_edge(BwdCall &c, int e) {
           w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g3(cdiv(w.base_h * w.base_w, w.chunk), B);
+          SENAS_TAG("dw_wgrad", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + ep.in_h * ep.in_w * C));
           if (C == 32) {
             auto kern = dw_wgrad_kernel<32>;
             SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
@@ -762,6 +783,7 @@ static int backward_edge(BwdCall &c, int e) {
             SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
           }
           const int n = C * T;
+          SENAS_TAG("reduce", 0, 0);
           SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
                        (const float *)tmp, (int)(g3.x * B), n);
         }
@@ -808,8 +830,10 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     const NodePlan &np = p->nodes[i];
     if (np.has_consumer && !c.touched[d.n_inputs + i])
       cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
+    SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
     SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
                  d.node_relu);
+    SENAS_TAG("node_bfin", 0, 0);
     SENAS_LAUNCH(node_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
     for (int e = 0; e < d.n_edges; ++e)
@@ -830,6 +854,51 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
 extern "C" const char *senas_version(void) { return "senas_b200 0.1 (sm_100a, fp32 exact path)"; }
 extern "C" const char *senas_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t senas_launch_count(void) { return g_launch_count; }
+
+// per-kernel-family timing: senas_profile(1) starts recording CUDA events around every launch,
+// senas_profile(0) stops; senas_profile_dump() synchronises the recorded events and returns one line
+// per family: "name launches total_ms algorithmic_flops algorithmic_bytes".
+extern "C" int senas_profile(int on) {
+#ifndef SENAS_EMU
+  if (on) {
+    for (auto &r : g_prof) cudaEventDestroy(r.e0), cudaEventDestroy(r.e1);
+    g_prof.clear();
+  }
+  g_prof_on = on != 0;
+#else
+  (void)on;
+#endif
+  return 0;
+}
+extern "C" int64_t senas_profile_dump(char *buf, int64_t cap) {
+  std::string out;
+#ifndef SENAS_EMU
+  struct Acc {
+    int64_t n = 0;
+    double ms = 0, flops = 0, bytes = 0;
+  };
+  std::map<std::string, Acc> acc;
+  for (auto &r : g_prof) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Acc &a = acc[r.name];
+    a.n++, a.ms += ms, a.flops += r.flops, a.bytes += r.bytes;
+  }
+  char line[256];
+  for (auto &kv : acc) {
+    snprintf(line, sizeof(line), "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms,
+             kv.second.flops, kv.second.bytes);
+    out += line;
+  }
+#endif
+  if (buf && cap > 0) {
+    const int64_t n = std::min<int64_t>((int64_t)out.size(), cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size();
+}
 
 extern "C" int senas_device_check(int device) {
 #ifdef SENAS_EMU

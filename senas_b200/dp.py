@@ -1,0 +1,83 @@
+"""Data-parallel search: one process per GPU, batch-sharded, gradients of the weights and of the
+architecture parameters (alpha/beta/gamma) all-reduced over NCCL (NVLink 5 / NVSwitch) in flat
+buckets that are launched from autograd hooks while backward is still running.
+
+Replaces the reference's in-process replica path (search/senas_search.py:262-279, broken as shipped,
+SURVEY.md section 2.2).  Semantics kept from it: BatchNorm statistics stay local to each replica; the
+loss is the global-batch loss (senas_b200.loss with ``group``), hence gradients are SUMMED.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    """Buckets follow reverse parameter order (head -> up cells -> down cells -> stem), i.e. roughly the
+    order in which backward produces gradients; arch parameters (which accumulate over every cell) go
+    into the last bucket."""
+
+    def __init__(self, params, arch_params=(), bucket_floats=1 << 19, group=None):
+        self.group = group
+        arch_ids = {id(p) for p in arch_params}
+        seen, ordered = set(), []
+        for p in reversed([p for p in params if p.requires_grad]):
+            if id(p) not in seen and id(p) not in arch_ids:
+                seen.add(id(p))
+                ordered.append(p)
+        buckets, cur, n = [], [], 0
+        for p in ordered:
+            cur.append(p)
+            n += p.numel()
+            if n >= bucket_floats:
+                buckets.append(cur)
+                cur, n = [], 0
+        if cur:
+            buckets.append(cur)
+        arch = [p for p in arch_params if p.requires_grad]
+        if arch:
+            buckets.append(list({id(p): p for p in arch}.values()))
+        self.buckets = buckets
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device) for b in buckets]
+        self.where = {}
+        for bi, b in enumerate(buckets):
+            for p in b:
+                self.where[id(p)] = bi
+        self.pending = [0] * len(buckets)
+        self.work = [None] * len(buckets)
+        self.expect = [len(b) for b in buckets]
+        self.hooks = [p.register_post_accumulate_grad_hook(self._hook) for b in buckets for p in b]
+        self.enabled = True
+
+    def _hook(self, p):
+        if not self.enabled:
+            return
+        bi = self.where[id(p)]
+        self.pending[bi] += 1
+        if self.pending[bi] == self.expect[bi]:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
+        torch._foreach_copy_(list(self.flat[bi].split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        self.work[bi] = dist.all_reduce(self.flat[bi], group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for every bucket (launching those whose hooks did not all fire, e.g. unused parameters)
+        and write the reduced gradients back.  Call after ``loss.backward()``, before clip / step."""
+        for bi, b in enumerate(self.buckets):
+            if self.work[bi] is None:
+                self._launch(bi)
+        for bi, b in enumerate(self.buckets):
+            self.work[bi].wait()
+            outs = self.flat[bi].split([p.numel() for p in b])
+            for p, o in zip(b, outs):
+                if p.grad is None:
+                    p.grad = o.view_as(p).clone()
+                else:
+                    p.grad.copy_(o.view_as(p))
+            self.work[bi], self.pending[bi] = None, 0
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Make every replica start from rank ``src``'s weights, arch parameters and BN buffers."""
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src, group=group)

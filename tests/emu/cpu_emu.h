@@ -195,6 +195,7 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
     }                                                                       \
     emu::launch((grid), (block), [=]() { kern(__VA_ARGS__); });             \
     ++g_launch_count;                                                       \
+    g_tag = "other";                                                        \
   } while (0)
 #define SENAS_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
 

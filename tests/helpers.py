@@ -23,7 +23,7 @@ def golden_names(prefix):
 
 
 def sub(g, prefix):
-    return {k[len(prefix):]: torch.from_numpy(np.ascontiguousarray(v)) for k, v in g.items() if k.startswith(prefix)}
+    return {k[len(prefix):]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith(prefix)}
 
 
 def max_err(a, b):

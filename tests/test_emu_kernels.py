@@ -1,0 +1,96 @@
+"""Kernel logic on the CPU emulator (tests/emu) against the reference's golden fixtures.
+
+The same kernel sources that nvcc compiles for sm_100a are compiled by g++ against a fiber-based
+emulation of the CUDA execution model; this catches indexing / reduction / math errors without a
+GPU.  It is NOT a product path (see tests/emu/cpu_emu.h); the GPU parity tests are in
+tests/test_gpu_parity.py and run the real library."""
+import sys
+import os
+
+import pytest
+import torch
+
+from helpers import cell_module, golden, golden_names, max_err, mixed_module, run_graph_raw, sub
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+import build_emu  # noqa: E402
+from senas_b200 import _lib  # noqa: E402
+from senas_b200.fused import GraphRunner  # noqa: E402
+
+TOL = 1e-4  # BASELINE.json: fp32 within 1e-4 relative
+
+
+@pytest.fixture(scope='module')
+def emu():
+    return _lib.bind(build_emu.build())
+
+
+def check(name, got, want, tol=TOL, report=None):
+    e = max_err(got, want)
+    if report is not None:
+        report.append((name, e))
+    assert e <= tol, f'{name}: rel err {e:.3e}'
+
+
+@pytest.mark.parametrize('name', golden_names('mixed_'))
+def test_mixed_op_emulated(emu, name):
+    g = golden(name)
+    m = mixed_module(g)
+    training = bool(g['meta'][4])
+    runner = GraphRunner([m._edge(0, 0)], n_inputs=1, n_nodes=1, node_relu=False, lib=emu)
+    gout = torch.from_numpy(g['gout']) if training else None
+    r = run_graph_raw(runner, [torch.from_numpy(g['x'])], torch.from_numpy(g['alpha']).view(1, 6), None, gout, training)
+    check('out', r['out'], g['out'])
+    if not training:
+        return
+    check('gx', r['g_ins'][0], g['gx'])
+    check('galpha', r['g_alpha'].view(-1), g['galpha'])
+    names = {id(p): n for n, p in m.named_parameters()}
+    want = sub(g, 'grad.')
+    for p, gp in zip(runner.params, r['g_params']):
+        check('grad.' + names[id(p)], gp, want[names[id(p)]])
+    after = sub(g, 'after.')
+    sd = m.state_dict()
+    for k, v in after.items():
+        check('after.' + k, sd[k], v, 1e-5)
+
+
+@pytest.mark.parametrize('name,cell_type', [('cell_down', 'down'), ('cell_up', 'up')])
+def test_cell_nodes_emulated(emu, name, cell_type):
+    """Node loop + concat through the emulated kernels; preprocess / post_process through torch."""
+    g = golden(name)
+    c = cell_module(g, cell_type)
+    in0 = torch.from_numpy(g['in0']).requires_grad_(True)
+    in1 = torch.from_numpy(g['in1']).requires_grad_(True)
+    wn, wc, betas = (torch.from_numpy(g[k]) for k in ('wn', 'wc', 'betas'))
+    p0 = c.preprocess0(in0)
+    p1 = c.preprocess1(in1)
+    edges = [op._edge(s, d) for op, s, d in zip(c._ops, c._srcs, c._dsts)]
+    runner = GraphRunner(edges, n_inputs=2, n_nodes=3, node_relu=True, lib=emu)
+    alpha = torch.where(c._norm_rows, wn, wc)
+    nhwc = lambda t: t.contiguous(memory_format=torch.channels_last)
+    ins = [nhwc(p0.detach()), nhwc(p1.detach())]
+    cat, saved = runner.forward(ins, alpha.contiguous(), betas.contiguous(), True)
+    cat_t = cat.detach().clone().requires_grad_(True)
+    out = c.post_process(cat_t)
+    check('out', out, g['out'])
+    out.backward(torch.from_numpy(g['gout']))
+    g_ins, g_alpha, g_beta, g_params = runner.backward(ins, alpha.contiguous(), betas.contiguous(), cat,
+                                                       nhwc(cat_t.grad), saved, True, [True, True])
+    p0.backward(g_ins[0])
+    p1.backward(g_ins[1])
+    check('gin0', in0.grad, g['gin0'])
+    check('gin1', in1.grad, g['gin1'])
+    check('gbetas', g_beta, g['gbetas'])
+    norm = c._norm_rows.view(-1)
+    check('gwn', g_alpha[norm], torch.from_numpy(g['gwn'])[norm])
+    check('gwc', g_alpha[~norm], torch.from_numpy(g['gwc'])[~norm])
+    names = {id(p): n for n, p in c.named_parameters()}
+    want = sub(g, 'grad.')
+    grads = [t.view(s) for t, s in zip(torch.split(g_params, runner.sizes), runner.shapes)]
+    for p, gp in zip(runner.params, grads):
+        check('grad.' + names[id(p)], gp, want[names[id(p)]])
+    sd = c.state_dict()
+    for k, v in sub(g, 'after.').items():
+        if k.startswith('_ops'):
+            check('after.' + k, sd[k], v, 1e-5)

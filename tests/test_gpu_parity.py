@@ -1,0 +1,185 @@
+"""Parity of the CUDA path (through the public MixedOp / Cell / NAS modules, i.e. through the C ABI)
+against the reference's golden fixtures and against the CPU oracle.  `-m gpu` only.
+
+Gates (BASELINE.json north_star): fp32 within 1e-4 relative (per tensor, max-abs error over max-abs
+value), index work (genotype) identical."""
+import numpy as np
+import pytest
+import torch
+
+import senas_b200
+import senas_oracle as oracle
+from helpers import OP_BY_ID, OP_NAME, cell_module, golden, golden_names, max_err, mixed_module, sub
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = 'cuda:0'
+
+
+def check(name, got, want, tol=TOL):
+    e = max_err(got, want)
+    assert e <= tol, f'{name}: rel err {e:.3e} > {tol}'
+
+
+def test_library_is_the_cuda_build():
+    from senas_b200 import _lib
+    lib = _lib.get()
+    assert b'sm_100a' in lib.senas_version()
+    assert lib.senas_device_check(0) == 0
+
+
+@pytest.mark.parametrize('name', golden_names('mixed_'))
+def test_mixed_op_golden(name):
+    g = golden(name)
+    m = mixed_module(g).to(DEV)
+    training = bool(g['meta'][4])
+    x = torch.from_numpy(g['x']).to(DEV).requires_grad_(True)
+    alpha = torch.from_numpy(g['alpha']).to(DEV).requires_grad_(True)
+    n0 = senas_b200._lib.get().senas_launch_count()
+    out = m(x, alpha, alpha)
+    assert senas_b200._lib.get().senas_launch_count() > n0, 'no kernel of libsenas_b200 was launched'
+    check('out', out, g['out'])
+    if not training:
+        return
+    out.backward(torch.from_numpy(g['gout']).to(DEV))
+    check('gx', x.grad, g['gx'])
+    check('galpha', alpha.grad, g['galpha'])
+    want = sub(g, 'grad.')
+    for n, p in m.named_parameters():
+        check('grad.' + n, p.grad, want[n])
+    sd = m.state_dict()
+    for k, v in sub(g, 'after.').items():
+        check('after.' + k, sd[k], v, 1e-5)
+
+
+@pytest.mark.parametrize('name,cell_type', [('cell_down', 'down'), ('cell_up', 'up')])
+def test_cell_golden(name, cell_type):
+    g = golden(name)
+    c = cell_module(g, cell_type).to(DEV)
+    t = {k: torch.from_numpy(g[k]).to(DEV).requires_grad_(True) for k in ('in0', 'in1', 'wn', 'wc', 'betas')}
+    out = c(t['in0'], t['in1'], t['wn'], t['wc'], t['betas'])
+    check('out', out, g['out'])
+    out.backward(torch.from_numpy(g['gout']).to(DEV))
+    norm = c._norm_rows.view(-1).cpu()
+    check('gin0', t['in0'].grad, g['gin0'])
+    check('gin1', t['in1'].grad, g['gin1'])
+    check('gbetas', t['betas'].grad, g['gbetas'])
+    check('gwn', t['wn'].grad.cpu()[norm], torch.from_numpy(g['gwn'])[norm])
+    check('gwc', t['wc'].grad.cpu()[~norm], torch.from_numpy(g['gwc'])[~norm])
+    want = sub(g, 'grad.')
+    for n, p in c.named_parameters():
+        check('grad.' + n, p.grad, want[n])
+    sd = c.state_dict()
+    for k, v in sub(g, 'after.').items():
+        check('after.' + k, sd[k], v, 1e-5)
+
+
+@pytest.mark.parametrize('op_id,c_in,B,H,W', [(3, 32, 4, 64, 64), (3, 8, 4, 64, 48), (2, 32, 4, 64, 64),
+                                               (1, 32, 3, 32, 32), (3, 8, 2, 8, 8), (1, 32, 1, 1, 1),
+                                               (2, 32, 1, 1, 3)])
+def test_mixed_op_vs_oracle(op_id, c_in, B, H, W):
+    """Seeded inputs at sizes the oracle finishes in seconds, including 1-pixel and ragged maps."""
+    torch.manual_seed(100 + op_id + c_in + H)
+    m = senas_b200.MixedOp(c_in, 8, OP_BY_ID[op_id])
+    m.apply(senas_b200.weights_init)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    store = oracle.clone_store(m.state_dict())
+    x = torch.randn(B, c_in, H, W)
+    alpha = torch.softmax(torch.randn(6), -1)
+    xo, ao = x.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], xo, ao, True)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    m = m.to(DEV)
+    xg, ag = x.to(DEV).requires_grad_(True), alpha.to(DEV).requires_grad_(True)
+    out = m(xg, ag, ag)
+    out.backward(gout.to(DEV))
+    single_px = B * ref.shape[2] * ref.shape[3] == 1  # BN over one value: var = 0, everything degenerate
+    tol = 5e-3 if single_px else TOL
+    check('out', out, ref.detach(), tol)
+    if not single_px:
+        check('gx', xg.grad, xo.grad)
+        check('galpha', ag.grad, ao.grad)
+        for n, p in m.named_parameters():
+            check('grad.' + n, p.grad, store[n].grad)
+
+
+def test_fixed_seed_search_genotype():
+    """Two search steps of the whole supernet from seed 0 on the GPU path: loss trajectory, alpha tables
+    and the derived genotype against the reference run (tests/golden/nas_search_2steps.npz)."""
+    g = golden('nas_search_2steps')
+    B, H, seed, steps = [int(v) for v in g['meta']]
+    torch.manual_seed(seed)
+    m = senas_b200.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
+                       supervision=False).to(DEV)
+    w_opt = torch.optim.SGD(m.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4)
+    a_opt = torch.optim.Adam(m.arch_parameters(), lr=1e-4, betas=(0.5, 0.999), weight_decay=1e-3)
+    crit = lambda outs, y: oracle.dice_ce_loss(outs[-1], y)  # loss is outside the hot path: same torch ops
+    arch = senas_b200.Architecture(m, a_opt, crit)
+    gen = torch.Generator().manual_seed(1234)
+    losses = []
+    m.train()
+    for s in range(steps):
+        xt = torch.randn(B, 1, H, H, generator=gen).to(DEV)
+        yt = (torch.rand(B, H, H, generator=gen) > 0.8).long().to(DEV)
+        xv = torch.randn(B, 1, H, H, generator=gen).to(DEV)
+        yv = (torch.rand(B, H, H, generator=gen) > 0.8).long().to(DEV)
+        arch.step(xv, yv)
+        if s == 0:
+            for n in ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma'):
+                check('archgrad.' + n, getattr(m, n).grad, g['archgrad.' + n], 2e-3)
+        w_opt.zero_grad()
+        loss = crit(m(xt), yt)
+        losses.append(loss.item())
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+        w_opt.step()
+    assert np.allclose(losses, g['losses'], rtol=1e-4), (losses, g['losses'])
+    for n in ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma'):
+        assert (getattr(m, n).detach().cpu() - torch.from_numpy(g['arch.' + n])).abs().max() < 2e-6, n
+    assert repr(m.genotype()) == str(g['genotype'])
+
+
+def test_bit_reproducible():
+    """Fixed-order reductions, no float atomics: two runs give identical bits."""
+    torch.manual_seed(3)
+    c = senas_b200.Cell(3, 1, 32, 32, 32, 'up').to(DEV)
+    in0, in1 = torch.randn(2, 32, 32, 32, device=DEV), torch.randn(2, 32, 16, 16, device=DEV)
+    wn, wc = torch.softmax(torch.randn(9, 6, device=DEV), -1), torch.softmax(torch.randn(9, 6, device=DEV), -1)
+    b = torch.softmax(torch.randn(9, device=DEV), -1)
+    outs = []
+    for _ in range(2):
+        c.zero_grad()
+        a, bb = in0.clone().requires_grad_(True), in1.clone().requires_grad_(True)
+        o = c(a, bb, wn, wc, b)
+        o.square().sum().backward()
+        outs.append((o.detach().clone(), a.grad.clone(), [p.grad.clone() for p in c.parameters()]))
+    # running stats moved between the runs, outputs in train mode do not depend on them
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert all(torch.equal(x, y) for x, y in zip(outs[0][2], outs[1][2]))
+
+
+def test_full_size_linearity_in_alpha():
+    """BASELINE size (batch 16, 32x256x256): with batch statistics, out is linear in the alpha row:
+    out(a1 + a2) == out(a1) + out(a2), and a one-hot on 'none' gives the constant BN bias."""
+    torch.manual_seed(5)
+    m = senas_b200.MixedOp(32, 8, OP_BY_ID[3]).to(DEV)
+    m._ops[1].norm.bias.data.normal_()
+    x = torch.randn(16, 32, 256, 256, device=DEV)
+    a1, a2 = torch.rand(6, device=DEV), torch.rand(6, device=DEV)
+    with torch.no_grad():
+        o1, o2, o12 = m(x, a1, a1), m(x, a2, a2), m(x, a1 + a2, a1 + a2)
+        assert max_err(o12, o1 + o2) < 1e-5
+        onehot = torch.zeros(6, device=DEV)
+        onehot[1] = 1.0
+        o = m(x, onehot, onehot)
+        assert max_err(o, m._ops[1].norm.bias.view(1, 8, 1, 1).expand_as(o)) < 1e-6
+
+
+def test_no_cpu_fallback():
+    m = senas_b200.MixedOp(32, 8, OP_BY_ID[3])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.randn(1, 32, 8, 8), torch.ones(6) / 6, torch.ones(6) / 6)
