@@ -168,6 +168,7 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.get()
     _lib.check(lib, lib.senas_device_check(local_rank))
     torch.backends.cudnn.benchmark = True  # as experiments/search_arc.py:72 (stems / pre / post convs)
+    senas_b200.exact_fp32()                # fp32 mode: no TF32 anywhere
 
     B, size = args.batch, args.size
     torch.manual_seed(0)

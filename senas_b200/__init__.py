@@ -12,3 +12,12 @@ from .supernet import Head, SenasSearch, NAS, Architecture  # noqa: F401
 from .build import build  # noqa: F401
 
 __version__ = '0.1.0'
+
+
+def exact_fp32():
+    """fp32 mode gate (1e-4 relative vs the reference): the fused MixedOp/Cell kernels are plain fp32
+    FMA already; this turns off cuDNN/cuBLAS TF32 for the stock-PyTorch blocks around them (stems,
+    ShrinkBlock / RectifyBlock convs), which PyTorch enables by default for convolutions."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
