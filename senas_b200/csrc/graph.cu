@@ -121,13 +121,14 @@ static Geo make_geo(int k, int dil, int op, int dir) {
 // ------------------------------------------------------------------------------------------------
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
 
 struct TermPlan {
   int kind = 0, k = 0, dil = 1;
   bool has_y = false, owns_y = false;
   int64_t y_off = -1, z_off = -1;
   int64_t mean_off = -1, istd_off = -1, mean1_off = -1, istd1_off = -1, ysum_off = -1, se_off = -1;
-  int64_t part_off = -1, part1_off = -1;
+  int64_t part_off = -1, part1_off = -1, psum_off = -1, psum1_off = -1;
   int nblk = 0, nblk1 = 0;
   int64_t scale_off = -1, coef_off = -1;
 };
@@ -136,7 +137,8 @@ struct EdgePlan {
   TermPlan t[SENAS_MAX_CAND];
 };
 struct NodePlan {
-  int64_t bias_off, gm_off, dnode_off, bpart_off;
+  int64_t bias_off, gm_off, dnode_off, bpart_off, bsum_off;
+  int nterms;
   int nblk;
   bool has_consumer;
 };
@@ -215,12 +217,12 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         case SENAS_KIND_IDENTITY:
           t.has_y = true, t.owns_y = (C != 8);
           t.nblk = nblk_px;
-          if (C != 8) tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * nblk_px * 8 * C);
+          if (C != 8) tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(HW, 128 * kPxTilesPerBlock) * 8 * C);
           break;
         case SENAS_KIND_AVG_POOL:
         case SENAS_KIND_UP_SAMPLE:
           t.has_y = t.owns_y = true, t.nblk = nblk_px;
-          tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(std::max(HW, ep.in_h * ep.in_w), 128) * 8 * C);
+          tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(std::max(HW, ep.in_h * ep.in_w), 128 * kPxTilesPerBlock) * 8 * C);
           break;
         case SENAS_KIND_CONV:
         case SENAS_KIND_SE_CONV: {
@@ -228,7 +230,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW);
-          tmp_need = std::max<int64_t>(tmp_need, (int64_t)296 * T * C * 8);
+          tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
           break;
         }
@@ -240,9 +242,9 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.nblk = nblk_px;
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
-          t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C);
-          const int64_t pw_tmp = (int64_t)B * nblk_px * 10 * C + 4 * C;
-          const int64_t dw_tmp = (int64_t)B * cdiv(bh * bw, 256) * C * T;
+          t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C), t.psum1_off = take(sc, (int64_t)B * 2 * C);
+          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 128 * kPxTilesPerBlock) * 10 * C + 16 * C;
+          const int64_t dw_tmp = (int64_t)B * cdiv(bh * bw, kDwChunk) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           break;
         }
@@ -251,7 +253,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           SENAS_FAIL("edge %d candidate %d: unknown kind %d", e, k, t.kind);
       }
       if (t.owns_y) t.y_off = take(sv, (int64_t)B * HW * 8);
-      if (t.has_y) t.part_off = take(sc, (int64_t)B * t.nblk * 16);
+      if (t.has_y) t.part_off = take(sc, (int64_t)B * t.nblk * 16), t.psum_off = take(sc, (int64_t)B * 16);
     }
   }
   p->nodes.resize(d.n_nodes);
@@ -272,6 +274,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     np.gm_off = take(sc, (int64_t)B * HW * 8);
     np.dnode_off = np.has_consumer ? take(sc, (int64_t)B * HW * 8) : -1;
     np.bpart_off = take(sc, (int64_t)B * nblk_px * (1 + nterms) * 8);
+    np.bsum_off = take(sc, (int64_t)B * (1 + nterms) * 8);
+    np.nterms = nterms;
   }
   p->tmp_off = take(sc, tmp_need);
   p->tmp_floats = tmp_need;
@@ -296,6 +300,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         b.C = 8, b.nblk = t.nblk, b.zero_input = t.kind == SENAS_KIND_NONE;
         b.count_per_sample = (float)HW;
         b.part_off = t.part_off, b.mean_off = t.mean_off, b.istd_off = t.istd_off, b.ysum_off = t.ysum_off;
+        b.psum_off = t.psum_off;
         b.gamma = (float *)ed.param[k][bs], b.beta = (float *)ed.param[k][bs + 1];
         b.rmean = (float *)ed.param[k][bs + 2], b.rvar = (float *)ed.param[k][bs + 3];
         b.nbt = (int64_t *)ed.param[k][bs + 4];
@@ -307,6 +312,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Bv.push_back(b);
           BnDesc b1 = b;
           b1.C = ed.c_in, b1.nblk = t.nblk1, b1.part_off = t.part1_off, b1.mean_off = t.mean1_off;
+          b1.psum_off = t.psum1_off;
           b1.istd_off = t.istd1_off, b1.ysum_off = -1;
           b1.gamma = (float *)ed.param[k][1], b1.beta = (float *)ed.param[k][2], b1.rmean = (float *)ed.param[k][3];
           b1.rvar = (float *)ed.param[k][4], b1.nbt = (int64_t *)ed.param[k][5];
@@ -326,7 +332,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     memset(&nd, 0, sizeof(nd));
     const NodePlan &np = p->nodes[i];
     nd.node = i, nd.bias_off = np.bias_off, nd.gm_off = np.gm_off, nd.dnode_off = np.dnode_off;
-    nd.bpart_off = np.bpart_off, nd.nblk = np.nblk, nd.hw = HW;
+    nd.bpart_off = np.bpart_off, nd.bsum_off = np.bsum_off, nd.nblk = np.nblk, nd.hw = HW;
     for (int e = 0; e < d.n_edges; ++e) {
       const senas_edge_desc_t &ed = d.edge[e];
       if (ed.dst != i) continue;
@@ -371,7 +377,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static const int kPersistBlocks = 296;
+static const int kPersistBlocks = 148 * 6;
 
 template <typename K>
 static void allow_smem(K kern, size_t bytes) {
@@ -571,15 +577,19 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
     if (p->n_bnA[s]) {
+      SENAS_TAG("bn_reduce", 0, 0);
+      SENAS_LAUNCH(bn_reduce_kernel, dim3(p->n_bnA[s], c.B), dim3(256), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases);
       SENAS_TAG("bn_finalize", 0, 0);
-      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnA[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases,
+      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnA[s]), dim3(64), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases,
                    c.B, a->training);
     }
     if (p->n_bnB[s]) {
       for (int e = 0; e < d.n_edges; ++e)
         if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, true)) return 1;
+      SENAS_TAG("bn_reduce", 0, 0);
+      SENAS_LAUNCH(bn_reduce_kernel, dim3(p->n_bnB[s], c.B), dim3(256), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases);
       SENAS_TAG("bn_finalize", 0, 0);
-      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnB[s]), dim3(128), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases,
+      SENAS_LAUNCH(bn_finalize_kernel, dim3(p->n_bnB[s]), dim3(64), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases,
                    c.B, a->training);
     }
     const int thr = std::min(1024, ((c.B * 8 + 31) / 32) * 32);
@@ -652,7 +662,7 @@ static int backward_edge(BwdCall &c, int e) {
         }
         if (a.w != nullptr && ed.grad_off[k][0] >= 0) {
           const int gpx = kk == AD_POOL ? HW : in_px;
-          dim3 grid(cdiv(gpx, 128), B);
+          dim3 grid(cdiv(gpx, 128 * kPxTilesPerBlock), B);
 #define SENAS_AD_DW(CC, KK)                                    \
   {                                                            \
     auto kern = adapter_dw_kernel<CC, KK>;                     \
@@ -664,8 +674,8 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_AD_DW(32, AD_UP)
           const int n = 8 * C;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
-                       (const float *)tmp, (int)(grid.x * B), n);
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, c.stream, (const float *)tmp,
+                       gp + ed.grad_off[k][0], (int)(grid.x * B), n);
         }
         break;
       }
@@ -712,7 +722,7 @@ static int backward_edge(BwdCall &c, int e) {
           conv_weight_strides(ed.op_type, C, T, DIR_FWD, &ws_ci, &ws_co);
           const int n = T * C * 8;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, (const float *)tmp, nblk, T, C,
+          SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 32)), dim3(256), 0, c.stream, (const float *)tmp, nblk, T, C,
                        gp + ed.grad_off[k][0], 1, ws_ci, ws_co, geo.taps);
         }
         break;
@@ -720,26 +730,29 @@ static int backward_edge(BwdCall &c, int e) {
       case SENAS_KIND_DEPSEP: {
         PwBwdArgs a;
         memset(&a, 0, sizeof(a));
-        float *coef1 = tmp + (int64_t)B * cdiv(HW, 128) * 10 * C;
+        const int nblk_pw = cdiv(HW, 128 * kPxTilesPerBlock);
+        float *sums1 = tmp + (int64_t)B * nblk_pw * 10 * C, *coef1 = sums1 + 12 * C;
         a.gm = gm, a.y = y, a.z = c.saved + t.z_off, a.hw = HW, a.batch = B, a.coefA = cA, a.coefB = cB, a.coefC = cC;
         a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
         a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
         a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1;
-        dim3 grid(cdiv(HW, 128), B);
+        dim3 grid(cdiv(HW, 128), B), grid_st(nblk_pw, B);
         if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
           SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
         if (C == 32) {
           auto kern = pw_bwd_stats_kernel<32>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+          SENAS_LAUNCH(kern, grid_st, dim3(128), 0, c.stream, a);
         } else {
           auto kern = pw_bwd_stats_kernel<8>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+          SENAS_LAUNCH(kern, grid_st, dim3(128), 0, c.stream, a);
         }
+        SENAS_TAG("reduce", 0, 0);
+        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, 32), 1), dim3(256), 0, c.stream, (const float *)tmp, sums1,
+                     (int)(nblk_pw * B), 10 * C);
         SENAS_TAG("pw_bfin", 0, 0);
-        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)tmp, (int)(grid.x * B), C,
-                     (float)B * (float)HW, a.g1, a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2],
-                     gp + ed.grad_off[k][6]);
+        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)sums1, C, (float)B * (float)HW, a.g1,
+                     a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
         if (C == 32) {
           auto kern = pw_bwd_dz_kernel<32>;
@@ -770,22 +783,25 @@ static int backward_edge(BwdCall &c, int e) {
         }
         {
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
-          w.x = x, w.x_ld = x_ld, w.partials = tmp, w.batch = B, w.chunk = 256;
+          w.x = x, w.x_ld = x_ld, w.partials = tmp, w.batch = B, w.chunk = kDwChunk;
           w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g3(cdiv(w.base_h * w.base_w, w.chunk), B);
           SENAS_TAG("dw_wgrad", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + ep.in_h * ep.in_w * C));
-          if (C == 32) {
-            auto kern = dw_wgrad_kernel<32>;
-            SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
-          } else {
-            auto kern = dw_wgrad_kernel<8>;
-            SENAS_LAUNCH(kern, g3, dim3(C * T), 0, c.stream, w);
-          }
+#define SENAS_DWW(CC, TT)                                      \
+  {                                                            \
+    auto kern = dw_wgrad_kernel<CC, TT>;                       \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+  }
+          if (C == 32 && T == 25) SENAS_DWW(32, 25)
+          else if (C == 32 && T == 9) SENAS_DWW(32, 9)
+          else if (C == 8 && T == 25) SENAS_DWW(8, 25)
+          else if (C == 8 && T == 9) SENAS_DWW(8, 9)
+          else SENAS_FAIL("dw wgrad: unsupported c_in %d k %d", C, t.k);
           const int n = C * T;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(reduce_partials_kernel, dim3(cdiv(n, 128)), dim3(128), 0, c.stream, gp + ed.grad_off[k][0],
-                       (const float *)tmp, (int)(g3.x * B), n);
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, c.stream, (const float *)tmp,
+                       gp + ed.grad_off[k][0], (int)(g3.x * B), n);
         }
         break;
       }
@@ -833,6 +849,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
     SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
                  d.node_relu);
+    {
+      const int V = (1 + np.nterms) * 8;
+      SENAS_TAG("reduce", 0, 0);
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(V, 32), c.B), dim3(256), 0, c.stream,
+                   (const float *)(c.scratch + np.bpart_off), c.scratch + np.bsum_off, np.nblk, V);
+    }
     SENAS_TAG("node_bfin", 0, 0);
     SENAS_LAUNCH(node_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);

@@ -245,6 +245,9 @@ __global__ void conv_wgrad_kernel(WgradArgs a) {
   for (int j = 0; j < TPT; ++j)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  int tdy[TPT], tdx[TPT], tph[TPT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) tdy[j] = a.taps.dy[tg * TPT + j], tdx[j] = a.taps.dx[tg * TPT + j], tph[j] = a.taps.phase[tg * TPT + j];
   const int tiles = a.tiles_x * a.tiles_y, total = tiles * a.batch;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int n = item / tiles, tile = item - n * tiles;
@@ -274,18 +277,22 @@ __global__ void conv_wgrad_kernel(WgradArgs a) {
       s_lo[i] = lo, s_hi[i] = hi;
     }
     __syncthreads();
+#pragma unroll 2
     for (int b = 0; b < kTileH * kTileW; ++b) {
       const int ty = b / kTileW, tx = b - ty * kTileW;
       const int by = by0 + ty, bx = bx0 + tx;
-      if (by >= a.base_h || bx >= a.base_w) continue;
+      const bool bok = by < a.base_h && bx < a.base_w;
+      float xv_[TPT];
+#pragma unroll
+      for (int j = 0; j < TPT; ++j) {  // all loads of this pixel first
+        const int iy = by * a.si + tdy[j], ix = bx * a.si + tdx[j];
+        const bool ok = bok && iy >= 0 && iy < a.x_h && ix >= 0 && ix < a.x_w;
+        xv_[j] = ok ? __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld + ci) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < TPT; ++j) {
-        const int t = tg * TPT + j;
-        const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t];
-        if (iy < 0 || iy >= a.x_h || ix < 0 || ix >= a.x_w) continue;
-        const float xv = __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld + ci);
-        const int ph = a.taps.phase[t];
-        const int idx = (ty * a.so + (ph >> 1)) * otw + tx * a.so + (ph & 1);
+        const float xv = xv_[j];
+        const int idx = (ty * a.so + (tph[j] >> 1)) * otw + tx * a.so + (tph[j] & 1);
         const float4 lo = s_lo[idx], hi = s_hi[idx];
         acc[j][0] = fmaf(xv, lo.x, acc[j][0]);
         acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
@@ -308,24 +315,39 @@ __global__ void conv_wgrad_kernel(WgradArgs a) {
   }
 }
 
-// dst[widx_t*ws_t + ci*ws_k + co*ws_n] = sum_blk partials[blk][t][ci][co]
-__global__ void wgrad_reduce_kernel(const float *partials, int nblk, int T, int KC, float *dst, int ws_t, int ws_k,
-                                    int ws_n, TapTable taps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, total = T * KC * 8;
-  if (i >= total) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[(int64_t)b * total + i];
-  const int co = i & 7, ci = (i >> 3) % KC, t = i / (8 * KC);
-  dst[(int64_t)taps.widx[t] * ws_t + (int64_t)ci * ws_k + (int64_t)co * ws_n] = s;
+// Sum `rows` rows of length V (fixed order): block = 256 threads = 8 warps x 32 consecutive columns; warp w takes
+// rows w, w+8, ...; the 8 partial sums are combined in warp order.  Returns the column sum in warp 0's lanes.
+SENAS_DEVFN float block_rows_sum(const float *src, int rows, int V, int col) {
+  __shared__ float s_rs[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float r = 0.f;
+  if (col < V)
+    for (int b = warp; b < rows; b += 8) r += src[(int64_t)b * V + col];
+  __syncthreads();
+  s_rs[warp][lane] = r;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0)
+    for (int w = 0; w < 8; ++w) t += s_rs[w][lane];
+  return t;
 }
 
-// dst[i] = sum_blk src[blk*n + i]
-__global__ void reduce_partials_kernel(float *dst, const float *src, int nblk, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += src[(int64_t)b * n + i];
-  dst[i] = s;
+// dst[group][V] = sum over rows of src[group][rows][V];  grid = (ceil(V/32), groups), block = 256
+__global__ void __launch_bounds__(256) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float t = block_rows_sum(src + (int64_t)blockIdx.y * rows * V, rows, V, col);
+  if (threadIdx.x < 32 && col < V) dst[(int64_t)blockIdx.y * V + col] = t;
+}
+
+// dst[widx_t*ws_t + ci*ws_k + co*ws_n] = sum_blk partials[blk][t][ci][co];  grid = ceil(T*KC*8/32), block = 256
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *partials, int nblk, int T, int KC, float *dst,
+                                                           int ws_t, int ws_k, int ws_n, TapTable taps) {
+  const int total = T * KC * 8, i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = block_rows_sum(partials, nblk, total, i);
+  if (threadIdx.x < 32 && i < total) {
+    const int co = i & 7, ci = (i >> 3) % KC, t = i / (8 * KC);
+    dst[(int64_t)taps.widx[t] * ws_t + (int64_t)ci * ws_k + (int64_t)co * ws_n] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,6 +493,7 @@ SENAS_DEVFN int pool_cnt(int o, int n_in) {
 }
 
 enum { AD_IDENTITY = 1, AD_POOL = 2, AD_UP = 3 };
+constexpr int kPxTilesPerBlock = 8;  // 128-pixel tiles per block in the pixel-wise weight-gradient kernels
 
 struct AdapterArgs {
   const float *x;
@@ -681,12 +704,17 @@ __global__ void __launch_bounds__(128) adapter_dw_kernel(AdapterBwdArgs a) {
   __shared__ float s_s[128][9];
   const int tid = threadIdx.x, n = blockIdx.y;
   const int gh = (KIND == AD_POOL) ? a.o_h : a.x_h, gw = (KIND == AD_POOL) ? a.o_w : a.x_w;
-  const int p = blockIdx.x * 128 + tid;
+  float racc[(8 * C + 127) / 128];
+#pragma unroll
+  for (int i = 0; i < (8 * C + 127) / 128; ++i) racc[i] = 0.f;
+  for (int tile = 0; tile < kPxTilesPerBlock; ++tile) {
+  const int p = (blockIdx.x * kPxTilesPerBlock + tile) * 128 + tid;
   float av[C], s[8];
 #pragma unroll
   for (int c = 0; c < C; ++c) av[c] = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  __syncthreads();
   if (p < gh * gw) {
     const int py = p / gw, px = p - py * gw;
     const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld;
@@ -703,13 +731,15 @@ __global__ void __launch_bounds__(128) adapter_dw_kernel(AdapterBwdArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_s[tid][j] = s[j];
   __syncthreads();
-  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 8 * C;
-  for (int o = tid; o < 8 * C; o += 128) {
+  for (int o = tid, i = 0; o < 8 * C; o += 128, ++i) {
     const int co = o / C, ci = o - co * C;
-    float r = 0.f;
+    float r = racc[i];
     for (int q = 0; q < 128; ++q) r = fmaf(s_s[q][co], s_a[q][ci], r);
-    out[o] = r;
+    racc[i] = r;
   }
+  }
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 8 * C;
+  for (int o = tid, i = 0; o < 8 * C; o += 128, ++i) out[o] = racc[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,37 +762,50 @@ struct BnDesc {
   float count_per_sample;
   float pad2;
   int64_t part_off;                   // scratch: [B][nblk][2C]
+  int64_t psum_off;                   // scratch: [B][2C] per-sample sums (stage 1 -> stage 2)
   int64_t mean_off, istd_off;         // saved
   int64_t ysum_off;                   // saved [B][C], -1 when not needed
   float *gamma, *beta, *rmean, *rvar;
   int64_t *nbt;
 };
 
-__global__ void __launch_bounds__(128) bn_finalize_kernel(const BnDesc *descs, Bases bases, int batch, int training) {
+// stage 1: per-sample sums.  grid = (instances, batch), block = 256: thread = (row group g, value j)
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const BnDesc *descs, Bases bases) {
+  const BnDesc d = descs[blockIdx.x];
+  if (d.zero_input) return;
+  __shared__ float s_g[256];
+  float *scratch = bases.p[SP_SCRATCH];
+  const int tid = threadIdx.x, n = blockIdx.y, V = 2 * d.C, G = 256 / V, j = tid % V, g = tid / V;
+  const float *part = scratch + d.part_off + (int64_t)n * d.nblk * V;
+  float r = 0.f;
+  for (int b = g; b < d.nblk; b += G) r += part[(int64_t)b * V + j];
+  s_g[tid] = r;
+  __syncthreads();
+  if (tid < V) {
+    float t = 0.f;
+    for (int gg = 0; gg < G; ++gg) t += s_g[gg * V + tid];
+    scratch[d.psum_off + (int64_t)n * V + tid] = t;
+  }
+}
+
+// stage 2: one block per BN instance
+__global__ void __launch_bounds__(64) bn_finalize_kernel(const BnDesc *descs, Bases bases, int batch, int training) {
   const BnDesc d = descs[blockIdx.x];
   float *saved = bases.p[SP_SAVED], *scratch = bases.p[SP_SCRATCH];
   __shared__ double s_tot[64];
-  __shared__ float s_grp[128];
-  const int tid = threadIdx.x, V = 2 * d.C, G = 128 / V, j = tid % V, g = tid / V;
-  if (tid < V) s_tot[tid] = 0.0;
-  __syncthreads();
-  if (!d.zero_input) {
-    const float *part = scratch + d.part_off;
-    for (int n = 0; n < batch; ++n) {
-      float r = 0.f;
-      if (g < G)
-        for (int b = g; b < d.nblk; b += G) r += part[((int64_t)n * d.nblk + b) * V + j];
-      s_grp[tid] = r;
-      __syncthreads();
-      if (tid < V) {
-        float t = 0.f;
-        for (int gg = 0; gg < G; ++gg) t += s_grp[gg * V + tid];
-        s_tot[tid] += (double)t;
-        if (d.ysum_off >= 0 && tid < d.C) saved[d.ysum_off + (int64_t)n * d.C + tid] = t;
+  const int tid = threadIdx.x, V = 2 * d.C;
+  if (tid < V) {
+    double t = 0.0;
+    if (!d.zero_input) {
+      for (int n = 0; n < batch; ++n) {
+        const float v = scratch[d.psum_off + (int64_t)n * V + tid];
+        t += (double)v;
+        if (d.ysum_off >= 0 && tid < d.C) saved[d.ysum_off + (int64_t)n * d.C + tid] = v;
       }
-      __syncthreads();
     }
+    s_tot[tid] = t;
   }
+  __syncthreads();
   if (tid < d.C) {
     const double cnt = (double)d.count_per_sample * batch;
     const double mean = s_tot[tid] / cnt;
@@ -805,6 +848,7 @@ struct NodeDesc {
   int64_t gm_off;       // scratch [B][HW][8]
   int64_t dnode_off;    // scratch [B][HW][8], -1 when the node feeds no edge
   int64_t bpart_off;    // scratch [B][nblk][(1+nterms)*8]
+  int64_t bsum_off;     // scratch [B][(1+nterms)*8]: rows_reduce of bpart
   int32_t nblk, hw;
   TermDesc t[kMaxTerms];
 };
@@ -936,27 +980,17 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
   __shared__ float s_T[8], s_dg[8], s_db[8];
   __shared__ float s_gbeta[4];
   const int tid = threadIdx.x, total = batch * 8, V = (1 + nd.nterms) * 8;
-  const float *part = scratch + nd.bpart_off;
+  const float *bsum = scratch + nd.bsum_off;
   const float M = (float)batch * (float)nd.hw;
   if (tid < 4) s_gbeta[tid] = 0.f;
-  for (int i = tid; i < total; i += 128) {
-    const int n = i >> 3, c = i & 7;
-    float r = 0.f;
-    for (int b = 0; b < nd.nblk; ++b) r += part[((int64_t)n * nd.nblk + b) * V + c];
-    s_S1[i] = r;
-  }
+  for (int i = tid; i < total; i += 128) s_S1[i] = bsum[(int64_t)(i >> 3) * V + (i & 7)];
   __syncthreads();
   for (int ti = 0; ti < nd.nterms; ++ti) {
     const TermDesc &t = nd.t[ti];
     const float w = alpha[t.edge * 6 + t.cand], be = beta ? beta[t.edge] : 1.f, kappa = w * be;
     const bool se = t.kind == 5;
-    for (int i = tid; i < total; i += 128) {
-      const int n = i >> 3, c = i & 7;
-      float r = 0.f;
-      if (t.has_y)
-        for (int b = 0; b < nd.nblk; ++b) r += part[((int64_t)n * nd.nblk + b) * V + (1 + ti) * 8 + c];
-      s_S2[i] = r;
-    }
+    for (int i = tid; i < total; i += 128)
+      s_S2[i] = t.has_y ? bsum[(int64_t)(i >> 3) * V + (1 + ti) * 8 + (i & 7)] : 0.f;
     __syncthreads();
     if (se) {  // through the gate: u = ds * s(1-s), dh = relu'(h) * sum_c u*W2
       for (int n = tid; n < batch; n += 128) {
@@ -1083,24 +1117,29 @@ __global__ void __launch_bounds__(128) pw_bwd_stats_kernel(PwBwdArgs a) {
     s_sc[tid] = sc, s_sh[tid] = a.b1[tid] - a.mean1[tid] * sc;
   }
   __syncthreads();
-  const int p = blockIdx.x * 128 + tid;
+  float racc[(8 * C + 127) / 128], sacc0 = 0.f, sacc1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < (8 * C + 127) / 128; ++i) racc[i] = 0.f;
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
+  for (int tile = 0; tile < kPxTilesPerBlock; ++tile) {
+  const int p = (blockIdx.x * kPxTilesPerBlock + tile) * 128 + tid;
   float dy[8], r[C], du[C];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dy[j] = 0.f;
 #pragma unroll
   for (int c = 0; c < C; ++c) r[c] = du[c] = 0.f;
+  __syncthreads();
   if (p < a.hw) pw_pixel_backward<C>(a, s_w, s_sc, s_sh, n, p, dy, r, du, true);
 #pragma unroll
   for (int c = 0; c < C; ++c) s_r[tid][c] = r[c];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s_dy[tid][j] = dy[j];
   __syncthreads();
-  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
-  for (int o = tid; o < 8 * C; o += 128) {
+  for (int o = tid, i = 0; o < 8 * C; o += 128, ++i) {
     const int co = o / C, ci = o - co * C;
-    float acc = 0.f;
+    float acc = racc[i];
     for (int q = 0; q < 128; ++q) acc = fmaf(s_dy[q][co], s_r[q][ci], acc);
-    out[2 * C + o] = acc;
+    racc[i] = acc;
   }
   __syncthreads();
   // du and du*zhat: zhat = (r>0 ? (u - b1)/g1 ...) is not recoverable from r; recompute from z
@@ -1108,9 +1147,9 @@ __global__ void __launch_bounds__(128) pw_bwd_stats_kernel(PwBwdArgs a) {
   for (int c = 0; c < C; ++c) s_r[tid][c] = du[c];
   __syncthreads();
   if (tid < C) {
-    float acc = 0.f;
+    float acc = sacc0;
     for (int q = 0; q < 128; ++q) acc += s_r[q][tid];
-    out[tid] = acc;
+    sacc0 = acc;
   }
   __syncthreads();
   if (p < a.hw) {
@@ -1123,20 +1162,21 @@ __global__ void __launch_bounds__(128) pw_bwd_stats_kernel(PwBwdArgs a) {
   }
   __syncthreads();
   if (tid < C) {
-    float acc = 0.f;
+    float acc = sacc1;
     for (int q = 0; q < 128; ++q) acc += s_r[q][tid];
-    out[C + tid] = acc;
+    sacc1 = acc;
   }
+  }
+  for (int o = tid, i = 0; o < 8 * C; o += 128, ++i) out[2 * C + o] = racc[i];
+  if (tid < C) out[tid] = sacc0, out[C + tid] = sacc1;
 }
 
-// BN1 backward finalize (one block): reduce pass-1 partials, write d gamma1 / d beta1 / dW_pw, coefficient table
-__global__ void __launch_bounds__(128) pw_bfin_kernel(const float *partials, int nblk_total, int C, float M, const float *g1,
-                                                      const float *istd1, float *coef /*[3][C]*/, float *g_gamma1,
-                                                      float *g_beta1, float *g_wpw) {
+// BN1 backward finalize (one block) on the already reduced pass-1 sums [10C]: d gamma1 / d beta1 / dW_pw, coefficients
+__global__ void __launch_bounds__(128) pw_bfin_kernel(const float *sums, int C, float M, const float *g1, const float *istd1,
+                                                      float *coef /*[3][C]*/, float *g_gamma1, float *g_beta1, float *g_wpw) {
   const int V = 10 * C;
   for (int i = threadIdx.x; i < V; i += 128) {
-    float s = 0.f;
-    for (int b = 0; b < nblk_total; ++b) s += partials[(int64_t)b * V + i];
+    const float s = sums[i];
     if (i < C) {
       g_beta1[i] = s;
       coef[C + i] = s / M;
@@ -1233,22 +1273,50 @@ __global__ void __launch_bounds__(128) dw_dx_kernel(DwBwdArgs a) {
 }
 
 // depthwise weight gradient: dW[c][t] = sum_b x[b*si + d_t][c] * dz[b*so + phase_t][c]; forward tap table.
-// thread = (c, t); each block walks `chunk` base pixels of one sample.
-template <int C>
-__global__ void dw_wgrad_kernel(DwBwdArgs a) {
-  const int tid = threadIdx.x, c = tid % C, t = tid / C, n = blockIdx.y;
+// thread = (pixel strip, channel) with all taps in registers; strips are combined through shared memory in
+// fixed order; one partial per block.  block = 256 threads, `chunk` base pixels of one sample per block.
+template <int C, int T>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(DwBwdArgs a) {
+  constexpr int NS = 256 / C;  // strips
+  __shared__ float s_red[NS][C * T + 1];
+  const int tid = threadIdx.x, c = tid % C, strip = tid / C, n = blockIdx.y;
   const int npix = a.base_h * a.base_w;
   const int b0 = blockIdx.x * a.chunk, b1 = b0 + a.chunk < npix ? b0 + a.chunk : npix;
   const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld + c;
   const float *zn = a.dz + (int64_t)n * a.z_h * a.z_w * C + c;
-  const int dy = a.taps.dy[t], dx = a.taps.dx[t], ph = a.taps.phase[t];
-  float acc = 0.f;
-  for (int b = b0; b < b1; ++b) {
+  float acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.f;
+  for (int b = b0 + strip; b < b1; b += NS) {
     const int by = b / a.base_w, bx = b - by * a.base_w;
-    const int iy = by * a.si + dy, ix = bx * a.si + dx;
-    const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
-    if (iy < 0 || iy >= a.x_h || ix < 0 || ix >= a.x_w || oy >= a.z_h || ox >= a.z_w) continue;
-    acc = fmaf(__ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld), zn[((int64_t)oy * a.z_w + ox) * C], acc);
+    if (a.so == 1) {
+      const float zv = zn[((int64_t)by * a.z_w + bx) * C];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t];
+        const bool ok = iy >= 0 && iy < a.x_h && ix >= 0 && ix < a.x_w;
+        const float xv = ok ? __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld) : 0.f;
+        acc[t] = fmaf(xv, zv, acc[t]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int iy = by * a.si + a.taps.dy[t], ix = bx * a.si + a.taps.dx[t], ph = a.taps.phase[t];
+        const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+        const bool ok = iy >= 0 && iy < a.x_h && ix >= 0 && ix < a.x_w && oy < a.z_h && ox < a.z_w;
+        const float xv = ok ? __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld) : 0.f;
+        const float zv = ok ? zn[((int64_t)oy * a.z_w + ox) * C] : 0.f;
+        acc[t] = fmaf(xv, zv, acc[t]);
+      }
+    }
   }
-  a.partials[((int64_t)n * gridDim.x + blockIdx.x) * C * a.taps.n + c * a.taps.n + a.taps.widx[t]] = acc;
+#pragma unroll
+  for (int t = 0; t < T; ++t) s_red[strip][c * T + a.taps.widx[t]] = acc[t];
+  __syncthreads();
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * C * T;
+  for (int o = tid; o < C * T; o += 256) {
+    float r = 0.f;
+    for (int q = 0; q < NS; ++q) r += s_red[q][o];
+    out[o] = r;
+  }
 }
