@@ -191,6 +191,16 @@ class RectifyBlock(nn.Module):
         return self.norm(self.conv(x))
 
 
+class _AvgPool2dNCHW(nn.AvgPool2d):
+    """``nn.AvgPool2d`` evaluated on an NCHW-contiguous input.  PyTorch 2.11's CUDA avg_pool2d *backward*
+    returns wrong gradients for channels_last inputs (measured on B200: max abs error 0.25-0.5 against the
+    CPU result for k=3, s=2, p=1, either ``count_include_pad``; the NCHW path is exact -- see
+    scripts/diag_pool.py), and the rest of the network runs channels_last."""
+
+    def forward(self, x):
+        return super().forward(x.contiguous())
+
+
 def build_rectify(c_in, c_ot, cell_type):
     act = nn.ReLU(inplace=False)
     if cell_type == 'up':
@@ -200,7 +210,7 @@ def build_rectify(c_in, c_ot, cell_type):
         return nn.Sequential(act, nn.ConvTranspose2d(c_in, c_ot, kernel_size=1, stride=2, output_padding=1,
                                                      bias=False), nn.BatchNorm2d(c_ot))
     if c_in == c_ot:
-        return nn.Sequential(act, nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False),
+        return nn.Sequential(act, _AvgPool2dNCHW(3, stride=2, padding=1, count_include_pad=False),
                              nn.BatchNorm2d(c_ot))
     return nn.Sequential(act, nn.Conv2d(c_in, c_ot, kernel_size=1, stride=2, bias=False), nn.BatchNorm2d(c_ot))
 
