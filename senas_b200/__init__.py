@@ -10,6 +10,7 @@ from .cell import MixedOp, Cell  # noqa: F401
 from .genotype import Genotype, GenoParser  # noqa: F401
 from .supernet import Head, SenasSearch, NAS, Architecture  # noqa: F401
 from .build import build  # noqa: F401
+from .patch import patch_reference  # noqa: F401
 
 __version__ = '0.1.0'
 

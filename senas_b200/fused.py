@@ -9,8 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .ops import (KIND_AVG_POOL, KIND_CONV, KIND_DEPSEP, KIND_IDENTITY, KIND_NONE, KIND_SE_CONV, KIND_UP_SAMPLE,
-                  AdapterBlock, ConvBn, ConvBnSe, DepSepConv)
+from .ops import KIND_AVG_POOL, KIND_CONV, KIND_DEPSEP, KIND_IDENTITY, KIND_NONE, KIND_SE_CONV, KIND_UP_SAMPLE
 
 
 def _bn_slots(bn):
@@ -18,28 +17,38 @@ def _bn_slots(bn):
 
 
 def candidate_slots(op):
-    """(kind, ksize, dilation, [12 slot tensors or None]) for one candidate block, in the slot order
-    documented in include/senas_b200.h."""
+    """(kind, ksize, dilation, [12 slot tensors or None]) for one candidate block, in the slot order documented in
+    include/senas_b200.h.  Structural (duck-typed) so that it reads senas_b200's parameter containers and the
+    reference's own modules (utils/operations.py:89-115,167-203) alike."""
     slots = [None] * _lib.SLOTS
-    if isinstance(op, AdapterBlock):
+    if hasattr(op, 'norm') and hasattr(op, 'module'):  # AdapterBlock
+        mod = op.module
+        if isinstance(mod, torch.nn.Identity):
+            kind = KIND_IDENTITY
+        elif isinstance(mod, torch.nn.AvgPool2d):
+            kind = KIND_AVG_POOL
+        elif isinstance(mod, torch.nn.Upsample):
+            kind = KIND_UP_SAMPLE
+        elif type(mod).__name__ == 'ZeroOp':
+            kind = KIND_NONE
+        else:
+            raise TypeError(f'unsupported adapter module {type(mod).__name__}')
         slots[0] = op.conv.weight if hasattr(op, 'conv') else None
         slots[1:6] = _bn_slots(op.norm)
-        return op.kind, 0, 1, slots
-    if isinstance(op, ConvBnSe):
-        slots[0] = op[0].weight
+        return kind, 0, 1, slots
+    if isinstance(op, torch.nn.Sequential) and len(op) in (2, 3, 5):
+        conv = op[0]
+        k, dil = conv.kernel_size[0], conv.dilation[0]
+        slots[0] = conv.weight
         slots[1:6] = _bn_slots(op[1])
-        slots[6], slots[7] = op[2].excitation[0].weight, op[2].excitation[2].weight
-        return KIND_SE_CONV, op.k, op.dilation, slots
-    if isinstance(op, ConvBn):
-        slots[0] = op[0].weight
-        slots[1:6] = _bn_slots(op[1])
-        return KIND_CONV, op.k, op.dilation, slots
-    if isinstance(op, DepSepConv):
-        slots[0] = op[0].weight
-        slots[1:6] = _bn_slots(op[1])
+        if len(op) == 2:
+            return KIND_CONV, k, dil, slots
+        if len(op) == 3:
+            slots[6], slots[7] = op[2].excitation[0].weight, op[2].excitation[2].weight
+            return KIND_SE_CONV, k, dil, slots
         slots[6] = op[3].weight
         slots[7:12] = _bn_slots(op[4])
-        return KIND_DEPSEP, op.k, 1, slots
+        return KIND_DEPSEP, k, 1, slots
     raise TypeError(f'not a MixedOp candidate: {type(op).__name__}')
 
 

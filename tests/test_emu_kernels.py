@@ -94,3 +94,39 @@ def test_cell_nodes_emulated(emu, name, cell_type):
     for k, v in sub(g, 'after.').items():
         if k.startswith('_ops'):
             check('after.' + k, sd[k], v, 1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/search'), reason='reference tree only in the build container')
+def test_patch_reference_classes_emulated(emu):
+    """senas_b200.patch_reference() on the UNMODIFIED reference classes (emulated kernels, CPU tensors): the
+    reference's own Cell / MixedOp objects, parameters and autograd graph, only forward() rerouted."""
+    import copy
+    import ref_shim
+    import senas_b200
+    cell_mod, _, ops_mod = ref_shim.load()
+    orig_m, orig_c = cell_mod.MixedOp.forward, cell_mod.Cell.forward
+    torch.manual_seed(5)
+    ref_cell = cell_mod.Cell(3, 1, 32, 32, 32, 'up')
+    new_cell = copy.deepcopy(ref_cell)
+    in0, in1 = torch.randn(2, 32, 8, 8), torch.randn(2, 32, 4, 4)
+    wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
+    b = torch.softmax(torch.randn(9), -1)
+    t_ref = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    out_ref = ref_cell(*t_ref)
+    gout = torch.randn(out_ref.shape)
+    out_ref.backward(gout)
+    try:
+        senas_b200.patch_reference(cell_mod, lib=emu)
+        t_new = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+        out_new = new_cell(*t_new)
+        out_new.backward(gout)
+    finally:
+        cell_mod.MixedOp.forward, cell_mod.Cell.forward = orig_m, orig_c
+    check('out', out_new, out_ref.detach())
+    for i, n in enumerate(('gin0', 'gin1', 'gwn', 'gwc', 'gbetas')):
+        check(n, t_new[i].grad, t_ref[i].grad)
+    for (n, p), (_, q) in zip(new_cell.named_parameters(), ref_cell.named_parameters()):
+        check('grad.' + n, p.grad, q.grad)
+    assert list(new_cell.state_dict().keys()) == list(ref_cell.state_dict().keys())
+    for k, v in ref_cell.state_dict().items():
+        assert torch.allclose(new_cell.state_dict()[k].float(), v.float(), rtol=1e-4, atol=1e-6), k
