@@ -36,6 +36,7 @@ extern "C" {
 #define SENAS_SLOTS 12     /* parameter/buffer slots per candidate, see table below */
 #define SENAS_MAX_EDGES 16
 #define SENAS_MAX_NODES 4
+#define SENAS_FLAG_TC_BF16 1
 
 /* OpType ids: the reference's OpType.value['id'] (utils/operations.py:51-54) */
 enum { SENAS_OP_UP = 1, SENAS_OP_DOWN = 2, SENAS_OP_NORM = 3 };
@@ -79,7 +80,7 @@ typedef struct {
   int32_t n_edges;
   int32_t c_out;               /* channels per node; only 8 is supported (Cell.k = 4, c = 32) */
   int32_t node_relu;           /* 1: node = relu(sum), cell.py:107; 0: plain sum (MixedOp) */
-  int32_t reserved;
+  int32_t reserved;            /* flags: bit 0 = SENAS_FLAG_TC_BF16 (tcgen05 convs with bf16 operands, fp32 accumulation) */
   int64_t grad_floats;         /* length of the flat parameter-gradient buffer */
   senas_edge_desc_t edge[SENAS_MAX_EDGES];
 } senas_graph_desc_t;

@@ -1,0 +1,328 @@
+// conv_tc.cuh -- tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation).
+//
+// Covers the dense 3x3 / dilated 5x5 candidates of the MixedOp (utils/operations.py:89-104 of the reference) for the
+// stride-1 geometries: NORM (Conv2d) and UP (ConvTranspose2d as 4 output phases on the input grid),
+// c_in = 32, and the *same candidate of up to 4 edges that share an input* in one GEMM (Cell edges 0/2/5 read in0,
+// 1/3/6 read in1, search/cell.py:76-90), so N = 8 * edges (24 padded to 32) instead of 8.
+//
+//   D[128 pixels x 32] (TMEM, fp32) += A_tap[128 pixels x 32 ch] (smem, bf16) * W_tap[32 ch x 32] (smem, bf16)
+//
+// * One CTA owns a 128-pixel-wide column strip of `rows_per_cta` output rows of one image and walks down the rows.
+//   Input rows live in a shared-memory ring; every input row is fetched ONCE per strip by TMA (5-D tensor map over
+//   the NHWC bf16 tensor viewed as (c8, W, H, plane, N): box = one row x (128 + halo) pixels x 4 planes of 8 channels,
+//   out-of-image coordinates are zero-filled by the TMA unit = the convolution's zero padding).
+// * In shared memory a row block is [plane][pixel][8 ch] (16 B per pixel and plane): the canonical no-swizzle K-major
+//   UMMA layout with SBO = 128 B (8 pixels) and LBO = plane stride.  A tap (dy, dx) is just a different start address
+//   of the A descriptor: row slot (r + dy), pixel offset dx -- no im2col, no data movement.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 kind::f16,
+//   M = 128, N = 32, K = 16), warps 2-5 = epilogue (tcgen05.ld 32x32b, fp32 stores of the pre-BN outputs y_k and the
+//   BatchNorm statistics).  Accumulators are double-buffered in TMEM so MMA of row r+1 overlaps the epilogue of row r.
+#pragma once
+#ifndef SENAS_EMU
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kernels.cuh"
+
+constexpr int kTcM = 128;        // pixels per MMA
+constexpr int kTcN = 32;         // padded output channels (<= 4 terms x 8)
+constexpr int kTcThreads = 192;  // 6 warps
+constexpr int kTcMaxTerms = 4;
+
+struct TcConvArgs {
+  const float *w[kTcMaxTerms];
+  float *y[kTcMaxTerms];         // [B][Ho][Wo][8] fp32
+  float *partials[kTcMaxTerms];  // [B][gridDim.x][16]
+  int32_t nterms;
+  int32_t ws_t, ws_k, ws_n;      // weight strides: tap, input channel, output channel
+  int32_t H, W, Ho, Wo, so;
+  int32_t rows_per_cta, row_chunks;
+  int32_t P, S;                  // staged pixels per row (even), ring slots
+  TapTable taps;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr uint32_t kTcTmemCols = 256;  // 2 buffers x 4 phases x 32 columns
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 32, M = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, TcConvArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y;
+  const int xseg = blockIdx.x / a.row_chunks, chunk = blockIdx.x - xseg * a.row_chunks;
+  const int x0 = xseg * kTcM;
+  const int r0 = chunk * a.rows_per_cta, r_end = min(r0 + a.rows_per_cta, a.H);
+  const int T = a.taps.n, NPH = a.taps.nphase;
+  const uint32_t row_bytes = (uint32_t)a.P * 64u;
+  unsigned char *rows = smem;
+  unsigned char *wsm = smem + (size_t)a.S * row_bytes;  // [T][4 k-chunks][32 n][8 k] bf16
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + (size_t)T * 2048);
+  uint64_t *full = bars, *empty = bars + a.S, *acc_full = bars + 2 * a.S, *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  __shared__ float s_red[4][64];
+
+  // ---- weights: fp32 global (PyTorch layout) -> bf16 canonical K-major tiles in shared memory
+  for (int i = tid; i < T * 4 * kTcN; i += kTcThreads) {
+    const int nn = i % kTcN, kc = (i / kTcN) & 3, t = i / (4 * kTcN);
+    const int g = nn >> 3, co = nn & 7;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f = 0.f;
+      if (g < a.nterms) f = __ldg(a.w[g] + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)(kc * 8 + j) * a.ws_k + (int64_t)co * a.ws_n);
+      v[j] = __float2bfloat16(f);
+    }
+    *reinterpret_cast<uint4 *>(wsm + (size_t)i * 16) = *reinterpret_cast<const uint4 *>(v);
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.S; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4), mbar_init(&acc_empty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy weight stores -> visible to the MMA unit
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int first_in = r0 + a.taps.min_dy;
+  const int last_in = r_end - 1 + a.taps.max_dy;
+  float st_s[kTcN], st_q[kTcN];
+#pragma unroll
+  for (int i = 0; i < kTcN; ++i) st_s[i] = st_q[i] = 0.f;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int idx = 0;
+      for (int y = first_in; y <= last_in; ++y, ++idx) {
+        const int slot = idx % a.S, use = idx / a.S;
+        if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+        mbar_expect_tx(&full[slot], row_bytes);
+        tma_load_5d(rows + (size_t)slot * row_bytes, &tmap, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t rows_addr = smem_u32(rows), w_addr = smem_u32(wsm);
+      const uint32_t lbo_a = (uint32_t)a.P * 16u;
+      int waited = 0, it = 0;
+      for (int r = r0; r < r_end; ++r, ++it) {
+        const int need = r + a.taps.max_dy - first_in + 1;
+        while (waited < need) {
+          mbar_wait(&full[waited % a.S], (uint32_t)((waited / a.S) & 1));
+          ++waited;
+        }
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) - 1) & 1));
+        tc_fence_after();
+        for (int ph = 0; ph < NPH; ++ph) {
+          const uint32_t d = tmem_base + (uint32_t)((buf * NPH + ph) * kTcN);
+          uint32_t acc = 0;
+          for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
+            const int slot = (r + a.taps.dy[t] - first_in) % a.S;
+            const uint32_t a0 = rows_addr + (uint32_t)slot * row_bytes + (uint32_t)(a.taps.dx[t] - a.taps.min_dx) * 16u;
+            const uint32_t b0 = w_addr + (uint32_t)t * 2048u;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {  // K = 32 channels = 2 x (K = 16)
+              umma_bf16(d, umma_desc(a0 + (uint32_t)j * 2u * lbo_a, lbo_a, 128u), umma_desc(b0 + (uint32_t)j * 1024u, 512u, 128u),
+                        kTcIdesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        tc_commit(&acc_full[buf]);   // accumulators of this row are complete when all MMAs above retire
+        tc_commit(&empty[it % a.S]); // ... and input row (r + min_dy) is no longer needed by any later row
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> y (fp32) + statistics =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int px = x0 + q * 32 + lane;
+    int it = 0;
+    for (int r = r0; r < r_end; ++r, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      for (int ph = 0; ph < NPH; ++ph) {
+        float v[kTcN];
+        if (a.taps.pstart[ph + 1] > a.taps.pstart[ph]) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * NPH + ph) * kTcN), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTcN; ++i) v[i] = 0.f;  // phase without taps (UP dil_2_conv_5): exact zeros
+        }
+        const int oy = r * a.so + (ph >> 1), ox = px * a.so + (ph & 1);
+        if (px < a.W && oy < a.Ho && ox < a.Wo) {
+          const int64_t pix = ((int64_t)n * a.Ho + oy) * a.Wo + ox;
+#pragma unroll
+          for (int g = 0; g < kTcMaxTerms; ++g) {
+            if (g < a.nterms) {
+              float *o = a.y[g] + pix * 8;
+              st4(o, make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]));
+              st4(o + 4, make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kTcN; ++i) st_s[i] += v[i], st_q[i] += v[i] * v[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  // ---- statistics: 128 epilogue threads -> per-term partial sums (fixed order)
+  __syncthreads();
+  if (warp >= 2) {
+    const int q = warp & 3;
+#pragma unroll
+    for (int i = 0; i < kTcN; ++i) {
+      const float s = warp_sum(st_s[i]), sq = warp_sum(st_q[i]);
+      if (lane == 0) s_red[q][i] = s, s_red[q][kTcN + i] = sq;
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const float r = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+    const int which = tid >> 5, col = tid & 31, g = col >> 3, c = col & 7;
+    if (g < a.nterms) a.partials[g][((int64_t)n * gridDim.x + blockIdx.x) * 16 + which * 8 + c] = r;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols));
+  }
+}
+
+// fp32 NHWC (any pixel stride) -> dense bf16 NHWC, 32 channels; thread = (pixel, 8-channel plane)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float *src, int64_t ld, __nv_bfloat16 *dst, int64_t npix) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= npix * 4) return;
+  const int64_t pix = i >> 2;
+  const int pl = (int)(i & 3);
+  const float4 lo = ld4(src + pix * ld + pl * 8), hi = ld4(src + pix * ld + pl * 8 + 4);
+  __align__(16) __nv_bfloat16 v[8] = {__float2bfloat16(lo.x), __float2bfloat16(lo.y), __float2bfloat16(lo.z), __float2bfloat16(lo.w),
+                                      __float2bfloat16(hi.x), __float2bfloat16(hi.y), __float2bfloat16(hi.z), __float2bfloat16(hi.w)};
+  *reinterpret_cast<uint4 *>(dst + pix * 32 + pl * 8) = *reinterpret_cast<const uint4 *>(v);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tc_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static size_t tc_smem_bytes(const TcConvArgs &a) {
+  return (size_t)a.S * a.P * 64 + (size_t)a.taps.n * 2048 + (size_t)(2 * a.S + 4) * 8 + 64;
+}
+
+// xb: dense bf16 NHWC [B][H][W][32].  Returns 0 on success, 1 when the geometry cannot run here (caller falls back
+// to the exact fp32 kernel of the same family, still on the GPU), 2 on a driver error.
+static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *stream) {
+  PFN_tmapEncodeTiled enc = tc_encode_fn();
+  if (!enc) return 2;
+  const int span_x = a.taps.max_dx - a.taps.min_dx, span_y = a.taps.max_dy - a.taps.min_dy;
+  a.P = (kTcM + span_x + 1) & ~1;
+  a.S = span_y + 1 + 3;
+  if (a.P > 256 || a.W % kTcM != 0) return 1;
+  const size_t smem = tc_smem_bytes(a);
+  if (smem > 227 * 1024) return 1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, 4, (cuuint64_t)B};
+  const cuuint64_t gstr[4] = {64, (cuuint64_t)a.W * 64, 16, (cuuint64_t)a.H * a.W * 64};
+  const cuuint32_t box[5] = {8, (cuuint32_t)a.P, 1, 4, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16 *>(xb), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((a.W / kTcM) * a.row_chunks, B);
+  SENAS_LAUNCH(conv_tc_fwd_kernel, grid, dim3(kTcThreads), smem, stream, tmap, a);
+  return 0;
+}
+#endif  // SENAS_EMU

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "conv_tc.cuh"
 
 #ifdef SENAS_EMU
 static void *dev_upload(const void *h, size_t n) {
@@ -131,6 +132,11 @@ struct TermPlan {
   int64_t part_off = -1, part1_off = -1, psum_off = -1, psum1_off = -1;
   int nblk = 0, nblk1 = 0;
   int64_t scale_off = -1, coef_off = -1;
+  bool tc = false;  // forward runs in a tcgen05 group (bf16 operands)
+};
+struct TcGroup {
+  int src, op, kind, k, dil, nterms;
+  int edge[4], cand[4];
 };
 struct EdgePlan {
   int in_h, in_w;
@@ -147,6 +153,8 @@ struct Plan {
   int64_t saved_floats = 0, scratch_floats = 0, tmp_off = 0, tmp_floats = 0;
   std::vector<EdgePlan> edges;
   std::vector<NodePlan> nodes;
+  std::vector<TcGroup> tc_groups;
+  int64_t xb_off[2] = {-1, -1};  // saved: dense bf16 NHWC copy of an input state (floats offset)
   std::vector<BnDesc *> d_bnA, d_bnB;  // per stage
   std::vector<int> n_bnA, n_bnB;
   NodeDesc *d_nodes = nullptr;
@@ -201,6 +209,38 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
   };
   const int nblk_px = cdiv(HW, 128);
   int64_t tmp_need = 0;
+#ifndef SENAS_EMU
+  if (d.reserved & 1) {  // SENAS_FLAG_TC_BF16: group equal candidates of edges that share an input
+    for (int e = 0; e < d.n_edges; ++e) {
+      const senas_edge_desc_t &ed = d.edge[e];
+      if (ed.src >= d.n_inputs || ed.c_in != 32 || ed.op_type == SENAS_OP_DOWN) continue;
+      if (p->edges[e].in_w % kTcM != 0) continue;
+      for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+        if (ed.kind[k] != SENAS_KIND_CONV && ed.kind[k] != SENAS_KIND_SE_CONV) continue;
+        Geo geo = make_geo(ed.ksize[k], ed.dilation[k], ed.op_type, DIR_FWD);
+        TcConvArgs probe;
+        probe.taps = geo.taps;
+        probe.P = (kTcM + geo.taps.max_dx - geo.taps.min_dx + 1) & ~1;
+        probe.S = geo.taps.max_dy - geo.taps.min_dy + 4;
+        if (probe.P > 256 || tc_smem_bytes(probe) > 227 * 1024) continue;
+        TcGroup *grp = nullptr;
+        for (auto &g2 : p->tc_groups)
+          if (g2.src == ed.src && g2.op == ed.op_type && g2.kind == ed.kind[k] && g2.k == ed.ksize[k] &&
+              g2.dil == ed.dilation[k] && g2.nterms < kTcMaxTerms)
+            grp = &g2;
+        if (!grp) {
+          p->tc_groups.push_back(TcGroup{ed.src, ed.op_type, ed.kind[k], ed.ksize[k], ed.dilation[k], 0, {0}, {0}});
+          grp = &p->tc_groups.back();
+        }
+        grp->edge[grp->nterms] = e, grp->cand[grp->nterms] = k, grp->nterms++;
+        p->edges[e].t[k].tc = true;
+      }
+    }
+    for (auto &g2 : p->tc_groups)
+      if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
+  }
+#endif
+  const int kTcRows = 32;
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
     EdgePlan &ep = p->edges[e];
@@ -230,6 +270,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW);
+          if (t.tc) t.nblk = (ep.in_w / 128) * cdiv(ep.in_h, kTcRows);
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
           break;
@@ -503,6 +544,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
       }
       case SENAS_KIND_CONV:
       case SENAS_KIND_SE_CONV: {
+        if (t.tc) break;  // done by its tcgen05 group
         Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
         GatherArgs a;
         memset(&a, 0, sizeof(a));
@@ -573,6 +615,35 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
   c.bases.p[SP_IN0] = (float *)a->in[0], c.bases.ld[SP_IN0] = a->in_ld[0];
   c.bases.p[SP_IN1] = (float *)a->in[1], c.bases.ld[SP_IN1] = a->in_ld[1];
   c.bases.p[SP_OUT] = a->out, c.bases.ld[SP_OUT] = a->out_ld;
+#ifndef SENAS_EMU
+  for (int i = 0; i < d.n_inputs; ++i) {
+    if (p->xb_off[i] < 0) continue;
+    const int64_t npix = (int64_t)c.B * p->in_h[i] * p->in_w[i];
+    SENAS_TAG("cast_bf16", 0, 6.0 * npix * 32);
+    SENAS_LAUNCH(cast_bf16_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, c.stream, a->in[i], a->in_ld[i],
+                 reinterpret_cast<__nv_bfloat16 *>(c.saved + p->xb_off[i]), npix);
+  }
+  for (const TcGroup &g2 : p->tc_groups) {
+    Geo geo = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
+    TcConvArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    const EdgePlan &ep0 = p->edges[g2.edge[0]];
+    ta.nterms = g2.nterms;
+    for (int i = 0; i < g2.nterms; ++i) {
+      const TermPlan &t = p->edges[g2.edge[i]].t[g2.cand[i]];
+      ta.w[i] = (const float *)d.edge[g2.edge[i]].param[g2.cand[i]][0];
+      ta.y[i] = c.saved + t.y_off, ta.partials[i] = c.scratch + t.part_off;
+    }
+    ta.ws_t = 1;
+    conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ta.ws_k, &ta.ws_n);
+    ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = p->out_h, ta.Wo = p->out_w, ta.so = geo.so;
+    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
+    SENAS_TAG("conv_tc_fwd", 2.0 * c.B * ep0.in_h * ep0.in_w * geo.taps.n * 32 * 8 * g2.nterms,
+              2.0 * c.B * ep0.in_h * ep0.in_w * 32 + 4.0 * c.B * p->hw * 8 * g2.nterms);
+    const int rc = launch_conv_tc(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), c.B, ta, c.stream);
+    if (rc) SENAS_FAIL("tcgen05 conv launch failed (code %d)", rc);
+  }
+#endif
   for (int s = 0; s < d.n_nodes; ++s) {
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;

@@ -53,6 +53,20 @@ def candidate_slots(op):
 
 
 _scratch = {}
+_flags = {'tc_bf16': False}
+
+
+def set_conv_mode(mode):
+    """'fp32' : every convolution in exact fp32 FMA (gate 1e-4 against the reference);
+    'bf16' : the dense / dilated / transposed c_in = 32 convolutions of a cell run as tcgen05 implicit GEMMs with
+    TMA-staged NHWC bf16 operands and fp32 TMEM accumulation (gate 2e-2)."""
+    if mode not in ('fp32', 'bf16'):
+        raise ValueError(mode)
+    _flags['tc_bf16'] = mode == 'bf16'
+
+
+def get_conv_mode():
+    return 'bf16' if _flags['tc_bf16'] else 'fp32'
 
 
 def scratch_for(device, nbytes):
@@ -83,6 +97,8 @@ class GraphRunner:
         desc = _lib.GraphDesc()
         desc.n_inputs, desc.n_nodes, desc.n_edges = self.n_inputs, self.n_nodes, len(self.edges)
         desc.c_out, desc.node_relu = 8, int(self.node_relu)
+        self.tc_bf16 = _flags['tc_bf16']
+        desc.reserved = 1 if self.tc_bf16 else 0
         self.params, self.sizes, self.shapes = [], [], []
         off = 0
         for e, (cands, src, dst, op_type, c_in) in enumerate(self.edges):
@@ -118,7 +134,7 @@ class GraphRunner:
     def refresh(self):
         """Re-read parameter pointers if the module was moved (``.to()``) since the graph was built."""
         fp = (self.params[0].data_ptr(), self.params[-1].data_ptr(), self.params[0].device)
-        if fp != self._fingerprint:
+        if fp != self._fingerprint or self.tc_bf16 != _flags['tc_bf16']:
             self._build()
 
     def __del__(self):

@@ -247,3 +247,56 @@ def test_no_cpu_fallback():
     m = senas_b200.MixedOp(32, 8, OP_BY_ID[3])
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         m(torch.randn(1, 32, 8, 8), torch.ones(6) / 6, torch.ones(6) / 6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 mode: tcgen05 implicit-GEMM convolutions (TMA-staged bf16 operands, fp32 accumulation).  Gate 2e-2.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def bf16_mode():
+    senas_b200.set_conv_mode('bf16')
+    yield
+    senas_b200.set_conv_mode('fp32')
+
+
+@pytest.mark.parametrize('op_id,B,H,W', [(3, 2, 24, 128), (1, 2, 10, 128), (3, 1, 40, 256)])
+def test_mixed_op_bf16_tensor_core(bf16_mode, op_id, B, H, W):
+    torch.manual_seed(200 + op_id + H)
+    m = senas_b200.MixedOp(32, 8, OP_BY_ID[op_id])
+    m.apply(senas_b200.weights_init)
+    store = oracle.clone_store(m.state_dict())
+    x = torch.randn(B, 32, H, W)
+    alpha = torch.softmax(torch.randn(6), -1)
+    xo, ao = x.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], xo, ao, True)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    m = m.to(DEV)
+    xg, ag = x.to(DEV).requires_grad_(True), alpha.to(DEV).requires_grad_(True)
+    lib = senas_b200._lib.get()
+    lib.senas_profile(1)
+    out = m(xg, ag, ag)
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    lib.senas_profile(0)
+    assert 'conv_tc_fwd' in senas_b200._lib.profile_dump(lib), 'the tcgen05 kernel did not run'
+    check('out', out, ref.detach(), 2e-2)
+    check('gx', xg.grad, xo.grad, 2e-2)
+    check('galpha', ag.grad, ao.grad, 2e-2)
+    for n, p in m.named_parameters():
+        check('grad.' + n, p.grad, store[n].grad, 2e-2)
+
+
+def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode):
+    torch.manual_seed(11)
+    c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
+    c.apply(senas_b200.weights_init)
+    store = oracle.clone_store(c.state_dict())
+    in0, in1 = torch.randn(2, 32, 16, 128), torch.randn(2, 32, 8, 64)   # in0: NORM edges at W = 128 -> tcgen05 groups
+    wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
+    b = torch.softmax(torch.randn(9), -1)
+    ref = oracle.cell_nodes(oracle.Params(store), 'up', in0, in1, wn, wc, b)
+    c = c.to(DEV)
+    with torch.no_grad():
+        out = c.nodes(in0.to(DEV), in1.to(DEV), wn.to(DEV), wc.to(DEV), b.to(DEV))
+    check('cat', out, ref.detach(), 2e-2)
