@@ -168,7 +168,8 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.get()
     _lib.check(lib, lib.senas_device_check(local_rank))
     torch.backends.cudnn.benchmark = True  # as experiments/search_arc.py:72 (stems / pre / post convs)
-    senas_b200.exact_fp32()                # fp32 mode: no TF32 anywhere
+    senas_b200.exact_fp32()                # no TF32 in the stock-PyTorch blocks around the cells
+    senas_b200.set_conv_mode(args.conv_mode)
 
     B, size = args.batch, args.size
     torch.manual_seed(0)
@@ -254,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
     value, value_e2e = gB / (ms_step * 1e-3), gB / (ms_step_e2e * 1e-3)
     top = max(prof.items(), key=lambda kv: kv[1]['ms'])
     name, t = top
-    tensor_bound = name.startswith('conv_')
+    tensor_bound = name.startswith('conv_')  # conv_fwd / conv_dgrad / conv_wgrad / conv_tc_*
     if tensor_bound:
         ach = t['flops'] / (t['ms'] * 1e-3) / 1e12
         roof = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
@@ -273,10 +274,10 @@ def run_ours(args, rank, world, local_rank):
     out = {
         'metric': 'search_step_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
+        'dtype': 'bf16' if args.conv_mode == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': f'SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
                                f'{B} x 1x{size}x{size} per GPU, global batch {gB}',
-                   'parallelism': f'dp{world}', 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
+                   'parallelism': f'dp{world}', 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate/storage)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
         'e2e': {'value': value_e2e, 'unit': 'images/s', 'ms_per_step': ms_step_e2e,
                 'h2d_bytes_per_step': 2 * B * size * size * (4 + 8), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'roofline': roof, 'kernel_families': families, 'clocks': clk,
@@ -308,6 +309,8 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=1)
     ap.add_argument('--ref-max-steps', type=int, default=6)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--conv-mode', default='bf16', choices=['fp32', 'bf16'],
+                    help='bf16: tcgen05 implicit-GEMM convs with bf16 operands / fp32 accumulation; fp32: exact FMA path')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

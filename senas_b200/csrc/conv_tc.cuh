@@ -34,7 +34,11 @@ struct TcConvArgs {
   float *y[kTcMaxTerms];         // [B][Ho][Wo][8] fp32
   float *partials[kTcMaxTerms];  // [B][gridDim.x][16]
   int32_t nterms;
-  int32_t ws_t, ws_k, ws_n;      // weight strides: tap, input channel, output channel
+  int32_t mode;                  // 0: forward (per-term y + statistics); 1: data gradient (one 32-channel output)
+  float *out32;                  // mode 1: dx [B][H][W][out_ld], += when accumulate
+  int64_t out_ld;
+  int32_t accumulate;
+  int32_t ws_t, ws_k, ws_n;      // weight strides: tap, GEMM-K channel, GEMM-N channel
   int32_t H, W, Ho, Wo, so;
   int32_t rows_per_cta, row_chunks;
   int32_t P, S;                  // staged pixels per row (even), ring slots
@@ -128,12 +132,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   // ---- weights: fp32 global (PyTorch layout) -> bf16 canonical K-major tiles in shared memory
   for (int i = tid; i < T * 4 * kTcN; i += kTcThreads) {
     const int nn = i % kTcN, kc = (i / kTcN) & 3, t = i / (4 * kTcN);
-    const int g = nn >> 3, co = nn & 7;
+    // forward : K = input channel (kc*8+j), N = (term, out channel);  dgrad: K = (term = kc, out channel j), N = in channel
+    const int g = a.mode == 0 ? (nn >> 3) : kc;
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float f = 0.f;
-      if (g < a.nterms) f = __ldg(a.w[g] + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)(kc * 8 + j) * a.ws_k + (int64_t)co * a.ws_n);
+      if (g < a.nterms) {
+        const int kk = a.mode == 0 ? kc * 8 + j : j, cn = a.mode == 0 ? (nn & 7) : nn;
+        f = __ldg(a.w[g] + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)kk * a.ws_k + (int64_t)cn * a.ws_n);
+      }
       v[j] = __float2bfloat16(f);
     }
     *reinterpret_cast<uint4 *>(wsm + (size_t)i * 16) = *reinterpret_cast<const uint4 *>(v);
@@ -224,7 +232,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
           for (int i = 0; i < kTcN; ++i) v[i] = 0.f;  // phase without taps (UP dil_2_conv_5): exact zeros
         }
         const int oy = r * a.so + (ph >> 1), ox = px * a.so + (ph & 1);
-        if (px < a.W && oy < a.Ho && ox < a.Wo) {
+        if (a.mode == 1) {
+          float *o = a.out32 + (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.out_ld;
+#pragma unroll
+          for (int j = 0; j < kTcN; j += 4) {
+            float4 u = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (a.accumulate) {
+              const float4 w4 = ld4(o + j);
+              u.x += w4.x, u.y += w4.y, u.z += w4.z, u.w += w4.w;
+            }
+            st4(o + j, u);
+          }
+        } else if (px < a.W && oy < a.Ho && ox < a.Wo) {
           const int64_t pix = ((int64_t)n * a.Ho + oy) * a.Wo + ox;
 #pragma unroll
           for (int g = 0; g < kTcMaxTerms; ++g) {
@@ -254,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
     }
   }
   __syncthreads();
-  if (tid < 64) {
+  if (tid < 64 && a.mode == 0) {
     const float r = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
     const int which = tid >> 5, col = tid & 31, g = col >> 3, c = col & 7;
     if (g < a.nterms) a.partials[g][((int64_t)n * gridDim.x + blockIdx.x) * 16 + which * 8 + c] = r;
@@ -276,6 +295,35 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float *src, int64_
   __align__(16) __nv_bfloat16 v[8] = {__float2bfloat16(lo.x), __float2bfloat16(lo.y), __float2bfloat16(lo.z), __float2bfloat16(lo.w),
                                       __float2bfloat16(hi.x), __float2bfloat16(hi.y), __float2bfloat16(hi.z), __float2bfloat16(hi.w)};
   *reinterpret_cast<uint4 *>(dst + pix * 32 + pl * 8) = *reinterpret_cast<const uint4 *>(v);
+}
+
+// dy of up to 4 grouped terms -> one dense bf16 NHWC tensor [B][hw][32] (channels g*8.. = dy of term g, rest 0),
+// dy_g = A_g*gm_g + B_g*y_g + C_g with per-(sample, channel) coefficients.  thread = (pixel, term slot)
+struct PackDyArgs {
+  const float *gm[kTcMaxTerms], *y[kTcMaxTerms], *coef[kTcMaxTerms];  // coef: [3][B][8]
+  int64_t y_ld[kTcMaxTerms];
+  int32_t nterms, hw, batch;
+  __nv_bfloat16 *dst;
+};
+__global__ void __launch_bounds__(256) pack_dy_kernel(PackDyArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x, total = (int64_t)a.batch * a.hw * 4;
+  if (i >= total) return;
+  const int64_t pix = i >> 2;
+  const int g = (int)(i & 3), n = (int)(pix / a.hw);
+  __align__(16) __nv_bfloat16 v[8];
+  if (g < a.nterms) {
+    const float4 glo = ld4(a.gm[g] + pix * 8), ghi = ld4(a.gm[g] + pix * 8 + 4);
+    const float4 ylo = ld4(a.y[g] + pix * a.y_ld[g]), yhi = ld4(a.y[g] + pix * a.y_ld[g] + 4);
+    const float *A = a.coef[g] + n * 8, *B = A + a.batch * 8, *C = B + a.batch * 8;
+    v[0] = __float2bfloat16(A[0] * glo.x + B[0] * ylo.x + C[0]), v[1] = __float2bfloat16(A[1] * glo.y + B[1] * ylo.y + C[1]);
+    v[2] = __float2bfloat16(A[2] * glo.z + B[2] * ylo.z + C[2]), v[3] = __float2bfloat16(A[3] * glo.w + B[3] * ylo.w + C[3]);
+    v[4] = __float2bfloat16(A[4] * ghi.x + B[4] * yhi.x + C[4]), v[5] = __float2bfloat16(A[5] * ghi.y + B[5] * yhi.y + C[5]);
+    v[6] = __float2bfloat16(A[6] * ghi.z + B[6] * yhi.z + C[6]), v[7] = __float2bfloat16(A[7] * ghi.w + B[7] * yhi.w + C[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(0.f);
+  }
+  *reinterpret_cast<uint4 *>(a.dst + pix * 32 + g * 8) = *reinterpret_cast<const uint4 *>(v);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -306,7 +354,7 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
   a.S = span_y + 1 + 3;
   if (a.P > 256 || a.W % kTcM != 0) return 1;
   const size_t smem = tc_smem_bytes(a);
-  if (smem > 227 * 1024) return 1;
+  if (smem > 220 * 1024) return 1;
   CUtensorMap tmap;
   const cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, 4, (cuuint64_t)B};
   const cuuint64_t gstr[4] = {64, (cuuint64_t)a.W * 64, 16, (cuuint64_t)a.H * a.W * 64};
@@ -316,10 +364,10 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {  // (static shared memory of the kernel counts against the same 227 KB)
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    attr_smem = smem;
   }
   dim3 grid((a.W / kTcM) * a.row_chunks, B);
   SENAS_LAUNCH(conv_tc_fwd_kernel, grid, dim3(kTcThreads), smem, stream, tmap, a);

@@ -155,6 +155,7 @@ struct Plan {
   std::vector<NodePlan> nodes;
   std::vector<TcGroup> tc_groups;
   int64_t xb_off[2] = {-1, -1};  // saved: dense bf16 NHWC copy of an input state (floats offset)
+  int64_t dyb_off = -1;          // scratch: packed bf16 dy of a NORM group (backward)
   std::vector<BnDesc *> d_bnA, d_bnB;  // per stage
   std::vector<int> n_bnA, n_bnB;
   NodeDesc *d_nodes = nullptr;
@@ -222,7 +223,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         probe.taps = geo.taps;
         probe.P = (kTcM + geo.taps.max_dx - geo.taps.min_dx + 1) & ~1;
         probe.S = geo.taps.max_dy - geo.taps.min_dy + 4;
-        if (probe.P > 256 || tc_smem_bytes(probe) > 227 * 1024) continue;
+        if (probe.P > 256 || tc_smem_bytes(probe) > 220 * 1024) continue;
         TcGroup *grp = nullptr;
         for (auto &g2 : p->tc_groups)
           if (g2.src == ed.src && g2.op == ed.op_type && g2.kind == ed.kind[k] && g2.k == ed.ksize[k] &&
@@ -318,6 +319,9 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     np.bsum_off = take(sc, (int64_t)B * (1 + nterms) * 8);
     np.nterms = nterms;
   }
+  p->dyb_off = -1;
+  for (auto &g2 : p->tc_groups)
+    if (g2.op == SENAS_OP_NORM && p->dyb_off < 0) p->dyb_off = take(sc, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
   p->tmp_off = take(sc, tmp_need);
   p->tmp_floats = tmp_need;
   p->saved_floats = sv, p->scratch_floats = sc;
@@ -752,7 +756,7 @@ static int backward_edge(BwdCall &c, int e) {
       }
       case SENAS_KIND_CONV:
       case SENAS_KIND_SE_CONV: {
-        if (dx) {
+        if (dx && !(t.tc && ed.op_type == SENAS_OP_NORM)) {  // NORM tcgen05 groups: data gradient at the end of backward
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_DGRAD);
           GatherArgs a;
           memset(&a, 0, sizeof(a));
@@ -932,6 +936,40 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     for (int e = 0; e < d.n_edges; ++e)
       if (d.edge[e].dst == i && backward_edge(c, e)) return 1;
   }
+#ifndef SENAS_EMU
+  // grouped data gradient of the NORM tcgen05 groups: dx[src] += sum over the group's edges and taps (K = 8 x edges)
+  for (const TcGroup &g2 : p->tc_groups) {
+    if (g2.op != SENAS_OP_NORM || !a->grad_in[g2.src]) continue;
+    const EdgePlan &ep0 = p->edges[g2.edge[0]];
+    const int64_t npix = (int64_t)c.B * ep0.in_h * ep0.in_w;
+    __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off);
+    PackDyArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.nterms = g2.nterms, pa.hw = ep0.in_h * ep0.in_w, pa.batch = c.B, pa.dst = dyb;
+    TcConvArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.nterms = g2.nterms, ta.mode = 1;
+    for (int i = 0; i < g2.nterms; ++i) {
+      const int e = g2.edge[i], k = g2.cand[i];
+      const TermPlan &t = p->edges[e].t[k];
+      pa.gm[i] = c.scratch + p->nodes[d.edge[e].dst].gm_off, pa.y[i] = c.saved + t.y_off, pa.y_ld[i] = 8;
+      pa.coef[i] = c.scratch + t.coef_off;
+      ta.w[i] = (const float *)d.edge[e].param[k][0];
+    }
+    SENAS_TAG("pack_dy", 0, npix * (64.0 * g2.nterms + 64.0));
+    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, c.stream, pa);
+    Geo geo = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD);
+    ta.ws_t = 1;
+    conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);
+    ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = ep0.in_h, ta.Wo = ep0.in_w, ta.so = 1;
+    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
+    ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src], ta.accumulate = c.touched[g2.src];
+    SENAS_TAG("conv_tc_dgrad", 2.0 * npix * geo.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
+    const int rc = launch_conv_tc(dyb, c.B, ta, c.stream);
+    if (rc) SENAS_FAIL("tcgen05 dgrad launch failed (code %d)", rc);
+    c.touched[g2.src] = true;
+  }
+#endif
   for (int i = 0; i < d.n_inputs; ++i)
     if (a->grad_in[i] && !c.touched[i]) {
       if (a->grad_in_ld[i] != d.edge[0].c_in) SENAS_FAIL("backward: cannot zero a strided grad_in");
