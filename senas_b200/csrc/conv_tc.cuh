@@ -128,6 +128,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   uint64_t *full = bars, *empty = bars + a.S, *acc_full = bars + 2 * a.S, *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
   __shared__ float s_red[4][64];
+  __shared__ uint2 s_tap[25];
+  __shared__ uint32_t s_blo[25];
+  if (tid < T) {
+    s_tap[tid] = make_uint2((uint32_t)(a.taps.dy[tid] - a.taps.min_dy), (uint32_t)(a.taps.dx[tid] - a.taps.min_dx));
+    s_blo[tid] = (((smem_u32(smem) + (uint32_t)a.S * (uint32_t)a.P * 64u + (uint32_t)tid * 2048u) >> 4) & 0x3FFF) | ((512u >> 4) << 16);
+  }
 
   // ---- weights: fp32 global (PyTorch layout) -> bf16 canonical K-major tiles in shared memory
   for (int i = tid; i < T * 4 * kTcN; i += kTcThreads) {
@@ -174,22 +180,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
     if (lane == 0) {
       int idx = 0;
       for (int y = first_in; y <= last_in; ++y, ++idx) {
-        const int slot = idx % a.S, use = idx / a.S;
+        const int slot = idx & (a.S - 1), use = idx / a.S;
         if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
         mbar_expect_tx(&full[slot], row_bytes);
         tma_load_5d(rows + (size_t)slot * row_bytes, &tmap, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer =====  (one thread; the loop body is kept to a handful of integer ops per MMA: the ring has
+    // a power-of-two number of slots and the per-tap parts of both descriptors are precomputed in shared memory)
     if (lane == 0) {
-      const uint32_t rows_addr = smem_u32(rows), w_addr = smem_u32(wsm);
       const uint32_t lbo_a = (uint32_t)a.P * 16u;
+      const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;                  // SBO = 128 B, version 1
+      const uint32_t a_lo_base = ((smem_u32(rows) >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
+      const uint32_t a_khalf = (2u * lbo_a) >> 4, row16 = row_bytes >> 4;
+      const uint32_t smask = (uint32_t)a.S - 1u;
       int waited = 0, it = 0;
       for (int r = r0; r < r_end; ++r, ++it) {
         const int need = r + a.taps.max_dy - first_in + 1;
         while (waited < need) {
-          mbar_wait(&full[waited % a.S], (uint32_t)((waited / a.S) & 1));
+          mbar_wait(&full[waited & smask], (uint32_t)((waited / a.S) & 1));
           ++waited;
         }
         const int buf = it & 1;
@@ -198,20 +208,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
         for (int ph = 0; ph < NPH; ++ph) {
           const uint32_t d = tmem_base + (uint32_t)((buf * NPH + ph) * kTcN);
           uint32_t acc = 0;
-          for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
-            const int slot = (r + a.taps.dy[t] - first_in) % a.S;
-            const uint32_t a0 = rows_addr + (uint32_t)slot * row_bytes + (uint32_t)(a.taps.dx[t] - a.taps.min_dx) * 16u;
-            const uint32_t b0 = w_addr + (uint32_t)t * 2048u;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {  // K = 32 channels = 2 x (K = 16)
-              umma_bf16(d, umma_desc(a0 + (uint32_t)j * 2u * lbo_a, lbo_a, 128u), umma_desc(b0 + (uint32_t)j * 1024u, 512u, 128u),
-                        kTcIdesc, acc);
-              acc = 1;
-            }
+          const int t1 = a.taps.pstart[ph + 1];
+          for (int t = a.taps.pstart[ph]; t < t1; ++t) {
+            const uint2 tp = s_tap[t];  // x: dy - min_dy (rows), y: ((dx - min_dx) pixels) in 16-byte units
+            const uint32_t alo = a_lo_base + (((uint32_t)it + tp.x) & smask) * row16 + tp.y;
+            const uint32_t blo = s_blo[t];
+            umma_bf16(d, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, kTcIdesc, acc);
+            umma_bf16(d, ((uint64_t)a_hi << 32) | (alo + a_khalf), ((uint64_t)b_hi << 32) | (blo + 64u), kTcIdesc, 1u);
+            acc = 1;
           }
         }
-        tc_commit(&acc_full[buf]);   // accumulators of this row are complete when all MMAs above retire
-        tc_commit(&empty[it % a.S]); // ... and input row (r + min_dy) is no longer needed by any later row
+        tc_commit(&acc_full[buf]);        // accumulators of this row are complete when all MMAs above retire
+        tc_commit(&empty[it & smask]);    // ... and input row (r + min_dy) is no longer needed by any later row
       }
     }
   } else {
@@ -351,7 +359,8 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
   if (!enc) return 2;
   const int span_x = a.taps.max_dx - a.taps.min_dx, span_y = a.taps.max_dy - a.taps.min_dy;
   a.P = (kTcM + span_x + 1) & ~1;
-  a.S = span_y + 1 + 3;
+  a.S = 16;  // power of two (cheap slot arithmetic in the single-thread issue loop)
+  if (span_y + 4 > a.S) return 1;
   if (a.P > 256 || a.W % kTcM != 0) return 1;
   const size_t smem = tc_smem_bytes(a);
   if (smem > 220 * 1024) return 1;

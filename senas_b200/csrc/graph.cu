@@ -222,8 +222,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         TcConvArgs probe;
         probe.taps = geo.taps;
         probe.P = (kTcM + geo.taps.max_dx - geo.taps.min_dx + 1) & ~1;
-        probe.S = geo.taps.max_dy - geo.taps.min_dy + 4;
-        if (probe.P > 256 || tc_smem_bytes(probe) > 220 * 1024) continue;
+        probe.S = 16;
+        if (geo.taps.max_dy - geo.taps.min_dy + 4 > probe.S || probe.P > 256 || tc_smem_bytes(probe) > 220 * 1024) continue;
         TcGroup *grp = nullptr;
         for (auto &g2 : p->tc_groups)
           if (g2.src == ed.src && g2.op == ed.op_type && g2.kind == ed.kind[k] && g2.k == ed.ksize[k] &&
@@ -285,8 +285,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
           t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C), t.psum1_off = take(sc, (int64_t)B * 2 * C);
-          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 128 * kPxTilesPerBlock) * 10 * C + 16 * C;
-          const int64_t dw_tmp = (int64_t)B * cdiv(bh * bw, kDwChunk) * C * T;
+          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 2048) * 10 * C + 16 * C;
+          const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 8)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           break;
         }
@@ -805,36 +805,38 @@ static int backward_edge(BwdCall &c, int e) {
       case SENAS_KIND_DEPSEP: {
         PwBwdArgs a;
         memset(&a, 0, sizeof(a));
-        const int nblk_pw = cdiv(HW, 128 * kPxTilesPerBlock);
-        float *sums1 = tmp + (int64_t)B * nblk_pw * 10 * C, *coef1 = sums1 + 12 * C;
+        float *sums1 = nullptr, *coef1 = nullptr;
         a.gm = gm, a.y = y, a.z = c.saved + t.z_off, a.hw = HW, a.batch = B, a.coefA = cA, a.coefB = cB, a.coefC = cC;
         a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
         a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
         a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1;
-        dim3 grid(cdiv(HW, 128), B), grid_st(nblk_pw, B);
+        const int px_pb = 2048, nblk_cc = cdiv(HW, px_pb);
+        dim3 grid_cc(nblk_cc, B);
         if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
           SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
+        sums1 = tmp + (int64_t)B * nblk_cc * 10 * C, coef1 = sums1 + 12 * C;
+        a.bn1_coef = coef1;
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
         if (C == 32) {
-          auto kern = pw_bwd_stats_kernel<32>;
-          SENAS_LAUNCH(kern, grid_st, dim3(128), 0, c.stream, a);
+          auto kern = pw_bwd_cc_kernel<32, 1>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
         } else {
-          auto kern = pw_bwd_stats_kernel<8>;
-          SENAS_LAUNCH(kern, grid_st, dim3(128), 0, c.stream, a);
+          auto kern = pw_bwd_cc_kernel<8, 1>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
         }
         SENAS_TAG("reduce", 0, 0);
         SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, 32), 1), dim3(256), 0, c.stream, (const float *)tmp, sums1,
-                     (int)(nblk_pw * B), 10 * C);
+                     (int)(nblk_cc * B), 10 * C);
         SENAS_TAG("pw_bfin", 0, 0);
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)sums1, C, (float)B * (float)HW, a.g1,
                      a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
         if (C == 32) {
-          auto kern = pw_bwd_dz_kernel<32>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a, c.a->training);
+          auto kern = pw_bwd_cc_kernel<32, 2>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
         } else {
-          auto kern = pw_bwd_dz_kernel<8>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a, c.a->training);
+          auto kern = pw_bwd_cc_kernel<8, 2>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
         }
         DwBwdArgs w;
         memset(&w, 0, sizeof(w));
@@ -863,12 +865,27 @@ static int backward_edge(BwdCall &c, int e) {
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g3(cdiv(w.base_h * w.base_w, w.chunk), B);
           SENAS_TAG("dw_wgrad", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + ep.in_h * ep.in_w * C));
+#define SENAS_DWSW(CC, KK, SS)                                 \
+  {                                                            \
+    auto kern = dw_wgrad_sw_kernel<CC, KK, SS>;                \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+  }
+          if (geo.so == 1) {  // NORM / DOWN: sliding register window, `chunk` = base rows per block
+            w.chunk = 8;
+            g3 = dim3(cdiv(w.base_h, w.chunk), B);
+          }
 #define SENAS_DWW(CC, TT)                                      \
   {                                                            \
     auto kern = dw_wgrad_kernel<CC, TT>;                       \
     SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
   }
-          if (C == 32 && T == 25) SENAS_DWW(32, 25)
+          if (geo.so == 1 && C == 32 && t.k == 5 && geo.si == 1) SENAS_DWSW(32, 5, 1)
+          else if (geo.so == 1 && C == 32 && t.k == 5 && geo.si == 2) SENAS_DWSW(32, 5, 2)
+          else if (geo.so == 1 && C == 32 && t.k == 3 && geo.si == 1) SENAS_DWSW(32, 3, 1)
+          else if (geo.so == 1 && C == 32 && t.k == 3 && geo.si == 2) SENAS_DWSW(32, 3, 2)
+          else if (geo.so == 1 && C == 8 && t.k == 5 && geo.si == 1) SENAS_DWSW(8, 5, 1)
+          else if (geo.so == 1 && C == 8 && t.k == 3 && geo.si == 1) SENAS_DWSW(8, 3, 1)
+          else if (C == 32 && T == 25) SENAS_DWW(32, 25)
           else if (C == 32 && T == 9) SENAS_DWW(32, 9)
           else if (C == 8 && T == 25) SENAS_DWW(8, 25)
           else if (C == 8 && T == 9) SENAS_DWW(8, 9)

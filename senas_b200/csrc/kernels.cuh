@@ -1320,3 +1320,139 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(DwBwdArgs a) {
     out[o] = r;
   }
 }
+
+// depthwise weight gradient, stride-1 output grids (NORM, DOWN): sliding register window along x.
+// thread = (channel, strip); a strip walks 64-pixel row segments keeping the K x K input window of its channel in
+// registers, so each step loads K*SI new inputs instead of K*K.  Same partial layout as dw_wgrad_kernel.
+template <int C, int K, int SI>
+__global__ void __launch_bounds__(256) dw_wgrad_sw_kernel(DwBwdArgs a) {
+  constexpr int NS = 256 / C, T = K * K, PAD = K / 2, L = 64, WC = K + SI - 1;
+  __shared__ float s_red[NS][C * T + 1];
+  const int tid = threadIdx.x, c = tid % C, strip = tid / C, n = blockIdx.y;
+  const int segs = (a.base_w + L - 1) / L;
+  const int row0 = blockIdx.x * a.chunk, rows = min(a.chunk, a.base_h - row0);
+  const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld + c;
+  const float *zn = a.dz + (int64_t)n * a.z_h * a.z_w * C + c;
+  float acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.f;
+  for (int item = strip; item < rows * segs; item += NS) {
+    const int by = row0 + item / segs, bx0 = (item % segs) * L, bx1 = min(bx0 + L, a.base_w);
+    float win[K][WC];  // win[j][i] = x[by*SI + j - PAD][bx*SI + i - PAD]
+    const float *xr[K];
+    bool rok[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int iy = by * SI + j - PAD;
+      rok[j] = iy >= 0 && iy < a.x_h;
+      xr[j] = xn + (int64_t)(rok[j] ? iy : 0) * a.x_w * a.x_ld;
+#pragma unroll
+      for (int i = SI; i < WC; ++i) {  // columns that survive the first shift
+        const int ix = bx0 * SI + (i - SI) - PAD;
+        win[j][i] = (rok[j] && ix >= 0 && ix < a.x_w) ? __ldg(xr[j] + (int64_t)ix * a.x_ld) : 0.f;
+      }
+    }
+    for (int bx = bx0; bx < bx1; ++bx) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+#pragma unroll
+        for (int i = 0; i + SI < WC; ++i) win[j][i] = win[j][i + SI];
+#pragma unroll
+        for (int i = WC - SI; i < WC; ++i) {
+          const int ix = bx * SI + i - PAD;
+          win[j][i] = (rok[j] && ix >= 0 && ix < a.x_w) ? __ldg(xr[j] + (int64_t)ix * a.x_ld) : 0.f;
+        }
+      }
+      const float zv = zn[((int64_t)by * a.z_w + bx) * C];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc[j * K + i] = fmaf(win[j][i], zv, acc[j * K + i]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) s_red[strip][c * T + t] = acc[t];
+  __syncthreads();
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * C * T;
+  for (int o = tid; o < C * T; o += 256) {
+    float r = 0.f;
+    for (int q = 0; q < NS; ++q) r += s_red[q][o];
+    out[o] = r;
+  }
+}
+
+// dep-sep pointwise backward, channel-centric: lane = channel (C = 32: one pixel per warp step; C = 8: four pixels),
+// the 8 dy values of a pixel are computed once per warp and broadcast with shuffles, the column W_pw[:, c] lives in
+// registers, and every reduction (sum du, sum du*zhat, dW_pw[:, c]) stays inside the lane -- no shared-memory transposes.
+//   PASS 1: statistics + dW_pw partials ([10C] per block, same layout as before);   PASS 2: dz in place over z.
+template <int C, int PASS>
+__global__ void __launch_bounds__(256) pw_bwd_cc_kernel(PwBwdArgs a, int px_per_block, int training) {
+  constexpr int PPW = 32 / C;  // pixels per warp step
+  __shared__ float s_part[8][10 * C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+  const int c = lane % C, sub = lane / C;
+  const float g1 = a.g1[c], b1 = a.b1[c], mean1 = a.mean1[c], istd1 = a.istd1[c];
+  const float sc = g1 * istd1, sh = b1 - mean1 * sc;
+  float wc[8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co) wc[co] = __ldg(a.wpw + co * C + c);
+  const int co_l = lane & 7;
+  const float cA = a.coefA[n * 8 + co_l], cB = a.coefB[n * 8 + co_l], cC = a.coefC[n * 8 + co_l];
+  float k0 = 0.f, k1 = 0.f, k2 = 0.f;
+  if (PASS == 2) k0 = a.bn1_coef[c], k1 = a.bn1_coef[C + c], k2 = a.bn1_coef[2 * C + c];
+  float s_du = 0.f, s_duz = 0.f, dw[8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co) dw[co] = 0.f;
+  const int p_begin = blockIdx.x * px_per_block, p_end = min(p_begin + px_per_block, a.hw);
+  const int per_warp = (px_per_block + 7) / 8;
+  const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
+  for (int p0 = w_begin; p0 < w_end; p0 += PPW) {
+    const int p = p0 + sub;
+    const bool ok = p < w_end;
+    const int64_t pix = (int64_t)n * a.hw + (ok ? p : w_begin);
+    // dy[co] of this lane's pixel: lane (sub*C.. ) group computes co = lane & 7 (C == 32: 4x redundant, coalesced)
+    const int64_t pix_d = (C == 32) ? pix : (int64_t)n * a.hw + min(p0 + (lane >> 3), w_end - 1);
+    const float dyl = cA * a.gm[pix_d * 8 + co_l] + cB * a.y[pix_d * 8 + co_l] + cC;
+    float dy[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) dy[co] = __shfl_sync(0xffffffffu, dyl, (C == 32 ? 0 : sub * 8) + co);
+    const float z = a.z[pix * C + c];
+    const float u = fmaf(z, sc, sh);
+    float dr = 0.f;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) dr = fmaf(dy[co], wc[co], dr);
+    const float du = (u > 0.f && ok) ? dr : 0.f;
+    const float zhat = (z - mean1) * istd1;
+    if (PASS == 1) {
+      const float r = ok ? fmaxf(u, 0.f) : 0.f;
+      s_du += du, s_duz += du * zhat;
+#pragma unroll
+      for (int co = 0; co < 8; ++co) dw[co] = fmaf(dy[co], r, dw[co]);
+    } else if (ok) {
+      a.z[pix * C + c] = training ? k0 * (du - k1 - zhat * k2) : k0 * du;
+    }
+  }
+  if (PASS == 1) {
+    // combine the PPW pixel groups of a warp (C == 8) and the 8 warps in fixed order
+    if (C == 8) {
+#pragma unroll
+      for (int m = 8; m < 32; m <<= 1) {
+        s_du += __shfl_xor_sync(0xffffffffu, s_du, m), s_duz += __shfl_xor_sync(0xffffffffu, s_duz, m);
+#pragma unroll
+        for (int co = 0; co < 8; ++co) dw[co] += __shfl_xor_sync(0xffffffffu, dw[co], m);
+      }
+    }
+    if (lane < C) {
+      s_part[warp][c] = s_du, s_part[warp][C + c] = s_duz;
+#pragma unroll
+      for (int co = 0; co < 8; ++co) s_part[warp][2 * C + co * C + c] = dw[co];
+    }
+    __syncthreads();
+    float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
+    for (int o = tid; o < 10 * C; o += 256) {
+      float r = 0.f;
+      for (int w = 0; w < 8; ++w) r += s_part[w][o];
+      out[o] = r;
+    }
+  }
+}

@@ -184,6 +184,8 @@ static inline T __shfl_sync(unsigned, T v, int s) {
   return emu::warp_exchange<T>(v, emu::lane_idx, s);
 }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 
 
 #define SENAS_LAUNCH(kern, grid, block, smem, stream, ...)                  \
