@@ -285,8 +285,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
           t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C), t.psum1_off = take(sc, (int64_t)B * 2 * C);
-          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 2048) * 10 * C + 16 * C;
-          const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 8)) * C * T;
+          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
+          const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           break;
         }
@@ -810,7 +810,7 @@ static int backward_edge(BwdCall &c, int e) {
         a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
         a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
         a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1;
-        const int px_pb = 2048, nblk_cc = cdiv(HW, px_pb);
+        const int px_pb = 512, nblk_cc = cdiv(HW, px_pb);
         dim3 grid_cc(nblk_cc, B);
         if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
           SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
@@ -831,12 +831,13 @@ static int backward_edge(BwdCall &c, int e) {
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)sums1, C, (float)B * (float)HW, a.g1,
                      a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
+        dim3 grid_px(cdiv(HW, 128), B);
         if (C == 32) {
-          auto kern = pw_bwd_cc_kernel<32, 2>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
+          auto kern = pw_bwd_dz_kernel<32>;
+          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, c.stream, a, c.a->training);
         } else {
-          auto kern = pw_bwd_cc_kernel<8, 2>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
+          auto kern = pw_bwd_dz_kernel<8>;
+          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, c.stream, a, c.a->training);
         }
         DwBwdArgs w;
         memset(&w, 0, sizeof(w));
@@ -871,7 +872,7 @@ static int backward_edge(BwdCall &c, int e) {
     SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
   }
           if (geo.so == 1) {  // NORM / DOWN: sliding register window, `chunk` = base rows per block
-            w.chunk = 8;
+            w.chunk = 4;
             g3 = dim3(cdiv(w.base_h, w.chunk), B);
           }
 #define SENAS_DWW(CC, TT)                                      \

@@ -289,11 +289,15 @@ __global__ void conv_wgrad_kernel(WgradArgs a) {
         const bool ok = bok && iy >= 0 && iy < a.x_h && ix >= 0 && ix < a.x_w;
         xv_[j] = ok ? __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld + ci) : 0.f;
       }
+      const float4 lo1 = s_lo[ty * otw + tx], hi1 = s_hi[ty * otw + tx];  // so == 1: one dy per pixel for every tap
 #pragma unroll
       for (int j = 0; j < TPT; ++j) {
         const float xv = xv_[j];
-        const int idx = (ty * a.so + (tph[j] >> 1)) * otw + tx * a.so + (tph[j] & 1);
-        const float4 lo = s_lo[idx], hi = s_hi[idx];
+        float4 lo = lo1, hi = hi1;
+        if (a.so != 1) {
+          const int idx = (ty * a.so + (tph[j] >> 1)) * otw + tx * a.so + (tph[j] & 1);
+          lo = s_lo[idx], hi = s_hi[idx];
+        }
         acc[j][0] = fmaf(xv, lo.x, acc[j][0]);
         acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
         acc[j][2] = fmaf(xv, lo.z, acc[j][2]);
@@ -1406,30 +1410,42 @@ __global__ void __launch_bounds__(256) pw_bwd_cc_kernel(PwBwdArgs a, int px_per_
   const int p_begin = blockIdx.x * px_per_block, p_end = min(p_begin + px_per_block, a.hw);
   const int per_warp = (px_per_block + 7) / 8;
   const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
-  for (int p0 = w_begin; p0 < w_end; p0 += PPW) {
-    const int p = p0 + sub;
-    const bool ok = p < w_end;
-    const int64_t pix = (int64_t)n * a.hw + (ok ? p : w_begin);
-    // dy[co] of this lane's pixel: lane (sub*C.. ) group computes co = lane & 7 (C == 32: 4x redundant, coalesced)
-    const int64_t pix_d = (C == 32) ? pix : (int64_t)n * a.hw + min(p0 + (lane >> 3), w_end - 1);
-    const float dyl = cA * a.gm[pix_d * 8 + co_l] + cB * a.y[pix_d * 8 + co_l] + cC;
-    float dy[8];
+  constexpr int UN = 4;  // pixel groups in flight per warp step (memory-level parallelism)
+  for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
+    float zv[UN], dyl[UN];
+    bool okv[UN];
+    int64_t pixv[UN];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) dy[co] = __shfl_sync(0xffffffffu, dyl, (C == 32 ? 0 : sub * 8) + co);
-    const float z = a.z[pix * C + c];
-    const float u = fmaf(z, sc, sh);
-    float dr = 0.f;
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      okv[u] = p < w_end;
+      pixv[u] = (int64_t)n * a.hw + (okv[u] ? p : w_begin);
+      const int pd = p0 + u * PPW + (C == 32 ? 0 : (lane >> 3));
+      const int64_t pix_d = (int64_t)n * a.hw + (pd < w_end ? pd : w_begin);
+      zv[u] = a.z[pixv[u] * C + c];
+      dyl[u] = cA * a.gm[pix_d * 8 + co_l] + cB * a.y[pix_d * 8 + co_l] + cC;
+    }
 #pragma unroll
-    for (int co = 0; co < 8; ++co) dr = fmaf(dy[co], wc[co], dr);
-    const float du = (u > 0.f && ok) ? dr : 0.f;
-    const float zhat = (z - mean1) * istd1;
-    if (PASS == 1) {
-      const float r = ok ? fmaxf(u, 0.f) : 0.f;
-      s_du += du, s_duz += du * zhat;
+    for (int u = 0; u < UN; ++u) {
+      float dy[8];
 #pragma unroll
-      for (int co = 0; co < 8; ++co) dw[co] = fmaf(dy[co], r, dw[co]);
-    } else if (ok) {
-      a.z[pix * C + c] = training ? k0 * (du - k1 - zhat * k2) : k0 * du;
+      for (int co = 0; co < 8; ++co) dy[co] = __shfl_sync(0xffffffffu, dyl[u], (C == 32 ? 0 : sub * 8) + co);
+      const float z = zv[u];
+      const bool ok = okv[u];
+      const float uu = fmaf(z, sc, sh);
+      float dr = 0.f;
+#pragma unroll
+      for (int co = 0; co < 8; ++co) dr = fmaf(dy[co], wc[co], dr);
+      const float du = (uu > 0.f && ok) ? dr : 0.f;
+      const float zhat = (z - mean1) * istd1;
+      if (PASS == 1) {
+        const float r = ok ? fmaxf(uu, 0.f) : 0.f;
+        s_du += du, s_duz += du * zhat;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) dw[co] = fmaf(dy[co], r, dw[co]);
+      } else if (ok) {
+        a.z[pixv[u] * C + c] = training ? k0 * (du - k1 - zhat * k2) : k0 * du;
+      }
     }
   }
   if (PASS == 1) {
