@@ -871,10 +871,15 @@ static int backward_edge(BwdCall &c, int e) {
     auto kern = dw_wgrad_sw_kernel<CC, KK, SS>;                \
     SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
   }
-          if (geo.so == 1) {  // NORM / DOWN: sliding register window, `chunk` = base rows per block
+          {  // sliding register window kernels: `chunk` = base rows per block
             w.chunk = 4;
             g3 = dim3(cdiv(w.base_h, w.chunk), B);
           }
+#define SENAS_DWUP(CC, KK)                                     \
+  {                                                            \
+    auto kern = dw_wgrad_up_kernel<CC, KK>;                    \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+  }
 #define SENAS_DWW(CC, TT)                                      \
   {                                                            \
     auto kern = dw_wgrad_kernel<CC, TT>;                       \
@@ -886,6 +891,8 @@ static int backward_edge(BwdCall &c, int e) {
           else if (geo.so == 1 && C == 32 && t.k == 3 && geo.si == 2) SENAS_DWSW(32, 3, 2)
           else if (geo.so == 1 && C == 8 && t.k == 5 && geo.si == 1) SENAS_DWSW(8, 5, 1)
           else if (geo.so == 1 && C == 8 && t.k == 3 && geo.si == 1) SENAS_DWSW(8, 3, 1)
+          else if (geo.so == 2 && C == 32 && t.k == 5) SENAS_DWUP(32, 5)
+          else if (geo.so == 2 && C == 32 && t.k == 3) SENAS_DWUP(32, 3)
           else if (C == 32 && T == 25) SENAS_DWW(32, 25)
           else if (C == 32 && T == 9) SENAS_DWW(32, 9)
           else if (C == 8 && T == 25) SENAS_DWW(8, 25)

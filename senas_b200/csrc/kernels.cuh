@@ -289,15 +289,11 @@ __global__ void conv_wgrad_kernel(WgradArgs a) {
         const bool ok = bok && iy >= 0 && iy < a.x_h && ix >= 0 && ix < a.x_w;
         xv_[j] = ok ? __ldg(xn + ((int64_t)iy * a.x_w + ix) * a.x_ld + ci) : 0.f;
       }
-      const float4 lo1 = s_lo[ty * otw + tx], hi1 = s_hi[ty * otw + tx];  // so == 1: one dy per pixel for every tap
 #pragma unroll
       for (int j = 0; j < TPT; ++j) {
         const float xv = xv_[j];
-        float4 lo = lo1, hi = hi1;
-        if (a.so != 1) {
-          const int idx = (ty * a.so + (tph[j] >> 1)) * otw + tx * a.so + (tph[j] & 1);
-          lo = s_lo[idx], hi = s_hi[idx];
-        }
+        const int idx = (ty * a.so + (tph[j] >> 1)) * otw + tx * a.so + (tph[j] & 1);
+        const float4 lo = s_lo[idx], hi = s_hi[idx];
         acc[j][0] = fmaf(xv, lo.x, acc[j][0]);
         acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
         acc[j][2] = fmaf(xv, lo.z, acc[j][2]);
@@ -1470,5 +1466,70 @@ __global__ void __launch_bounds__(256) pw_bwd_cc_kernel(PwBwdArgs a, int px_per_
       for (int w = 0; w < 8; ++w) r += s_part[w][o];
       out[o] = r;
     }
+  }
+}
+
+// depthwise weight gradient of the transposed (UP) depthwise conv: dW[c][ky][kx] = sum_b x[b + d(ky), b + d(kx)] *
+// dz[2b + p(ky), 2b + p(kx)] with p(kk) = (K/2 + kk) & 1, d(kk) = (p + K/2 - kk) / 2.  Per input
+// pixel b only a 3x3 window of x and the 2x2 block of dz are needed; the x window slides along the row in registers.
+template <int C, int K>
+__global__ void __launch_bounds__(256) dw_wgrad_up_kernel(DwBwdArgs a) {
+  constexpr int NS = 256 / C, T = K * K, PAD = K / 2, L = 64;
+  __shared__ float s_red[NS][C * T + 1];
+  const int tid = threadIdx.x, c = tid % C, strip = tid / C, n = blockIdx.y;
+  const int segs = (a.base_w + L - 1) / L;
+  const int row0 = blockIdx.x * a.chunk, rows = min(a.chunk, a.base_h - row0);
+  const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld + c;
+  const float *zn = a.dz + (int64_t)n * a.z_h * a.z_w * C + c;
+  float acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.f;
+  for (int item = strip; item < rows * segs; item += NS) {
+    const int by = row0 + item / segs, bx0 = (item % segs) * L, bx1 = min(bx0 + L, a.base_w);
+    float win[3][3];  // win[j][i] = x[by + j - 1][bx + i - 1]
+    const float *xr[3];
+    bool rok[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int iy = by + j - 1;
+      rok[j] = iy >= 0 && iy < a.x_h;
+      xr[j] = xn + (int64_t)(rok[j] ? iy : 0) * a.x_w * a.x_ld;
+#pragma unroll
+      for (int i = 1; i < 3; ++i) {
+        const int ix = bx0 + (i - 1) - 1;
+        win[j][i] = (rok[j] && ix >= 0 && ix < a.x_w) ? __ldg(xr[j] + (int64_t)ix * a.x_ld) : 0.f;
+      }
+    }
+    for (int bx = bx0; bx < bx1; ++bx) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        win[j][0] = win[j][1], win[j][1] = win[j][2];
+        const int ix = bx + 1;
+        win[j][2] = (rok[j] && ix < a.x_w) ? __ldg(xr[j] + (int64_t)ix * a.x_ld) : 0.f;
+      }
+      float zv[2][2];
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) zv[py][px] = zn[((int64_t)(2 * by + py) * a.z_w + 2 * bx + px) * C];
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int py = (PAD + ky) & 1, dy = (py + PAD - ky) / 2;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int px = (PAD + kx) & 1, dx = (px + PAD - kx) / 2;
+          acc[ky * K + kx] = fmaf(win[dy + 1][dx + 1], zv[py][px], acc[ky * K + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) s_red[strip][c * T + t] = acc[t];
+  __syncthreads();
+  float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * C * T;
+  for (int o = tid; o < C * T; o += 256) {
+    float r = 0.f;
+    for (int q = 0; q < NS; ++q) r += s_red[q][o];
+    out[o] = r;
   }
 }
