@@ -158,7 +158,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import senas_b200
     from senas_b200 import _lib
-    from senas_b200.dp import GradBuckets, broadcast_parameters
+    from senas_b200.dp import FusedGradReducer, GradBuckets, broadcast_parameters
     from senas_b200.loss import SegmentationLosses
 
     dev = torch.device('cuda', local_rank)
@@ -183,7 +183,15 @@ def run_ours(args, rank, world, local_rank):
     buckets = None
     if world > 1:
         broadcast_parameters(model)
-        buckets = GradBuckets(list(model.parameters()), model.arch_parameters())
+        fused_red = FusedGradReducer()            # cells: flat gradient buffers straight from the kernels
+        hooks = GradBuckets(list(model.parameters()), model.arch_parameters(), exclude=fused_red.owned(model))
+
+        class _Both:                              # the rest (stems, pre/post blocks, arch parameters): hook buckets
+            @staticmethod
+            def finish():
+                fused_red.finish()
+                hooks.finish()
+        buckets = _Both
 
     host = [synth(B, size, 1234 + 17 * rank + i, True) for i in range(4)]  # train0, valid0, train1, valid1
     devb = [(x.to(dev), y.to(dev)) for x, y in host]

@@ -15,9 +15,9 @@ class GradBuckets:
     order in which backward produces gradients; arch parameters (which accumulate over every cell) go
     into the last bucket."""
 
-    def __init__(self, params, arch_params=(), bucket_floats=1 << 19, group=None):
+    def __init__(self, params, arch_params=(), bucket_floats=1 << 19, group=None, exclude=()):
         self.group = group
-        arch_ids = {id(p) for p in arch_params}
+        arch_ids = {id(p) for p in arch_params} | set(exclude)
         seen, ordered = set(), []
         for p in reversed([p for p in params if p.requires_grad]):
             if id(p) not in seen and id(p) not in arch_ids:
@@ -32,7 +32,7 @@ class GradBuckets:
                 cur, n = [], 0
         if cur:
             buckets.append(cur)
-        arch = [p for p in arch_params if p.requires_grad]
+        arch = [p for p in arch_params if p.requires_grad and id(p) not in set(exclude)]
         if arch:
             buckets.append(list({id(p): p for p in arch}.values()))
         self.buckets = buckets
@@ -75,6 +75,36 @@ class GradBuckets:
                 else:
                     p.grad.copy_(o.view_as(p))
             self.work[bi], self.pending[bi] = None, 0
+
+
+class FusedGradReducer:
+    """All-reduce of the fused cells' parameter gradients without per-parameter hooks: every fused backward hands
+    over its flat gradient buffer (one per MixedOp / Cell graph, ~0.1 M floats for a cell) and the NCCL all-reduce is
+    launched on it at once, overlapping the rest of backward.  Autograd then adopts *views* of that buffer as
+    ``p.grad`` (it steals a gradient when ``p.grad is None``), so the reduced values appear in place.  ``finish``
+    verifies the aliasing and falls back to a copy if autograd had to accumulate instead."""
+
+    def __init__(self, group=None):
+        from . import fused
+        self.group, self.pending = group, []
+        fused.set_grad_sink(self._sink)
+
+    def _sink(self, runner, flat):
+        self.pending.append((runner, flat, dist.all_reduce(flat, group=self.group, async_op=True)))
+
+    def finish(self):
+        for runner, flat, work in self.pending:
+            work.wait()
+            p0 = runner.params[0]
+            if p0.grad is None or p0.grad.data_ptr() != flat.data_ptr():  # not adopted as a view: write back
+                for p, g in zip(runner.params, torch.split(flat, runner.sizes)):
+                    p.grad = g.view_as(p).clone()
+        self.pending.clear()
+
+    def owned(self, module):
+        """ids of the parameters that travel through the fused graphs of ``module`` (every MixedOp candidate)."""
+        from .cell import MixedOp
+        return {id(p) for m in module.modules() if isinstance(m, MixedOp) for p in m.parameters()}
 
 
 def broadcast_parameters(module, src=0, group=None):

@@ -54,6 +54,13 @@ def candidate_slots(op):
 
 _scratch = {}
 _flags = {'tc_bf16': False}
+_grad_sink = [None]
+
+
+def set_grad_sink(fn):
+    """``fn(runner, flat_grad)`` is called from every fused backward right after the kernels are enqueued, with the
+    graph's flat parameter-gradient buffer (senas_b200.dp all-reduces it in place while backward continues)."""
+    _grad_sink[0] = fn
 
 
 def set_conv_mode(mode):
@@ -239,5 +246,7 @@ class _GraphFn(torch.autograd.Function):
         g_ins, g_alpha, g_beta, g_params = runner.backward(ins, alpha, beta, out, _nhwc(grad_out.float()),
                                                            ctx.saved_buf, ctx.training, need_in)
         ctx.saved_buf = None  # the library overwrote parts of it (dz in place of z)
+        if _grad_sink[0] is not None:
+            _grad_sink[0](runner, g_params)
         grads = [g.view(s) for g, s in zip(torch.split(g_params, runner.sizes), runner.shapes)]
         return (None, None, g_alpha, g_beta, g_ins[0], g_ins[1] if in1 is not None else None, *grads)
