@@ -779,20 +779,32 @@ static int backward_edge(BwdCall &c, int e) {
           a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.gm = gm, a.y = y, a.y_ld = y_ld;
           a.o_h = p.out_h, a.o_w = p.out_w, a.coefA = cA, a.coefB = cB, a.coefC = cC;
           a.base_h = geo.base_is_out ? p.out_h : ep.in_h, a.base_w = geo.base_is_out ? p.out_w : ep.in_w;
-          a.si = geo.si, a.so = geo.so, a.tiles_x = cdiv(a.base_w, kTileW), a.tiles_y = cdiv(a.base_h, kTileH);
+          a.si = geo.si, a.so = geo.so;
           a.batch = B, a.partials = tmp, a.taps = geo.taps;
-          const int items = a.tiles_x * a.tiles_y * B, nblk = std::min(items, kPersistBlocks);
-          const size_t smem = (size_t)2 * (kTileH * geo.so) * (kTileW * geo.so) * 16;
-#define SENAS_WGRAD(KC, TPT)                                                             \
-  {                                                                                      \
-    auto kern = conv_wgrad_kernel<KC, TPT>;                                              \
+          int nblk = 0;
+#define SENAS_WGRAD2(KC, KK, SI_, SO_)                                                                             \
+  {                                                                                                                \
+    using TL = WgradTile<KC, KK, SI_, SO_>;                                                                        \
+    a.tiles_x = cdiv(a.base_w, TL::TW), a.tiles_y = cdiv(a.base_h, TL::TH);                                        \
+    nblk = std::min(a.tiles_x * a.tiles_y * B, kPersistBlocks);                                                    \
+    const int XR = (TL::TH - 1) * SI_ + geo.taps.max_dy - geo.taps.min_dy + 1;                                     \
+    const int XC = (TL::TW - 1) * SI_ + geo.taps.max_dx - geo.taps.min_dx + 1;                                     \
+    const size_t smem = (size_t)((XR * XC * KC + 3) / 4) * 16 + (size_t)2 * TL::TH * SO_ * TL::TW * SO_ * 16;     \
+    auto kern = conv_wgrad2_kernel<KC, KK, SI_, SO_>;                                                              \
+    allow_smem(kern, smem);                                                                                        \
     SENAS_TAG("conv_wgrad", 2.0 * B * a.base_h * a.base_w * T * KC * 8, 4.0 * B * (ep.in_h * ep.in_w * KC + HW * 16)); \
-    SENAS_LAUNCH(kern, dim3(nblk), dim3(KC * (T / TPT)), smem, c.stream, a);             \
+    SENAS_LAUNCH(kern, dim3(nblk), dim3(TL::THREADS), smem, c.stream, a);                                          \
   }
-          if (C == 32 && t.k == 5) SENAS_WGRAD(32, 5)
-          else if (C == 32 && t.k == 3) SENAS_WGRAD(32, 3)
-          else if (C == 8) SENAS_WGRAD(8, 1)
-          else SENAS_FAIL("conv wgrad: unsupported c_in %d k %d", C, t.k);
+          const int si_ = geo.si, so_ = geo.so;
+          if (C == 32 && t.k == 5 && si_ == 1 && so_ == 1) SENAS_WGRAD2(32, 5, 1, 1)
+          else if (C == 32 && t.k == 5 && si_ == 2 && so_ == 1) SENAS_WGRAD2(32, 5, 2, 1)
+          else if (C == 32 && t.k == 5 && si_ == 1 && so_ == 2) SENAS_WGRAD2(32, 5, 1, 2)
+          else if (C == 32 && t.k == 3 && si_ == 2 && so_ == 1) SENAS_WGRAD2(32, 3, 2, 1)
+          else if (C == 32 && t.k == 3 && si_ == 1 && so_ == 2) SENAS_WGRAD2(32, 3, 1, 2)
+          else if (C == 32 && t.k == 3 && si_ == 1 && so_ == 1) SENAS_WGRAD2(32, 3, 1, 1)
+          else if (C == 8 && t.k == 5 && si_ == 1 && so_ == 1) SENAS_WGRAD2(8, 5, 1, 1)
+          else if (C == 8 && t.k == 3 && si_ == 1 && so_ == 1) SENAS_WGRAD2(8, 3, 1, 1)
+          else SENAS_FAIL("conv wgrad: unsupported c_in %d k %d geometry", C, t.k);
           int ws_ci, ws_co;
           conv_weight_strides(ed.op_type, C, T, DIR_FWD, &ws_ci, &ws_co);
           const int n = T * C * 8;

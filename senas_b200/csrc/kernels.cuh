@@ -1533,3 +1533,122 @@ __global__ void __launch_bounds__(256) dw_wgrad_up_kernel(DwBwdArgs a) {
     out[o] = r;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// convolution weight gradient, shared-memory tiled (replaces conv_wgrad_kernel on the hot path).
+// The ncu capture of the first version (profiles/) showed DRAM traffic ~ algorithmic but only ~21 % of the
+// executed instructions being FMAs (per-tap index math + global loads).  Here the x tile (with halo) and the dy tile
+// are staged once per tile, every tap address is `row base register + immediate`, and the pixel loop is fully
+// unrolled along x:  per pixel and thread  K LDS (x) + 2 LDS.128 (dy) + 8K FMA.
+//   thread = (ci, ky, pixel split)   KC = 32: 32 x K threads;   KC = 8: 8 x K x 4 (row-interleaved pixel splits)
+// ------------------------------------------------------------------------------------------------
+template <int KC, int K, int SI, int SO>
+struct WgradTile {
+  static constexpr int TH = (SI == 2) ? 4 : 8;
+  static constexpr int TW = (SI == 2) ? 8 : 16;
+  static constexpr int PS = 32 / KC;  // pixel splits per (ci, ky)
+  static constexpr int THREADS = 32 * K;
+};
+
+template <int KC, int K, int SI, int SO>
+__global__ void __launch_bounds__(32 * K) conv_wgrad2_kernel(WgradArgs a) {
+  using TL = WgradTile<KC, K, SI, SO>;
+  constexpr int TH = TL::TH, TW = TL::TW, PS = TL::PS, NT = TL::THREADS;
+  SENAS_DYN_SMEM(float4, smem);
+  const int tid = threadIdx.x, ci = tid % KC, ps = (tid / KC) % PS, ky = tid / 32;
+  const int span_y = a.taps.max_dy - a.taps.min_dy, span_x = a.taps.max_dx - a.taps.min_dx;
+  const int XR = (TH - 1) * SI + span_y + 1, XC = (TW - 1) * SI + span_x + 1;  // staged x tile (pixels)
+  constexpr int OTH = TH * SO, OTW = TW * SO;
+  float *s_x = reinterpret_cast<float *>(smem);                // [XR][XC][KC]
+  float4 *s_lo = smem + (XR * XC * KC + 3) / 4, *s_hi = s_lo + OTH * OTW;
+  // per-thread tap constants: taps of kernel row ky are t = ky*K + j in table order?  The table is phase-sorted, so
+  // look the K taps of this kernel row up by their weight index.
+  int xoff[K], doff[K], trow[K], tslot[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    int t = 0;
+    for (int q = 0; q < a.taps.n; ++q)
+      if (a.taps.widx[q] == ky * K + j) t = q;
+    tslot[j] = t;
+    trow[j] = a.taps.dy[t] - a.taps.min_dy;
+    xoff[j] = (a.taps.dx[t] - a.taps.min_dx) * KC + ci;
+    doff[j] = (a.taps.phase[t] >> 1) * OTW + (a.taps.phase[t] & 1);
+  }
+  float acc[K][8];
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  const int tiles = a.tiles_x * a.tiles_y, total = tiles * a.batch;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int n = item / tiles, tile = item - n * tiles;
+    const int by0 = (tile / a.tiles_x) * TH, bx0 = (tile % a.tiles_x) * TW;
+    const float *gmn = a.gm + (int64_t)n * a.o_h * a.o_w * 8;
+    const float *yn = a.y + (int64_t)n * a.o_h * a.o_w * a.y_ld;
+    const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld;
+    __syncthreads();
+    // x tile (zero outside the image)
+    const int gy0 = by0 * SI + a.taps.min_dy, gx0 = bx0 * SI + a.taps.min_dx;
+    for (int i = tid; i < XR * XC * (KC / 4); i += NT) {
+      const int q = i % (KC / 4), pxl = i / (KC / 4);
+      const int r = pxl / XC, c = pxl - r * XC;
+      const int gy = gy0 + r, gx = gx0 + c;
+      float4 v = f4zero();
+      if (gy >= 0 && gy < a.x_h && gx >= 0 && gx < a.x_w) v = ld4(xn + ((int64_t)gy * a.x_w + gx) * a.x_ld + q * 4);
+      st4(s_x + (int64_t)pxl * KC + q * 4, v);
+    }
+    // dy tile = A*gm + B*y + C (zero outside)
+    for (int i = tid; i < OTH * OTW; i += NT) {
+      const int r = i / OTW, c = i - r * OTW;
+      const int oy = by0 * SO + r, ox = bx0 * SO + c;
+      float4 lo = f4zero(), hi = f4zero();
+      if (oy < a.o_h && ox < a.o_w && by0 + r / SO < a.base_h && bx0 + c / SO < a.base_w) {
+        const int64_t pix = (int64_t)oy * a.o_w + ox;
+        const float4 glo = ld4(gmn + pix * 8), ghi = ld4(gmn + pix * 8 + 4);
+        const float4 ylo = ld4(yn + pix * a.y_ld), yhi = ld4(yn + pix * a.y_ld + 4);
+        const float *A = a.coefA + n * 8, *B = a.coefB + n * 8, *C = a.coefC + n * 8;
+        lo.x = A[0] * glo.x + B[0] * ylo.x + C[0], lo.y = A[1] * glo.y + B[1] * ylo.y + C[1];
+        lo.z = A[2] * glo.z + B[2] * ylo.z + C[2], lo.w = A[3] * glo.w + B[3] * ylo.w + C[3];
+        hi.x = A[4] * ghi.x + B[4] * yhi.x + C[4], hi.y = A[5] * ghi.y + B[5] * yhi.y + C[5];
+        hi.z = A[6] * ghi.z + B[6] * yhi.z + C[6], hi.w = A[7] * ghi.w + B[7] * yhi.w + C[7];
+      }
+      s_lo[i] = lo, s_hi[i] = hi;
+    }
+    __syncthreads();
+    for (int ty = ps; ty < TH; ty += PS) {
+      const float *xrow[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) xrow[j] = s_x + (int64_t)((ty * SI + trow[j]) * XC) * KC + xoff[j];
+      const float4 *dlo = s_lo + ty * SO * OTW, *dhi = s_hi + ty * SO * OTW;
+#pragma unroll
+      for (int tx = 0; tx < TW; ++tx) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float xv = xrow[j][tx * SI * KC];
+          const float4 lo = dlo[doff[j] + tx * SO], hi = dhi[doff[j] + tx * SO];
+          acc[j][0] = fmaf(xv, lo.x, acc[j][0]), acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
+          acc[j][2] = fmaf(xv, lo.z, acc[j][2]), acc[j][3] = fmaf(xv, lo.w, acc[j][3]);
+          acc[j][4] = fmaf(xv, hi.x, acc[j][4]), acc[j][5] = fmaf(xv, hi.y, acc[j][5]);
+          acc[j][6] = fmaf(xv, hi.z, acc[j][6]), acc[j][7] = fmaf(xv, hi.w, acc[j][7]);
+        }
+      }
+    }
+  }
+  if (PS > 1) {  // combine the pixel splits (lanes ci + 8*ps)
+#pragma unroll
+    for (int m = KC; m < 32; m <<= 1)
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], m);
+  }
+  if (ps == 0) {
+    float *out = a.partials + (int64_t)blockIdx.x * a.taps.n * KC * 8;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float *o = out + ((int64_t)tslot[j] * KC + ci) * 8;
+      st4(o, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+      st4(o + 4, make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]));
+    }
+  }
+}
