@@ -211,6 +211,21 @@ def run_ours(args, rank, world, local_rank):
         w_opt.step()
         return loss
 
+    # The step is static-shaped and host-bound when launched eagerly (~9k kernels + 3.4k parameter tensors of
+    # autograd/optimizer bookkeeping): capture arch step + weight step once and replay (senas_b200.GraphedSearchStep).
+    graphed, graph_note, eager_step, launches_per_step = None, 'eager', search_step, None
+    if not args.no_graph:
+        try:
+            n_before = lib.senas_launch_count()
+            graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
+                                                   warmup=3, post_backward=(buckets.finish if buckets else None))
+            launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
+            graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
+            search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731
+        except Exception as e:  # keep measuring, but say so
+            graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
+            torch.cuda.synchronize()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -243,13 +258,15 @@ def run_ours(args, rank, world, local_rank):
     n0 = lib.senas_launch_count()
     ms = timed(resident, args.steps)
     launches = lib.senas_launch_count() - n0
+    if graphed is not None:  # replayed graph nodes do not pass through the library's launch counter
+        launches = launches_per_step * args.steps
     ms_e2e = timed(e2e, args.steps)
     clk = clocks.stop() if clocks else None
 
     # per-kernel-family device time (CUDA events on the launch stream), one more step
     lib.senas_profile(1)
     barrier()
-    resident(0)
+    eager_step(*devb[0], *devb[1])   # eagerly launched so that every launch is bracketed by its own events
     barrier()
     lib.senas_profile(0)
     prof = _lib.profile_dump(lib)
@@ -285,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
         'dtype': 'bf16' if args.conv_mode == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': f'SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
                                f'{B} x 1x{size}x{size} per GPU, global batch {gB}',
-                   'parallelism': f'dp{world}', 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate/storage)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
+                   'parallelism': f'dp{world}', 'launch': graph_note, 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate/storage)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
         'e2e': {'value': value_e2e, 'unit': 'images/s', 'ms_per_step': ms_step_e2e,
                 'h2d_bytes_per_step': 2 * B * size * size * (4 + 8), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'roofline': roof, 'kernel_families': families, 'clocks': clk,
@@ -317,6 +334,7 @@ def main():
     ap.add_argument('--ref-batch', type=int, default=1)
     ap.add_argument('--ref-max-steps', type=int, default=6)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--conv-mode', default='bf16', choices=['fp32', 'bf16'],
                     help='bf16: tcgen05 implicit-GEMM convs with bf16 operands / fp32 accumulation; fp32: exact FMA path')
     args = ap.parse_args()
