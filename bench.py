@@ -183,6 +183,8 @@ def run_ours(args, rank, world, local_rank):
     buckets = None
     if world > 1:
         broadcast_parameters(model)
+
+    def make_eager_reducers():                    # eager DP path: NCCL all-reduces overlapped with backward
         fused_red = FusedGradReducer()            # cells: flat gradient buffers straight from the kernels
         hooks = GradBuckets(list(model.parameters()), model.arch_parameters(), exclude=fused_red.owned(model))
 
@@ -191,7 +193,10 @@ def run_ours(args, rank, world, local_rank):
             def finish():
                 fused_red.finish()
                 hooks.finish()
-        buckets = _Both
+        return _Both
+
+    if world > 1 and args.no_graph:
+        buckets = make_eager_reducers()
 
     host = [synth(B, size, 1234 + 17 * rank + i, True) for i in range(4)]  # train0, valid0, train1, valid1
     devb = [(x.to(dev), y.to(dev)) for x, y in host]
@@ -217,14 +222,19 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_graph:
         try:
             n_before = lib.senas_launch_count()
+            if world > 1:  # graphed DP path: local dice per rank, gradients averaged (senas_b200/graphs.py)
+                crit = SegmentationLosses('dice_ce')
             graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
-                                                   warmup=3, post_backward=(buckets.finish if buckets else None))
+                                                   warmup=3, group=group)
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
             search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731
         except Exception as e:  # keep measuring, but say so
             graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
             torch.cuda.synchronize()
+            if world > 1:
+                crit = SegmentationLosses('dice_ce', group=group)
+                buckets = make_eager_reducers()
 
     def barrier():
         if world > 1:

@@ -2,54 +2,127 @@
 
 The supernet has static shapes and the step issues ~9 000 small kernels plus ~3 400 parameter tensors worth of
 autograd / optimizer bookkeeping, so an eagerly launched step is bound by the host (measured on B200: enqueue time ==
-step time).  Capturing forward, loss, backward, gradient clipping and both optimizer steps into one CUDA graph makes
-the step cost what the kernels cost.  libsenas_b200 is capture-safe: it allocates nothing, never synchronises, and all
-its plans / scratch buffers are created during the warm-up iterations that precede the capture.
+step time).  Capturing forward, loss, backward, gradient clipping and both optimizer steps makes the step cost what the
+kernels cost.  libsenas_b200 is capture-safe: it allocates nothing, never synchronises, and all its plans / scratch
+buffers are created during the warm-up iterations that precede the capture.
+
+Data parallel (one process per GPU): NCCL collectives are kept OUT of the graphs (capturing them deadlocked on this
+stack); the step is captured as three graphs and the two gradient exchanges run eagerly between them, each as ONE
+all-reduce of a flat bucket that the graphs pack / unpack themselves:
+
+    graph 1: arch pass (fwd, loss, bwd)            -> pack arch grads (174 floats, pre-scaled 1/world)
+    all-reduce(bucket_arch)
+    graph 2: unpack, Adam on alpha/beta/gamma, weight pass (fwd, loss, bwd) -> pack all grads (1.97 M floats)
+    all-reduce(bucket_all)
+    graph 3: unpack, clip_grad_norm_, SGD
+
+BatchNorm statistics and the soft-dice sums stay local to each rank (replica semantics of the reference's DataParallel
+path for BN; per-shard dice is the stated choice of SURVEY.md H8 for the graphed path), gradients are averaged.
 """
 import torch
+import torch.distributed as dist
+
+
+def _flat_views(flat, tensors):
+    return [v.view_as(t) for v, t in zip(flat.split([t.numel() for t in tensors]), tensors)]
 
 
 class GraphedSearchStep:
-    """``step = GraphedSearchStep(model, criterion, w_opt, a_opt, example_batches, grad_clip=5)`` then
+    """``step = GraphedSearchStep(model, criterion, w_opt, a_opt, (xt, yt, xv, yv), grad_clip=5, group=None)`` then
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
-    def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, post_backward=None):
-        xt, yt, xv, yv = example
-        self.static = [t.clone() for t in (xt, yt, xv, yv)]
+    def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None):
+        self.static = [t.clone() for t in example]
         self.model, self.criterion, self.w_opt, self.a_opt = model, criterion, w_opt, a_opt
-        self.grad_clip, self.post_backward = grad_clip, post_backward
-        for group in a_opt.param_groups:          # Adam keeps `step` on the device when capturable
-            group['capturable'] = True
+        self.grad_clip, self.group = grad_clip, group
+        self.world = dist.get_world_size(group) if group is not None else 1
+        for g in a_opt.param_groups:  # Adam keeps `step` on the device when capturable
+            g['capturable'] = True
+        seen, self.params = set(), []
+        for p in model.parameters():
+            if id(p) not in seen and p.requires_grad:
+                seen.add(id(p))
+                self.params.append(p)
+        self.arch = [p for g in a_opt.param_groups for p in g['params']]
+        dev = self.params[0].device
+        if self.world > 1:
+            self.bucket_arch = torch.zeros(sum(p.numel() for p in self.arch), device=dev)
+            self.bucket_all = torch.zeros(sum(p.numel() for p in self.params), device=dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._eager_step()
+                self._run(capture=False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._eager_step()
+        self.graphs = []
+        self._run(capture=True)
 
-    def _eager_step(self):
+    # -- the three segments -----------------------------------------------------------------------------------
+    def _seg1(self):
         xt, yt, xv, yv = self.static
         self.a_opt.zero_grad(set_to_none=True)
         self.criterion(self.model(xv), yv).backward()
-        if self.post_backward:
-            self.post_backward()
+        if self.world > 1:
+            torch._foreach_copy_(_flat_views(self.bucket_arch, self.arch), [p.grad for p in self.arch])
+            self.bucket_arch.mul_(1.0 / self.world)
+
+    def _seg2(self):
+        xt, yt, xv, yv = self.static
+        if self.world > 1:
+            torch._foreach_copy_([p.grad for p in self.arch], _flat_views(self.bucket_arch, self.arch))
         self.a_opt.step()
         self.w_opt.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(xt), yt)
         loss.backward()
-        if self.post_backward:
-            self.post_backward()
+        if self.world > 1:
+            torch._foreach_copy_(_flat_views(self.bucket_all, self.params), [p.grad for p in self.params])
+            self.bucket_all.mul_(1.0 / self.world)
+        self.loss = loss.detach()
+
+    def _seg3(self):
+        if self.world > 1:
+            torch._foreach_copy_([p.grad for p in self.params], _flat_views(self.bucket_all, self.params))
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip)
         self.w_opt.step()
-        return loss.detach()
+
+    def _run(self, capture):
+        segs = (self._seg1, self._seg2, self._seg3)
+        if self.world == 1:  # nothing to exchange: one graph
+            if capture:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for s in segs:
+                        s()
+                self.graphs = [g]
+            else:
+                for s in segs:
+                    s()
+            return
+        pool = None
+        for i, s in enumerate(segs):
+            if capture:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    s()
+                pool = g.pool()
+                self.graphs.append(g)
+                g.replay()  # so that the eager exchange below (and the next capture) sees real values
+            else:
+                s()
+            if i < 2:
+                dist.all_reduce(self.bucket_arch if i == 0 else self.bucket_all, group=self.group)
 
     def __call__(self, xt, yt, xv, yv):
         for dst, src in zip(self.static, (xt, yt, xv, yv)):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        self.graph.replay()
+        if self.world == 1:
+            self.graphs[0].replay()
+        else:
+            self.graphs[0].replay()
+            dist.all_reduce(self.bucket_arch, group=self.group)
+            self.graphs[1].replay()
+            dist.all_reduce(self.bucket_all, group=self.group)
+            self.graphs[2].replay()
         return self.loss
