@@ -99,19 +99,16 @@ class GraphedSearchStep:
                 for s in segs:
                     s()
             return
-        pool = None
         for i, s in enumerate(segs):
-            if capture:
+            if capture:  # each graph keeps its own memory pool; nothing executes while capturing
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g):
                     s()
-                pool = g.pool()
                 self.graphs.append(g)
-                g.replay()  # so that the eager exchange below (and the next capture) sees real values
             else:
                 s()
-            if i < 2:
-                dist.all_reduce(self.bucket_arch if i == 0 else self.bucket_all, group=self.group)
+                if i < 2:
+                    dist.all_reduce(self.bucket_arch if i == 0 else self.bucket_all, group=self.group)
 
     def __call__(self, xt, yt, xv, yv):
         for dst, src in zip(self.static, (xt, yt, xv, yv)):
