@@ -91,7 +91,7 @@ class GraphedSearchStep:
         if self.world == 1:  # nothing to exchange: one graph
             if capture:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
                     for s in segs:
                         s()
                 self.graphs = [g]
@@ -102,7 +102,8 @@ class GraphedSearchStep:
         for i, s in enumerate(segs):
             if capture:  # each graph keeps its own memory pool; nothing executes while capturing
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the NCCL watchdog thread keeps polling CUDA events while we capture
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
                     s()
                 self.graphs.append(g)
             else:
