@@ -225,7 +225,8 @@ def run_ours(args, rank, world, local_rank):
             if world > 1:  # graphed DP path: local dice per rank, gradients averaged (senas_b200/graphs.py)
                 crit = SegmentationLosses('dice_ce')
             graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
-                                                   warmup=3, group=group)
+                                                   warmup=3, group=group,
+                                                   capture_error_mode='thread_local' if world > 1 else 'global')
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
             search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731

@@ -24,7 +24,7 @@ def eager():
 le = [eager() for _ in range(6)]
 # graphed: 3 warm-up steps inside the constructor, then 3 replays = steps 4..6 of the same trajectory
 m2, w2, a2 = build()
-step = senas_b200.GraphedSearchStep(m2, crit, w2, a2, (xs[0], ys[0], xs[1], ys[1]))
+step = senas_b200.GraphedSearchStep(m2, crit, w2, a2, (xs[0], ys[0], xs[1], ys[1]), force_segments=len(sys.argv) > 2 and sys.argv[2] != 'one', capture_error_mode=sys.argv[3] if len(sys.argv) > 3 else 'global')
 lg = [step(xs[0], ys[0], xs[1], ys[1]).item() for _ in range(2)]
 print('eager losses ', le)
 print('graph losses ', lg, '(capture = step 4, replays = steps 5, 6)')

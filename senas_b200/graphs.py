@@ -31,11 +31,14 @@ class GraphedSearchStep:
     """``step = GraphedSearchStep(model, criterion, w_opt, a_opt, (xt, yt, xv, yv), grad_clip=5, group=None)`` then
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
-    def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None):
+    def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
+                 force_segments=False, capture_error_mode='global'):
         self.static = [t.clone() for t in example]
         self.model, self.criterion, self.w_opt, self.a_opt = model, criterion, w_opt, a_opt
         self.grad_clip, self.group = grad_clip, group
         self.world = dist.get_world_size(group) if group is not None else 1
+        self.segmented = self.world > 1 or force_segments
+        self.capture_error_mode = capture_error_mode
         for g in a_opt.param_groups:  # Adam keeps `step` on the device when capturable
             g['capturable'] = True
         seen, self.params = set(), []
@@ -45,9 +48,11 @@ class GraphedSearchStep:
                 self.params.append(p)
         self.arch = [p for g in a_opt.param_groups for p in g['params']]
         dev = self.params[0].device
-        if self.world > 1:
+        if self.segmented:
             self.bucket_arch = torch.zeros(sum(p.numel() for p in self.arch), device=dev)
             self.bucket_all = torch.zeros(sum(p.numel() for p in self.params), device=dev)
+            self.arch_views = _flat_views(self.bucket_arch, self.arch)
+            self.all_views = _flat_views(self.bucket_all, self.params)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -59,39 +64,48 @@ class GraphedSearchStep:
         self._run(capture=True)
 
     # -- the three segments -----------------------------------------------------------------------------------
+    # Segments exchange gradients only through the two flat buckets (ordinary allocations): a segment packs its
+    # gradients and drops them before it ends, the next one adopts persistent *views* of the bucket as p.grad, so no
+    # tensor that lives in one graph's private memory pool is touched by another graph.
     def _seg1(self):
         xt, yt, xv, yv = self.static
         self.a_opt.zero_grad(set_to_none=True)
         self.criterion(self.model(xv), yv).backward()
-        if self.world > 1:
-            torch._foreach_copy_(_flat_views(self.bucket_arch, self.arch), [p.grad for p in self.arch])
+        if self.segmented:
+            torch._foreach_copy_(self.arch_views, [p.grad for p in self.arch])
             self.bucket_arch.mul_(1.0 / self.world)
+            for p in self.params:
+                p.grad = None
 
     def _seg2(self):
         xt, yt, xv, yv = self.static
-        if self.world > 1:
-            torch._foreach_copy_([p.grad for p in self.arch], _flat_views(self.bucket_arch, self.arch))
+        if self.segmented:
+            for p, v in zip(self.arch, self.arch_views):
+                p.grad = v
         self.a_opt.step()
         self.w_opt.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(xt), yt)
         loss.backward()
-        if self.world > 1:
-            torch._foreach_copy_(_flat_views(self.bucket_all, self.params), [p.grad for p in self.params])
+        if self.segmented:
+            torch._foreach_copy_(self.all_views, [p.grad for p in self.params])
             self.bucket_all.mul_(1.0 / self.world)
+            for p in self.params:
+                p.grad = None
         self.loss = loss.detach()
 
     def _seg3(self):
-        if self.world > 1:
-            torch._foreach_copy_([p.grad for p in self.params], _flat_views(self.bucket_all, self.params))
+        if self.segmented:
+            for p, v in zip(self.params, self.all_views):
+                p.grad = v
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip)
         self.w_opt.step()
 
     def _run(self, capture):
         segs = (self._seg1, self._seg2, self._seg3)
-        if self.world == 1:  # nothing to exchange: one graph
+        if not self.segmented:  # nothing to exchange: one graph
             if capture:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
                     for s in segs:
                         s()
                 self.graphs = [g]
@@ -103,24 +117,26 @@ class GraphedSearchStep:
             if capture:  # each graph keeps its own memory pool; nothing executes while capturing
                 g = torch.cuda.CUDAGraph()
                 # thread_local: the NCCL watchdog thread keeps polling CUDA events while we capture
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
                     s()
                 self.graphs.append(g)
             else:
                 s()
-                if i < 2:
+                if i < 2 and self.world > 1:
                     dist.all_reduce(self.bucket_arch if i == 0 else self.bucket_all, group=self.group)
 
     def __call__(self, xt, yt, xv, yv):
         for dst, src in zip(self.static, (xt, yt, xv, yv)):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
-        if self.world == 1:
+        if not self.segmented:
             self.graphs[0].replay()
         else:
             self.graphs[0].replay()
-            dist.all_reduce(self.bucket_arch, group=self.group)
+            if self.world > 1:
+                dist.all_reduce(self.bucket_arch, group=self.group)
             self.graphs[1].replay()
-            dist.all_reduce(self.bucket_all, group=self.group)
+            if self.world > 1:
+                dist.all_reduce(self.bucket_all, group=self.group)
             self.graphs[2].replay()
         return self.loss
