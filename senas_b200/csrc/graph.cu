@@ -123,6 +123,7 @@ static Geo make_geo(int k, int dil, int op, int dir) {
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
+static const int kDwRows = 4;       // output rows per block in the sliding-window depthwise kernels
 
 struct TermPlan {
   int kind = 0, k = 0, dil = 1;
@@ -280,7 +281,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.has_y = t.owns_y = true;
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
-          t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
+          t.nblk1 = geo.so == 1 ? cdiv(bh, kDwRows) : cdiv(bh * bw, 128 / (C / 4));
           t.nblk = nblk_px;
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -574,7 +575,21 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         a.taps = geo.taps;
         dim3 grid(t.nblk1, B);
         SENAS_TAG("dw_fwd", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C, 4.0 * B * (ep.in_h * ep.in_w * C + p.hw * C));
-        if (C == 32) {
+        if (geo.so == 1) {  // NORM / DOWN: sliding register window, t.nblk1 = blocks of kDwRows output rows
+#define SENAS_DWF(CC, KK, SS)                                                                                   \
+  {                                                                                                             \
+    auto kern = dw_sw_kernel<CC, KK, SS, false, true>;                                                          \
+    SENAS_LAUNCH(kern, grid, dim3(256), 0, c.stream, x, x_ld, ep.in_h, ep.in_w, a.z, (int64_t)CC, a.base_h,     \
+                 a.base_w, a.w, 0, a.partials, kDwRows);                                                        \
+  }
+          if (C == 32 && t.k == 5 && geo.si == 1) SENAS_DWF(32, 5, 1)
+          else if (C == 32 && t.k == 5 && geo.si == 2) SENAS_DWF(32, 5, 2)
+          else if (C == 32 && t.k == 3 && geo.si == 1) SENAS_DWF(32, 3, 1)
+          else if (C == 32 && t.k == 3 && geo.si == 2) SENAS_DWF(32, 3, 2)
+          else if (C == 8 && t.k == 5 && geo.si == 1) SENAS_DWF(8, 5, 1)
+          else if (C == 8 && t.k == 3 && geo.si == 1) SENAS_DWF(8, 3, 1)
+          else SENAS_FAIL("dw fwd: unsupported geometry");
+        } else if (C == 32) {
           auto kern = dw_fwd_kernel<32>;
           SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
         } else {
@@ -862,7 +877,20 @@ static int backward_edge(BwdCall &c, int e) {
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g2(cdiv(w.base_h * w.base_w, 128 / (C / 4)), B);
           SENAS_TAG("dw_dx", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + 2 * ep.in_h * ep.in_w * C));
-          if (C == 32) {
+          if (ed.op_type == SENAS_OP_NORM) {  // dx = dz (*) flipped kernel: same sliding-window kernel as forward
+            dim3 g2s(cdiv(ep.in_h, kDwRows), B);
+#define SENAS_DWB(CC, KK)                                                                                        \
+  {                                                                                                              \
+    auto kern = dw_sw_kernel<CC, KK, 1, true, false>;                                                            \
+    SENAS_LAUNCH(kern, g2s, dim3(256), 0, c.stream, (const float *)w.dz, (int64_t)CC, p.out_h, p.out_w, dx, dx_ld, \
+                 ep.in_h, ep.in_w, w.w, (int)c.touched[ed.src], (float *)nullptr, kDwRows);                      \
+  }
+            if (C == 32 && t.k == 5) SENAS_DWB(32, 5)
+            else if (C == 32 && t.k == 3) SENAS_DWB(32, 3)
+            else if (C == 8 && t.k == 5) SENAS_DWB(8, 5)
+            else if (C == 8 && t.k == 3) SENAS_DWB(8, 3)
+            else SENAS_FAIL("dw dx: unsupported geometry");
+          } else if (C == 32) {
             auto kern = dw_dx_kernel<32>;
             SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
           } else {

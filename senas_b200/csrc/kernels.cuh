@@ -1652,3 +1652,70 @@ __global__ void __launch_bounds__(32 * K) conv_wgrad2_kernel(WgradArgs a) {
     }
   }
 }
+
+// depthwise convolution with a sliding register window (stride-1 output grids: NORM / DOWN forward, NORM data
+// gradient).  thread = (channel, strip): the K x K input window of the thread's channel slides along x in registers,
+// K*SI global loads + 1 store per output instead of K*K loads (the first version was L1-bandwidth bound).
+//   out[b][c] = sum_{j,i} in[b*SI + (j - PAD), b*SI + (i - PAD)][c] * w[c][wj(j), wi(i)]     FLIP: w index mirrored (dgrad)
+// STATS: per-channel sum / sum of squares partials (forward);  ACC: out += (data gradient into a shared dx).
+template <int C, int K, int SI, bool FLIP, bool STATS>
+__global__ void __launch_bounds__(256) dw_sw_kernel(const float *in, int64_t in_ld, int in_h, int in_w, float *out,
+                                                    int64_t out_ld, int base_h, int base_w, const float *w, int accumulate,
+                                                    float *partials, int rows_per_block) {
+  constexpr int NS = 256 / C, T = K * K, PAD = K / 2, L = 64, WC = K + SI - 1;
+  __shared__ float s_red[STATS ? NS : 1][2 * C + 1];
+  const int tid = threadIdx.x, c = tid % C, strip = tid / C, n = blockIdx.y;
+  const int segs = (base_w + L - 1) / L;
+  const int row0 = blockIdx.x * rows_per_block, rows = min(rows_per_block, base_h - row0);
+  const float *inn = in + (int64_t)n * in_h * in_w * in_ld + c;
+  float *outn = out + (int64_t)n * base_h * base_w * out_ld + c;
+  float wk[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) wk[t] = __ldg(w + c * T + (FLIP ? T - 1 - t : t));
+  float ssum = 0.f, ssq = 0.f;
+  for (int item = strip; item < rows * segs; item += NS) {
+    const int by = row0 + item / segs, bx0 = (item % segs) * L, bx1 = min(bx0 + L, base_w);
+    float win[K][WC];
+    const float *xr[K];
+    bool rok[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int iy = by * SI + j - PAD;
+      rok[j] = iy >= 0 && iy < in_h;
+      xr[j] = inn + (int64_t)(rok[j] ? iy : 0) * in_w * in_ld;
+#pragma unroll
+      for (int i = SI; i < WC; ++i) {
+        const int ix = bx0 * SI + (i - SI) - PAD;
+        win[j][i] = (rok[j] && ix >= 0 && ix < in_w) ? __ldg(xr[j] + (int64_t)ix * in_ld) : 0.f;
+      }
+    }
+    for (int bx = bx0; bx < bx1; ++bx) {
+      float r = 0.f;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+#pragma unroll
+        for (int i = 0; i + SI < WC; ++i) win[j][i] = win[j][i + SI];
+#pragma unroll
+        for (int i = WC - SI; i < WC; ++i) {
+          const int ix = bx * SI + i - PAD;
+          win[j][i] = (rok[j] && ix >= 0 && ix < in_w) ? __ldg(xr[j] + (int64_t)ix * in_ld) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) r = fmaf(win[j][i], wk[j * K + i], r);
+      }
+      float *o = outn + ((int64_t)by * base_w + bx) * out_ld;
+      if (accumulate) r += *o;
+      *o = r;
+      if (STATS) ssum += r, ssq += r * r;
+    }
+  }
+  if (STATS) {
+    s_red[strip][c] = ssum, s_red[strip][C + c] = ssq;
+    __syncthreads();
+    if (tid < 2 * C) {
+      float r = 0.f;
+      for (int q = 0; q < NS; ++q) r += s_red[q][tid];
+      partials[((int64_t)n * gridDim.x + blockIdx.x) * 2 * C + tid] = r;
+    }
+  }
+}
