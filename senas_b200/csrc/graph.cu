@@ -281,7 +281,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.has_y = t.owns_y = true;
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
-          t.nblk1 = geo.so == 1 ? cdiv(bh, kDwRows) : cdiv(bh * bw, 128 / (C / 4));
+          t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
           t.nblk = nblk_px;
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -575,7 +575,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         a.taps = geo.taps;
         dim3 grid(t.nblk1, B);
         SENAS_TAG("dw_fwd", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C, 4.0 * B * (ep.in_h * ep.in_w * C + p.hw * C));
-        if (geo.so == 1) {  // NORM / DOWN: sliding register window, t.nblk1 = blocks of kDwRows output rows
+        if (false && geo.so == 1) {  // sliding-window variant: measured slower than the float4 kernel (more instructions)
 #define SENAS_DWF(CC, KK, SS)                                                                                   \
   {                                                                                                             \
     auto kern = dw_sw_kernel<CC, KK, SS, false, true>;                                                          \
@@ -877,7 +877,7 @@ static int backward_edge(BwdCall &c, int e) {
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g2(cdiv(w.base_h * w.base_w, 128 / (C / 4)), B);
           SENAS_TAG("dw_dx", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + 2 * ep.in_h * ep.in_w * C));
-          if (ed.op_type == SENAS_OP_NORM) {  // dx = dz (*) flipped kernel: same sliding-window kernel as forward
+          if (false && ed.op_type == SENAS_OP_NORM) {  // sliding-window variant: measured slower, kept for reference
             dim3 g2s(cdiv(ep.in_h, kDwRows), B);
 #define SENAS_DWB(CC, KK)                                                                                        \
   {                                                                                                              \
