@@ -334,6 +334,149 @@ __global__ void __launch_bounds__(256) pack_dy_kernel(PackDyArgs a) {
   *reinterpret_cast<uint4 *>(a.dst + pix * 32 + g * 8) = *reinterpret_cast<const uint4 *>(v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient on tcgen05:  dW_t[m = (term, co)][ci] = sum_pixels dy[pixel][m] * x[pixel + off_t][ci]
+// GEMM-K is the pixel dimension (16 pixels per MMA), both operands are MN-major views of the same
+// [plane][pixel][8 ch] row blocks the forward kernel stages:  A = packed dy row (M = 64: planes 0-3 real, 4-7 ignored),
+// B = x row shifted by the tap (N = 32 input channels).  One launch handles up to 13 taps whose 64 x 32 fp32
+// accumulators stay in TMEM (13 x 32 = 416 columns) for the whole strip; the epilogue writes one partial per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTcWTaps = 13;
+constexpr int kTcDySlots = 4;
+struct TcWgradArgs {
+  int32_t H, W, rows_per_cta, row_chunks, P, S;
+  int32_t t_begin, t_count;  // taps [t_begin, t_begin + t_count) of the table
+  float *partials;           // [B * gridDim.x][t_count][32 ci][32 m]
+  TapTable taps;
+};
+// D = F32, A = B = BF16, both MN-major, N = 32, M = 64
+constexpr uint32_t kTcIdescW = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                      const __grid_constant__ CUtensorMap tmap_dy,
+                                                                      TcWgradArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y;
+  const int xseg = blockIdx.x / a.row_chunks, chunk = blockIdx.x - xseg * a.row_chunks;
+  const int x0 = xseg * kTcM;
+  const int r0 = chunk * a.rows_per_cta, r_end = min(r0 + a.rows_per_cta, a.H);
+  const uint32_t row_bytes = (uint32_t)a.P * 64u, dy_bytes = 128u * 64u;
+  unsigned char *rows = smem;                                          // x ring: S slots
+  unsigned char *dyr = smem + (size_t)a.S * row_bytes;                 // dy ring: kTcDySlots slots + 1 pad slot
+  uint64_t *bars = reinterpret_cast<uint64_t *>(dyr + (size_t)(kTcDySlots + 1) * dy_bytes);
+  uint64_t *full = bars, *empty = bars + a.S, *dfull = bars + 2 * a.S, *dempty = dfull + kTcDySlots, *done = dempty + kTcDySlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+  __shared__ uint2 s_tap[kTcWTaps];
+  if (tid < a.t_count) {
+    const int t = a.t_begin + tid;
+    s_tap[tid] = make_uint2((uint32_t)(a.taps.dy[t] - a.taps.min_dy), (uint32_t)(a.taps.dx[t] - a.taps.min_dx));
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.S; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    for (int s = 0; s < kTcDySlots; ++s) mbar_init(&dfull[s], 1), mbar_init(&dempty[s], 1);
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int first_in = r0 + a.taps.min_dy, last_in = r_end - 1 + a.taps.max_dy;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: x rows (with halo) and dy rows, interleaved in consumption order
+      int idx = 0, y = first_in;
+      for (int r = r0, it = 0; r < r_end; ++r, ++it) {
+        for (; y <= min(r + a.taps.max_dy, last_in); ++y, ++idx) {
+          const int slot = idx & (a.S - 1), use = idx / a.S;
+          if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
+          mbar_expect_tx(&full[slot], row_bytes);
+          tma_load_5d(rows + (size_t)slot * row_bytes, &tmap_x, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n);
+        }
+        const int ds = it & (kTcDySlots - 1), duse = it / kTcDySlots;
+        if (duse > 0) mbar_wait(&dempty[ds], (uint32_t)((duse - 1) & 1));
+        mbar_expect_tx(&dfull[ds], dy_bytes);
+        tma_load_5d(dyr + (size_t)ds * dy_bytes, &tmap_dy, &dfull[ds], 0, x0, r, 0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      const uint32_t hi_a = ((128u * 16u) >> 4) | (1u << 14);               // SBO = dy plane stride (128 px * 16 B)
+      const uint32_t hi_b = (((uint32_t)a.P * 16u) >> 4) | (1u << 14);      // SBO = x plane stride
+      const uint32_t lbo = (128u >> 4) << 16;                               // LBO = 8 pixels * 16 B
+      const uint32_t a_base = ((smem_u32(dyr) >> 4) & 0x3FFF) | lbo, b_base = ((smem_u32(rows) >> 4) & 0x3FFF) | lbo;
+      const uint32_t row16 = row_bytes >> 4, smask = (uint32_t)a.S - 1u;
+      int waited = 0, it = 0;
+      for (int r = r0; r < r_end; ++r, ++it) {
+        const int need = r + a.taps.max_dy - first_in + 1;
+        while (waited < need) {
+          mbar_wait(&full[waited & smask], (uint32_t)((waited / a.S) & 1));
+          ++waited;
+        }
+        const int ds = it & (kTcDySlots - 1);
+        mbar_wait(&dfull[ds], (uint32_t)((it / kTcDySlots) & 1));
+        tc_fence_after();
+        const uint32_t alo0 = a_base + (uint32_t)ds * (dy_bytes >> 4);
+        for (int t = 0; t < a.t_count; ++t) {
+          const uint2 tp = s_tap[t];
+          const uint32_t blo0 = b_base + (((uint32_t)it + tp.x) & smask) * row16 + tp.y;
+          const uint32_t d = tmem_base + (uint32_t)t * 32u;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // 16 pixels per MMA
+            umma_bf16(d, ((uint64_t)hi_a << 32) | (alo0 + (uint32_t)kk * 16u), ((uint64_t)hi_b << 32) | (blo0 + (uint32_t)kk * 16u),
+                      kTcIdescW, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&dempty[ds]);
+        tc_commit(&empty[it & smask]);
+      }
+      tc_commit(done);
+    }
+  }
+  // ===== epilogue (after the whole strip): warps 2..5, TMEM lane quarters; rows m = 16*q' + lane for lane < 16
+  if (warp >= 2) {
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (q < 2) {
+      float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * a.t_count * 1024;
+      for (int t = 0; t < a.t_count; ++t) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 32u, v);
+        if (lane < 16) {
+          const int m = q * 16 + lane;
+#pragma unroll
+          for (int ci = 0; ci < 32; ++ci) out[((int64_t)t * 32 + ci) * 32 + m] = v[ci];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// dW of term g: dst_g[widx_t*ws_t + ci*ws_ci + co*ws_co] = sum_cta partials[cta][t][ci][g*8 + co]
+struct TcWgradReduceArgs {
+  const float *partials;
+  int32_t nrows, t_begin, t_count, nterms, ws_t, ws_ci, ws_co;
+  float *dst[kTcMaxTerms];
+  TapTable taps;
+};
+__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(TcWgradReduceArgs a) {
+  const int V = a.t_count * 1024, col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = block_rows_sum(a.partials, a.nrows, V, col);
+  if (threadIdx.x < 32 && col < V) {
+    const int m = col & 31, ci = (col >> 5) & 31, t = col >> 10, g = m >> 3, co = m & 7;
+    if (g < a.nterms)
+      a.dst[g][(int64_t)a.taps.widx[a.t_begin + t] * a.ws_t + (int64_t)ci * a.ws_ci + (int64_t)co * a.ws_co] = s;
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -380,6 +523,48 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
   }
   dim3 grid((a.W / kTcM) * a.row_chunks, B);
   SENAS_LAUNCH(conv_tc_fwd_kernel, grid, dim3(kTcThreads), smem, stream, tmap, a);
+  return 0;
+}
+static int tc_encode(CUtensorMap *tmap, const __nv_bfloat16 *p, int B, int H, int W, int box_w) {
+  PFN_tmapEncodeTiled enc = tc_encode_fn();
+  if (!enc) return 2;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, 4, (cuuint64_t)B};
+  const cuuint64_t gstr[4] = {64, (cuuint64_t)W * 64, 16, (cuuint64_t)H * W * 64};
+  const cuuint32_t box[5] = {8, (cuuint32_t)box_w, 1, 4, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16 *>(p), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
+}
+
+// wgrad of one NORM group: two launches of <= 13 taps each + reductions.  partials: >= B*ctas*13*1024 floats.
+static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dyb, int B, int H, int W, const TapTable &taps,
+                                float *partials, float *const *dst, int nterms, int ws_ci, int ws_co, void *stream) {
+  TcWgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.H = H, a.W = W, a.rows_per_cta = 32, a.row_chunks = (H + 31) / 32, a.taps = taps, a.partials = partials;
+  a.P = (kTcM + taps.max_dx - taps.min_dx + 1) & ~1, a.S = 16;
+  const size_t smem = (size_t)a.S * a.P * 64 + (size_t)(kTcDySlots + 1) * 8192 + (size_t)(2 * a.S + 2 * kTcDySlots + 2) * 8 + 64;
+  CUtensorMap mx, md;
+  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B, H, W, 128)) return 2;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
+    attr_smem = smem;
+  }
+  dim3 grid((W / kTcM) * a.row_chunks, B);
+  for (int tb = 0; tb < taps.n; tb += kTcWTaps) {
+    a.t_begin = tb, a.t_count = std::min(kTcWTaps, taps.n - tb);
+    SENAS_TAG("conv_tc_wgrad", 2.0 * B * H * W * a.t_count * 32 * 8 * nterms, 4.0 * B * H * W * 32);
+    SENAS_LAUNCH(conv_tc_wgrad_kernel, grid, dim3(kTcThreads), smem, stream, mx, md, a);
+    TcWgradReduceArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.partials = partials, ra.nrows = (int)(grid.x * B), ra.t_begin = tb, ra.t_count = a.t_count, ra.nterms = nterms;
+    ra.ws_t = 1, ra.ws_ci = ws_ci, ra.ws_co = ws_co, ra.taps = taps;
+    for (int g = 0; g < nterms; ++g) ra.dst[g] = dst[g];
+    SENAS_TAG("reduce", 0, 0);
+    SENAS_LAUNCH(tc_wgrad_reduce_kernel, dim3((a.t_count * 1024 + 31) / 32), dim3(256), 0, stream, ra);
+  }
   return 0;
 }
 #endif  // SENAS_EMU

@@ -238,8 +238,11 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         p->edges[e].t[k].tc = true;
       }
     }
-    for (auto &g2 : p->tc_groups)
+    for (auto &g2 : p->tc_groups) {
       if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
+      if (g2.op == SENAS_OP_NORM)
+        tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / kTcM) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
+    }
   }
 #endif
   const int kTcRows = 32;
@@ -787,7 +790,7 @@ static int backward_edge(BwdCall &c, int e) {
           if (launch_gather_any(a, geo, 8, C, B, c.stream)) return 1;
           c.touched[ed.src] = true;
         }
-        if (ed.grad_off[k][0] >= 0) {
+        if (ed.grad_off[k][0] >= 0 && !(t.tc && ed.op_type == SENAS_OP_NORM && c.a->grad_in[ed.src])) {
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           WgradArgs a;
           memset(&a, 0, sizeof(a));
@@ -1033,6 +1036,18 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     const int rc = launch_conv_tc(dyb, c.B, ta, c.stream);
     if (rc) SENAS_FAIL("tcgen05 dgrad launch failed (code %d)", rc);
     c.touched[g2.src] = true;
+    // weight gradients of the group from the same packed dy (pixels = GEMM-K)
+    {
+      Geo gf = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
+      float *dst[kTcMaxTerms] = {nullptr, nullptr, nullptr, nullptr};
+      for (int i = 0; i < g2.nterms; ++i) dst[i] = a->grad_params + d.edge[g2.edge[i]].grad_off[g2.cand[i]][0];
+      int ws_ci, ws_co;
+      conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ws_ci, &ws_co);
+      const int rcw = launch_conv_tc_wgrad(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), dyb, c.B,
+                                           ep0.in_h, ep0.in_w, gf.taps, c.scratch + p->tmp_off, dst, g2.nterms, ws_ci, ws_co,
+                                           c.stream);
+      if (rcw) SENAS_FAIL("tcgen05 wgrad launch failed (code %d)", rcw);
+    }
   }
 #endif
   for (int i = 0; i < d.n_inputs; ++i)
