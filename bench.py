@@ -170,6 +170,8 @@ def run_ours(args, rank, world, local_rank):
     torch.backends.cudnn.benchmark = True  # as experiments/search_arc.py:72 (stems / pre / post convs)
     senas_b200.exact_fp32()                # no TF32 in the stock-PyTorch blocks around the cells
     senas_b200.set_conv_mode(args.conv_mode)
+    if args.conv_mode == 'bf16':           # reduced-precision mode (gate 2e-2): the stock cuDNN convs may use TF32
+        torch.backends.cudnn.allow_tf32 = True
 
     B, size = args.batch, args.size
     torch.manual_seed(0)
