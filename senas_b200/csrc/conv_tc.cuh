@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -128,12 +137,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   uint64_t *full = bars, *empty = bars + a.S, *acc_full = bars + 2 * a.S, *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
   __shared__ float s_red[4][64];
-  __shared__ uint2 s_tap[25];
-  __shared__ uint32_t s_blo[25];
-  if (tid < T) {
-    s_tap[tid] = make_uint2((uint32_t)(a.taps.dy[tid] - a.taps.min_dy), (uint32_t)(a.taps.dx[tid] - a.taps.min_dx));
-    s_blo[tid] = (((smem_u32(smem) + (uint32_t)a.S * (uint32_t)a.P * 64u + (uint32_t)tid * 2048u) >> 4) & 0x3FFF) | ((512u >> 4) << 16);
-  }
 
   // ---- weights: fp32 global (PyTorch layout) -> bf16 canonical K-major tiles in shared memory
   for (int i = tid; i < T * 4 * kTcN; i += kTcThreads) {
@@ -187,14 +190,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====  (one thread; the loop body is kept to a handful of integer ops per MMA: the ring has
-    // a power-of-two number of slots and the per-tap parts of both descriptors are precomputed in shared memory)
-    if (lane == 0) {
+    // ===== MMA issuer =====  The whole warp runs the loop with warp-uniform values (kernel parameters, loop counters)
+    // so that the descriptors live in uniform registers -- UTCHMMA takes its operands from the uniform datapath; a
+    // loop under `if (lane == 0)` makes the compiler wrap every MMA in an ELECT / R2UR.BROADCAST waterfall (~100
+    // cycles per MMA, seen in the SASS of the first version).  Only the instruction itself is guarded by elect.sync.
+    {
       const uint32_t lbo_a = (uint32_t)a.P * 16u;
-      const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;                  // SBO = 128 B, version 1
+      const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1
       const uint32_t a_lo_base = ((smem_u32(rows) >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
+      const uint32_t b_lo_base = ((smem_u32(wsm) >> 4) & 0x3FFF) | ((512u >> 4) << 16);
       const uint32_t a_khalf = (2u * lbo_a) >> 4, row16 = row_bytes >> 4;
       const uint32_t smask = (uint32_t)a.S - 1u;
+      const bool leader = elect_one();
       int waited = 0, it = 0;
       for (int r = r0; r < r_end; ++r, ++it) {
         const int need = r + a.taps.max_dy - first_in + 1;
@@ -210,16 +217,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
           uint32_t acc = 0;
           const int t1 = a.taps.pstart[ph + 1];
           for (int t = a.taps.pstart[ph]; t < t1; ++t) {
-            const uint2 tp = s_tap[t];  // x: dy - min_dy (rows), y: ((dx - min_dx) pixels) in 16-byte units
-            const uint32_t alo = a_lo_base + (((uint32_t)it + tp.x) & smask) * row16 + tp.y;
-            const uint32_t blo = s_blo[t];
-            umma_bf16(d, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, kTcIdesc, acc);
-            umma_bf16(d, ((uint64_t)a_hi << 32) | (alo + a_khalf), ((uint64_t)b_hi << 32) | (blo + 64u), kTcIdesc, 1u);
+            const uint32_t trow = (uint32_t)(a.taps.dy[t] - a.taps.min_dy), tcol = (uint32_t)(a.taps.dx[t] - a.taps.min_dx);
+            const uint32_t alo = a_lo_base + (((uint32_t)it + trow) & smask) * row16 + tcol;
+            const uint32_t blo = b_lo_base + (uint32_t)t * 128u;
+            if (leader) {
+              umma_bf16(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, kTcIdesc, acc);
+              umma_bf16(d, ((uint64_t)hi << 32) | (alo + a_khalf), ((uint64_t)hi << 32) | (blo + 64u), kTcIdesc, 1u);
+            }
             acc = 1;
           }
         }
-        tc_commit(&acc_full[buf]);        // accumulators of this row are complete when all MMAs above retire
-        tc_commit(&empty[it & smask]);    // ... and input row (r + min_dy) is no longer needed by any later row
+        if (leader) {
+          tc_commit(&acc_full[buf]);        // accumulators of this row are complete when all MMAs above retire
+          tc_commit(&empty[it & smask]);    // ... and input row (r + min_dy) is no longer needed by any later row
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -367,11 +379,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
   uint64_t *bars = reinterpret_cast<uint64_t *>(dyr + (size_t)(kTcDySlots + 1) * dy_bytes);
   uint64_t *full = bars, *empty = bars + a.S, *dfull = bars + 2 * a.S, *dempty = dfull + kTcDySlots, *done = dempty + kTcDySlots;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
-  __shared__ uint2 s_tap[kTcWTaps];
-  if (tid < a.t_count) {
-    const int t = a.t_begin + tid;
-    s_tap[tid] = make_uint2((uint32_t)(a.taps.dy[t] - a.taps.min_dy), (uint32_t)(a.taps.dx[t] - a.taps.min_dx));
-  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.S; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
     for (int s = 0; s < kTcDySlots; ++s) mbar_init(&dfull[s], 1), mbar_init(&dempty[s], 1);
@@ -405,12 +412,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer
+    {  // ===== MMA issuer (warp-uniform loop, elected lane issues; see the forward kernel)
       const uint32_t hi_a = ((128u * 16u) >> 4) | (1u << 14);               // SBO = dy plane stride (128 px * 16 B)
       const uint32_t hi_b = (((uint32_t)a.P * 16u) >> 4) | (1u << 14);      // SBO = x plane stride
       const uint32_t lbo = (128u >> 4) << 16;                               // LBO = 8 pixels * 16 B
       const uint32_t a_base = ((smem_u32(dyr) >> 4) & 0x3FFF) | lbo, b_base = ((smem_u32(rows) >> 4) & 0x3FFF) | lbo;
       const uint32_t row16 = row_bytes >> 4, smask = (uint32_t)a.S - 1u;
+      const bool leader = elect_one();
       int waited = 0, it = 0;
       for (int r = r0; r < r_end; ++r, ++it) {
         const int need = r + a.taps.max_dy - first_in + 1;
@@ -423,18 +431,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
         tc_fence_after();
         const uint32_t alo0 = a_base + (uint32_t)ds * (dy_bytes >> 4);
         for (int t = 0; t < a.t_count; ++t) {
-          const uint2 tp = s_tap[t];
-          const uint32_t blo0 = b_base + (((uint32_t)it + tp.x) & smask) * row16 + tp.y;
+          const int tt = a.t_begin + t;
+          const uint32_t trow = (uint32_t)(a.taps.dy[tt] - a.taps.min_dy), tcol = (uint32_t)(a.taps.dx[tt] - a.taps.min_dx);
+          const uint32_t blo0 = b_base + (((uint32_t)it + trow) & smask) * row16 + tcol;
           const uint32_t d = tmem_base + (uint32_t)t * 32u;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // 16 pixels per MMA
-            umma_bf16(d, ((uint64_t)hi_a << 32) | (alo0 + (uint32_t)kk * 16u), ((uint64_t)hi_b << 32) | (blo0 + (uint32_t)kk * 16u),
-                      kTcIdescW, (it > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 8; ++kk)  // 16 pixels per MMA
+              umma_bf16(d, ((uint64_t)hi_a << 32) | (alo0 + (uint32_t)kk * 16u), ((uint64_t)hi_b << 32) | (blo0 + (uint32_t)kk * 16u),
+                        kTcIdescW, (it > 0 || kk > 0) ? 1u : 0u);
+          }
         }
-        tc_commit(&dempty[ds]);
-        tc_commit(&empty[it & smask]);
+        if (leader) {
+          tc_commit(&dempty[ds]);
+          tc_commit(&empty[it & smask]);
+        }
+        __syncwarp();
       }
-      tc_commit(done);
+      if (leader) tc_commit(done);
     }
   }
   // ===== epilogue (after the whole strip): warps 2..5, TMEM lane quarters; rows m = 16*q' + lane for lane < 16
