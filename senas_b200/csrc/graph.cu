@@ -563,7 +563,8 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         a.w = (const float *)ed.param[k][0], a.ws_t = 1;
         conv_weight_strides(ed.op_type, C, t.k * t.k, DIR_FWD, &a.ws_k, &a.ws_n);
         a.partials = part, a.taps = geo.taps;
-        SENAS_TAG("conv_fwd", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
+        SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_fwd.down" : (C == 8 ? "conv_fwd.n8" : (ed.op_type == SENAS_OP_UP ? "conv_fwd.up_small" : "conv_fwd.n32_small")),
+                  2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                   4.0 * B * (ep.in_h * ep.in_w * C + p.hw * 8));
         if (launch_gather_any(a, geo, C, 8, B, c.stream)) return 1;
         break;
@@ -785,7 +786,8 @@ static int backward_edge(BwdCall &c, int e) {
           a.si = geo.si, a.so = geo.so, a.w = (const float *)ed.param[k][0], a.ws_t = 1;
           conv_weight_strides(ed.op_type, C, T, DIR_DGRAD, &a.ws_k, &a.ws_n);
           a.partials = nullptr, a.taps = geo.taps;
-          SENAS_TAG("conv_dgrad", 2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
+          SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_dgrad.down" : (C == 8 ? "conv_dgrad.n8" : (ed.op_type == SENAS_OP_UP ? "conv_dgrad.up" : "conv_dgrad.n32_small")),
+                    2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                     4.0 * B * (ep.in_h * ep.in_w * C + HW * 16));
           if (launch_gather_any(a, geo, 8, C, B, c.stream)) return 1;
           c.touched[ed.src] = true;
@@ -810,7 +812,8 @@ static int backward_edge(BwdCall &c, int e) {
     const size_t smem = (size_t)((XR * XC * KC + 3) / 4) * 16 + (size_t)2 * TL::TH * SO_ * TL::TW * SO_ * 16;     \
     auto kern = conv_wgrad2_kernel<KC, KK, SI_, SO_>;                                                              \
     allow_smem(kern, smem);                                                                                        \
-    SENAS_TAG("conv_wgrad", 2.0 * B * a.base_h * a.base_w * T * KC * 8, 4.0 * B * (ep.in_h * ep.in_w * KC + HW * 16)); \
+    SENAS_TAG(SI_ == 2 ? "conv_wgrad.down" : (KC == 8 ? "conv_wgrad.n8" : (SO_ == 2 ? "conv_wgrad.up" : "conv_wgrad.n32_small")), \
+              2.0 * B * a.base_h * a.base_w * T * KC * 8, 4.0 * B * (ep.in_h * ep.in_w * KC + HW * 16)); \
     SENAS_LAUNCH(kern, dim3(nblk), dim3(TL::THREADS), smem, c.stream, a);                                          \
   }
           const int si_ = geo.si, so_ = geo.so;
