@@ -1622,10 +1622,12 @@ __global__ void __launch_bounds__(32 * K) conv_wgrad2_kernel(WgradArgs a) {
       const float4 *dlo = s_lo + ty * SO * OTW, *dhi = s_hi + ty * SO * OTW;
 #pragma unroll
       for (int tx = 0; tx < TW; ++tx) {
+        float4 lo1 = f4zero(), hi1 = f4zero();
+        if (SO == 1) lo1 = dlo[tx], hi1 = dhi[tx];  // stride-1 output: dy of this pixel is the same for every tap
 #pragma unroll
         for (int j = 0; j < K; ++j) {
           const float xv = xrow[j][tx * SI * KC];
-          const float4 lo = dlo[doff[j] + tx * SO], hi = dhi[doff[j] + tx * SO];
+          const float4 lo = SO == 1 ? lo1 : dlo[doff[j] + tx * SO], hi = SO == 1 ? hi1 : dhi[doff[j] + tx * SO];
           acc[j][0] = fmaf(xv, lo.x, acc[j][0]), acc[j][1] = fmaf(xv, lo.y, acc[j][1]);
           acc[j][2] = fmaf(xv, lo.z, acc[j][2]), acc[j][3] = fmaf(xv, lo.w, acc[j][3]);
           acc[j][4] = fmaf(xv, hi.x, acc[j][4]), acc[j][5] = fmaf(xv, hi.y, acc[j][5]);
