@@ -288,15 +288,35 @@ def test_mixed_op_bf16_tensor_core(bf16_mode, op_id, B, H, W):
 
 
 def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode):
+    """Up cell with in0 128 wide: the NORM edges 0/2/5 form 3-edge tcgen05 groups (forward, grouped data gradient,
+    weight gradient with 24 real rows), the UP edges 1/3/6 (in1 64 wide) stay on the exact kernels."""
     torch.manual_seed(11)
     c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
     c.apply(senas_b200.weights_init)
     store = oracle.clone_store(c.state_dict())
-    in0, in1 = torch.randn(2, 32, 16, 128), torch.randn(2, 32, 8, 64)   # in0: NORM edges at W = 128 -> tcgen05 groups
+    in0, in1 = torch.randn(2, 32, 16, 128), torch.randn(2, 32, 8, 64)
     wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
     b = torch.softmax(torch.randn(9), -1)
-    ref = oracle.cell_nodes(oracle.Params(store), 'up', in0, in1, wn, wc, b)
+    t = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    ref = oracle.cell_nodes(oracle.Params(store), 'up', *t)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
     c = c.to(DEV)
-    with torch.no_grad():
-        out = c.nodes(in0.to(DEV), in1.to(DEV), wn.to(DEV), wc.to(DEV), b.to(DEV))
+    g = [v.to(DEV).requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    lib = senas_b200._lib.get()
+    lib.senas_profile(1)
+    out = c.nodes(*g)
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    lib.senas_profile(0)
+    prof = senas_b200._lib.profile_dump(lib)
+    assert {'conv_tc_fwd', 'conv_tc_dgrad', 'conv_tc_wgrad'} <= set(prof), sorted(prof)
     check('cat', out, ref.detach(), 2e-2)
+    check('gin0', g[0].grad, t[0].grad, 2e-2)
+    check('gin1', g[1].grad, t[1].grad, 2e-2)
+    check('gbetas', g[4].grad, t[4].grad, 2e-2)
+    norm = c._norm_rows.view(-1).cpu()
+    check('gwn', g[2].grad.cpu()[norm], t[2].grad[norm], 2e-2)
+    check('gwc', g[3].grad.cpu()[~norm], t[3].grad[~norm], 2e-2)
+    for n, p in c._ops.named_parameters():
+        check('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 3e-2)
