@@ -144,6 +144,10 @@ int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a);
 int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t senas_launch_count(void);
+/* number of side streams ("lanes") over which independent candidate chains of a call are spread (fork/join with
+ * events on the caller's stream; a captured step becomes a DAG).  0 = strictly serial on the caller's stream,
+ * negative = default (environment variable SENAS_LANES, else 8).  Results are bit-identical for every setting. */
+int senas_set_lanes(int n);
 /* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
  * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
  * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */

@@ -4,6 +4,7 @@
 #include "../../include/senas_b200.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -120,6 +121,9 @@ static Geo make_geo(int k, int dil, int op, int dir) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+constexpr int kLanes = 8;                         // general lanes (each owns a slice of the tmp scratch)
+constexpr int kDxLanes = 2 + SENAS_MAX_NODES;     // one per state that receives a data gradient
+constexpr int kAllLanes = kLanes + kDxLanes;
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
@@ -156,7 +160,7 @@ struct Plan {
   std::vector<NodePlan> nodes;
   std::vector<TcGroup> tc_groups;
   int64_t xb_off[2] = {-1, -1};  // saved: dense bf16 NHWC copy of an input state (floats offset)
-  int64_t dyb_off = -1;          // scratch: packed bf16 dy of a NORM group (backward)
+  std::vector<int64_t> dyb_off;  // scratch: packed bf16 dy of each NORM group (backward)
   std::vector<BnDesc *> d_bnA, d_bnB;  // per stage
   std::vector<int> n_bnA, n_bnB;
   NodeDesc *d_nodes = nullptr;
@@ -323,10 +327,13 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     np.bsum_off = take(sc, (int64_t)B * (1 + nterms) * 8);
     np.nterms = nterms;
   }
-  p->dyb_off = -1;
-  for (auto &g2 : p->tc_groups)
-    if (g2.op == SENAS_OP_NORM && p->dyb_off < 0) p->dyb_off = take(sc, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
-  p->tmp_off = take(sc, tmp_need);
+  p->dyb_off.assign(p->tc_groups.size(), -1);
+  for (size_t gi = 0; gi < p->tc_groups.size(); ++gi) {  // one packed-dy buffer per NORM group (groups run concurrently)
+    const TcGroup &g2 = p->tc_groups[gi];
+    if (g2.op == SENAS_OP_NORM) p->dyb_off[gi] = take(sc, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
+  }
+  tmp_need = align4(tmp_need);
+  p->tmp_off = take(sc, tmp_need * kLanes);  // one slice per general lane
   p->tmp_floats = tmp_need;
   p->saved_floats = sv, p->scratch_floats = sc;
 
@@ -428,6 +435,101 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
 // ------------------------------------------------------------------------------------------------
 static const int kPersistBlocks = 148 * 6;
 
+// ------------------------------------------------------------------------------------------------
+// lanes: independent candidate chains of a call are spread over side streams (fork / join with events), so that a
+// captured search step is a DAG whose small kernels overlap instead of a 9 000-node chain (the cells at <= 64 x 64
+// are latency-bound: ~300 dependent launches of a few microseconds each).  Accumulations into a shared gradient
+// (dx of an input state) stay on ONE lane per state in issue order, so results are bit-identical to the serial order.
+// ------------------------------------------------------------------------------------------------
+static int g_lanes = -1;                          // -1: read SENAS_LANES on first use (default kLanes); 0: serial
+
+#ifndef SENAS_EMU
+constexpr int kEventPool = 4096;
+struct LaneSet {
+  cudaStream_t s[kAllLanes];
+  cudaEvent_t ev[kEventPool];
+  int next_ev = 0;
+};
+static LaneSet *lanes_for_current_device() {
+  static std::map<int, LaneSet *> sets;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = sets.find(dev);
+  if (it != sets.end()) return it->second;
+  LaneSet *ls = new LaneSet();
+  for (int i = 0; i < kAllLanes; ++i) cudaStreamCreateWithFlags(&ls->s[i], cudaStreamNonBlocking);
+  for (int i = 0; i < kEventPool; ++i) cudaEventCreateWithFlags(&ls->ev[i], cudaEventDisableTiming);
+  sets[dev] = ls;
+  return ls;
+}
+#endif
+
+struct Sched {
+  void *main = nullptr;
+  int n = 0;  // 0 = serial: every lane is the main stream
+  int rr = 0;
+#ifndef SENAS_EMU
+  LaneSet *ls = nullptr;
+#endif
+  void init(void *main_stream) {
+    main = main_stream;
+#ifndef SENAS_EMU
+    if (g_lanes < 0) {
+      const char *e = getenv("SENAS_LANES");
+      g_lanes = e ? std::max(0, std::min(kLanes, atoi(e))) : kLanes;
+    }
+    n = g_prof_on ? 0 : g_lanes;  // per-kernel timing wants serial launches
+    if (n > 0) ls = lanes_for_current_device();
+#endif
+  }
+  void *stream(int lane) const {
+#ifndef SENAS_EMU
+    if (n > 0 && lane >= 0) return (void *)ls->s[lane];
+#endif
+    (void)lane;
+    return main;
+  }
+  // next general lane (round robin); its index doubles as the tmp-scratch slot
+  int pick() {
+    if (n == 0) return -1;
+    const int l = rr;
+    rr = (rr + 1) % n;
+    return l;
+  }
+  int dx_lane(int state) const { return n == 0 ? -1 : kLanes + state; }
+  int tmp_slot(int lane) const { return lane < 0 ? 0 : lane; }
+  void dep(int from, int to) {  // work enqueued on `to` from now on waits for everything enqueued on `from` so far
+#ifndef SENAS_EMU
+    if (n == 0 || from == to) return;
+    cudaEvent_t e = ls->ev[ls->next_ev];
+    ls->next_ev = (ls->next_ev + 1) % kEventPool;
+    cudaEventRecord(e, (cudaStream_t)stream(from));
+    cudaStreamWaitEvent((cudaStream_t)stream(to), e, 0);
+#else
+    (void)from, (void)to;
+#endif
+  }
+  void fork() {  // every lane waits for the main stream's tail
+#ifndef SENAS_EMU
+    if (n == 0) return;
+    cudaEvent_t e = ls->ev[ls->next_ev];
+    ls->next_ev = (ls->next_ev + 1) % kEventPool;
+    cudaEventRecord(e, (cudaStream_t)main);
+    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(ls->s[i], e, 0);
+    for (int i = kLanes; i < kAllLanes; ++i) cudaStreamWaitEvent(ls->s[i], e, 0);
+#endif
+  }
+  void join() {  // the main stream waits for every lane
+#ifndef SENAS_EMU
+    if (n == 0) return;
+    for (int i = 0; i < kAllLanes; ++i) {
+      if (i >= n && i < kLanes) continue;
+      dep(i, -1);
+    }
+#endif
+  }
+};
+
 template <typename K>
 static void allow_smem(K kern, size_t bytes) {
 #ifndef SENAS_EMU
@@ -476,6 +578,8 @@ struct Call {  // per-call resolved pointers
   int64_t out_ld;
   void *stream;
   int B;
+  Sched S;
+  float *tmp(int lane) const { return scratch + p->tmp_off + (int64_t)S.tmp_slot(lane) * p->tmp_floats; }
 };
 static const float *state_ptr(const Call &c, int s, int64_t *ld) {
   if (s < c.d->n_inputs) {
@@ -496,7 +600,7 @@ static void conv_weight_strides(int op, int c_in, int T, int dir, int *ws_k, int
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-static int forward_edge(const Call &c, int e, bool second_pass) {
+static int forward_edge(Call &c, int e, bool second_pass) {
   const senas_edge_desc_t &ed = c.d->edge[e];
   const EdgePlan &ep = c.p->edges[e];
   const Plan &p = *c.p;
@@ -507,8 +611,11 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
     const TermPlan &t = ep.t[k];
     float *y = t.owns_y ? c.saved + t.y_off : nullptr;
     float *part = t.has_y ? c.scratch + t.part_off : nullptr;
+    if (t.kind == SENAS_KIND_NONE || (second_pass && t.kind != SENAS_KIND_DEPSEP) ||
+        (!second_pass && t.tc && (t.kind == SENAS_KIND_CONV || t.kind == SENAS_KIND_SE_CONV)))
+      continue;
+    void *st = c.S.stream(c.S.pick());  // candidates of a stage are independent: one lane each
     if (second_pass) {
-      if (t.kind != SENAS_KIND_DEPSEP) continue;
       PwArgs a;
       a.z = c.saved + t.z_off, a.hw = p.hw, a.y = y;
       a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
@@ -518,10 +625,10 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
       SENAS_TAG("pw_fwd", 2.0 * B * p.hw * C * 8, 4.0 * B * p.hw * (C + 8));
       if (C == 32) {
         auto kern = pw_fwd_kernel<32>;
-        SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
       } else {
         auto kern = pw_fwd_kernel<8>;
-        SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+        SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
       }
       continue;
     }
@@ -540,7 +647,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
   {                                                            \
     auto kern = adapter_fwd_kernel<CC, KK>;                    \
     SENAS_TAG("adapter_fwd", 2.0 * B * p.hw * CC * 8, 4.0 * B * (ep.in_h * ep.in_w * CC + p.hw * 8)); \
-    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);       \
   }
         const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
         if (C == 32 && kk == AD_IDENTITY) SENAS_AD_FWD(32, AD_IDENTITY)
@@ -566,7 +673,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
         SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_fwd.down" : (C == 8 ? "conv_fwd.n8" : (ed.op_type == SENAS_OP_UP ? "conv_fwd.up_small" : "conv_fwd.n32_small")),
                   2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                   4.0 * B * (ep.in_h * ep.in_w * C + p.hw * 8));
-        if (launch_gather_any(a, geo, C, 8, B, c.stream)) return 1;
+        if (launch_gather_any(a, geo, C, 8, B, st)) return 1;
         break;
       }
       case SENAS_KIND_DEPSEP: {
@@ -583,7 +690,7 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
 #define SENAS_DWF(CC, KK, SS)                                                                                   \
   {                                                                                                             \
     auto kern = dw_sw_kernel<CC, KK, SS, false, true>;                                                          \
-    SENAS_LAUNCH(kern, grid, dim3(256), 0, c.stream, x, x_ld, ep.in_h, ep.in_w, a.z, (int64_t)CC, a.base_h,     \
+    SENAS_LAUNCH(kern, grid, dim3(256), 0, st, x, x_ld, ep.in_h, ep.in_w, a.z, (int64_t)CC, a.base_h,     \
                  a.base_w, a.w, 0, a.partials, kDwRows);                                                        \
   }
           if (C == 32 && t.k == 5 && geo.si == 1) SENAS_DWF(32, 5, 1)
@@ -595,10 +702,10 @@ static int forward_edge(const Call &c, int e, bool second_pass) {
           else SENAS_FAIL("dw fwd: unsupported geometry");
         } else if (C == 32) {
           auto kern = dw_fwd_kernel<32>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
         } else {
           auto kern = dw_fwd_kernel<8>;
-          SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);
+          SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
         }
         break;
       }
@@ -638,6 +745,7 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
   c.bases.p[SP_IN0] = (float *)a->in[0], c.bases.ld[SP_IN0] = a->in_ld[0];
   c.bases.p[SP_IN1] = (float *)a->in[1], c.bases.ld[SP_IN1] = a->in_ld[1];
   c.bases.p[SP_OUT] = a->out, c.bases.ld[SP_OUT] = a->out_ld;
+  c.S.init(a->stream);
 #ifndef SENAS_EMU
   for (int i = 0; i < d.n_inputs; ++i) {
     if (p->xb_off[i] < 0) continue;
@@ -646,6 +754,9 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     SENAS_LAUNCH(cast_bf16_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, c.stream, a->in[i], a->in_ld[i],
                  reinterpret_cast<__nv_bfloat16 *>(c.saved + p->xb_off[i]), npix);
   }
+#endif
+  c.S.fork();
+#ifndef SENAS_EMU
   for (const TcGroup &g2 : p->tc_groups) {
     Geo geo = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
     TcConvArgs ta;
@@ -663,13 +774,16 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
     SENAS_TAG("conv_tc_fwd", 2.0 * c.B * ep0.in_h * ep0.in_w * geo.taps.n * 32 * 8 * g2.nterms,
               2.0 * c.B * ep0.in_h * ep0.in_w * 32 + 4.0 * c.B * p->hw * 8 * g2.nterms);
-    const int rc = launch_conv_tc(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), c.B, ta, c.stream);
+    const int rc = launch_conv_tc(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), c.B, ta,
+                                  c.S.stream(c.S.pick()));
     if (rc) SENAS_FAIL("tcgen05 conv launch failed (code %d)", rc);
   }
 #endif
   for (int s = 0; s < d.n_nodes; ++s) {
+    if (s > 0) c.S.fork();
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
+    c.S.join();
     if (p->n_bnA[s]) {
       SENAS_TAG("bn_reduce", 0, 0);
       SENAS_LAUNCH(bn_reduce_kernel, dim3(p->n_bnA[s], c.B), dim3(256), 0, c.stream, (const BnDesc *)p->d_bnA[s], c.bases);
@@ -678,8 +792,10 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
                    c.B, a->training);
     }
     if (p->n_bnB[s]) {
+      c.S.fork();
       for (int e = 0; e < d.n_edges; ++e)
         if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, true)) return 1;
+      c.S.join();
       SENAS_TAG("bn_reduce", 0, 0);
       SENAS_LAUNCH(bn_reduce_kernel, dim3(p->n_bnB[s], c.B), dim3(256), 0, c.stream, (const BnDesc *)p->d_bnB[s], c.bases);
       SENAS_TAG("bn_finalize", 0, 0);
@@ -717,11 +833,15 @@ static int backward_edge(BwdCall &c, int e) {
   float *dx = c.dstate[ed.src];
   const int64_t dx_ld = c.dstate_ld[ed.src];
   const float *gm = c.scratch + p.nodes[ed.dst].gm_off;
-  float *tmp = c.scratch + p.tmp_off;
   float *gp = c.a->grad_params;
+  const int dxl = c.S.dx_lane(ed.src);  // every accumulation into dx[src] runs on this lane, in issue order
+  void *sdx = c.S.stream(dxl);
   for (int k = 0; k < SENAS_MAX_CAND; ++k) {
     const TermPlan &t = ep.t[k];
     if (!t.has_y) continue;
+    const int ln = c.S.pick();            // the candidate's own chain (statistics, weight gradients, reductions)
+    void *st = c.S.stream(ln);
+    float *tmp = c.tmp(ln);
     int64_t y_ld = 8;
     const float *y = t.owns_y ? c.saved + t.y_off : x;
     if (!t.owns_y) y_ld = x_ld;
@@ -745,7 +865,7 @@ static int backward_edge(BwdCall &c, int e) {
   {                                                            \
     auto kern = adapter_dx_kernel<CC, KK>;                     \
     SENAS_TAG("adapter_dx", 2.0 * B * in_px * CC * 8, 4.0 * B * (in_px * CC + HW * 16)); \
-    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, sdx, a);            \
   }
           if (C == 32 && kk == AD_IDENTITY) SENAS_AD_DX(32, AD_IDENTITY)
           else if (C == 32 && kk == AD_POOL) SENAS_AD_DX(32, AD_POOL)
@@ -761,14 +881,14 @@ static int backward_edge(BwdCall &c, int e) {
   {                                                            \
     auto kern = adapter_dw_kernel<CC, KK>;                     \
     SENAS_TAG("adapter_dw", 2.0 * B * gpx * CC * 8, 4.0 * B * (in_px * CC + HW * 16)); \
-    SENAS_LAUNCH(kern, grid, dim3(128), 0, c.stream, a);       \
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);             \
   }
           if (kk == AD_IDENTITY) SENAS_AD_DW(32, AD_IDENTITY)
           else if (kk == AD_POOL) SENAS_AD_DW(32, AD_POOL)
           else SENAS_AD_DW(32, AD_UP)
           const int n = 8 * C;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, c.stream, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(grid.x * B), n);
         }
         break;
@@ -789,7 +909,7 @@ static int backward_edge(BwdCall &c, int e) {
           SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_dgrad.down" : (C == 8 ? "conv_dgrad.n8" : (ed.op_type == SENAS_OP_UP ? "conv_dgrad.up" : "conv_dgrad.n32_small")),
                     2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                     4.0 * B * (ep.in_h * ep.in_w * C + HW * 16));
-          if (launch_gather_any(a, geo, 8, C, B, c.stream)) return 1;
+          if (launch_gather_any(a, geo, 8, C, B, sdx)) return 1;
           c.touched[ed.src] = true;
         }
         if (ed.grad_off[k][0] >= 0 && !(t.tc && ed.op_type == SENAS_OP_NORM && c.a->grad_in[ed.src])) {
@@ -814,7 +934,7 @@ static int backward_edge(BwdCall &c, int e) {
     allow_smem(kern, smem);                                                                                        \
     SENAS_TAG(SI_ == 2 ? "conv_wgrad.down" : (KC == 8 ? "conv_wgrad.n8" : (SO_ == 2 ? "conv_wgrad.up" : "conv_wgrad.n32_small")), \
               2.0 * B * a.base_h * a.base_w * T * KC * 8, 4.0 * B * (ep.in_h * ep.in_w * KC + HW * 16)); \
-    SENAS_LAUNCH(kern, dim3(nblk), dim3(TL::THREADS), smem, c.stream, a);                                          \
+    SENAS_LAUNCH(kern, dim3(nblk), dim3(TL::THREADS), smem, st, a);                                          \
   }
           const int si_ = geo.si, so_ = geo.so;
           if (C == 32 && t.k == 5 && si_ == 1 && so_ == 1) SENAS_WGRAD2(32, 5, 1, 1)
@@ -830,7 +950,7 @@ static int backward_edge(BwdCall &c, int e) {
           conv_weight_strides(ed.op_type, C, T, DIR_FWD, &ws_ci, &ws_co);
           const int n = T * C * 8;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 32)), dim3(256), 0, c.stream, (const float *)tmp, nblk, T, C,
+          SENAS_LAUNCH(wgrad_reduce_kernel, dim3(cdiv(n, 32)), dim3(256), 0, st, (const float *)tmp, nblk, T, C,
                        gp + ed.grad_off[k][0], 1, ws_ci, ws_co, geo.taps);
         }
         break;
@@ -852,25 +972,25 @@ static int backward_edge(BwdCall &c, int e) {
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
         if (C == 32) {
           auto kern = pw_bwd_cc_kernel<32, 1>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         } else {
           auto kern = pw_bwd_cc_kernel<8, 1>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, c.stream, a, px_pb, c.a->training);
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
         SENAS_TAG("reduce", 0, 0);
-        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, 32), 1), dim3(256), 0, c.stream, (const float *)tmp, sums1,
+        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, 32), 1), dim3(256), 0, st, (const float *)tmp, sums1,
                      (int)(nblk_cc * B), 10 * C);
         SENAS_TAG("pw_bfin", 0, 0);
-        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const float *)sums1, C, (float)B * (float)HW, a.g1,
+        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums1, C, (float)B * (float)HW, a.g1,
                      a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
         dim3 grid_px(cdiv(HW, 128), B);
         if (C == 32) {
           auto kern = pw_bwd_dz_kernel<32>;
-          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, c.stream, a, c.a->training);
+          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, st, a, c.a->training);
         } else {
           auto kern = pw_bwd_dz_kernel<8>;
-          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, c.stream, a, c.a->training);
+          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, st, a, c.a->training);
         }
         DwBwdArgs w;
         memset(&w, 0, sizeof(w));
@@ -882,13 +1002,14 @@ static int backward_edge(BwdCall &c, int e) {
           w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
           w.si = geo.si, w.so = geo.so, w.taps = geo.taps;
           dim3 g2(cdiv(w.base_h * w.base_w, 128 / (C / 4)), B);
+          c.S.dep(ln, dxl);  // dz of this candidate is ready
           SENAS_TAG("dw_dx", 2.0 * B * w.base_h * w.base_w * T * C, 4.0 * B * (HW * C + 2 * ep.in_h * ep.in_w * C));
           if (false && ed.op_type == SENAS_OP_NORM) {  // sliding-window variant: measured slower, kept for reference
             dim3 g2s(cdiv(ep.in_h, kDwRows), B);
 #define SENAS_DWB(CC, KK)                                                                                        \
   {                                                                                                              \
     auto kern = dw_sw_kernel<CC, KK, 1, true, false>;                                                            \
-    SENAS_LAUNCH(kern, g2s, dim3(256), 0, c.stream, (const float *)w.dz, (int64_t)CC, p.out_h, p.out_w, dx, dx_ld, \
+    SENAS_LAUNCH(kern, g2s, dim3(256), 0, sdx, (const float *)w.dz, (int64_t)CC, p.out_h, p.out_w, dx, dx_ld, \
                  ep.in_h, ep.in_w, w.w, (int)c.touched[ed.src], (float *)nullptr, kDwRows);                      \
   }
             if (C == 32 && t.k == 5) SENAS_DWB(32, 5)
@@ -898,10 +1019,10 @@ static int backward_edge(BwdCall &c, int e) {
             else SENAS_FAIL("dw dx: unsupported geometry");
           } else if (C == 32) {
             auto kern = dw_dx_kernel<32>;
-            SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
+            SENAS_LAUNCH(kern, g2, dim3(128), 0, sdx, w);
           } else {
             auto kern = dw_dx_kernel<8>;
-            SENAS_LAUNCH(kern, g2, dim3(128), 0, c.stream, w);
+            SENAS_LAUNCH(kern, g2, dim3(128), 0, sdx, w);
           }
           c.touched[ed.src] = true;
         }
@@ -915,7 +1036,7 @@ static int backward_edge(BwdCall &c, int e) {
 #define SENAS_DWSW(CC, KK, SS)                                 \
   {                                                            \
     auto kern = dw_wgrad_sw_kernel<CC, KK, SS>;                \
-    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, st, w);         \
   }
           {  // sliding register window kernels: `chunk` = base rows per block
             w.chunk = 4;
@@ -924,12 +1045,12 @@ static int backward_edge(BwdCall &c, int e) {
 #define SENAS_DWUP(CC, KK)                                     \
   {                                                            \
     auto kern = dw_wgrad_up_kernel<CC, KK>;                    \
-    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, st, w);         \
   }
 #define SENAS_DWW(CC, TT)                                      \
   {                                                            \
     auto kern = dw_wgrad_kernel<CC, TT>;                       \
-    SENAS_LAUNCH(kern, g3, dim3(256), 0, c.stream, w);         \
+    SENAS_LAUNCH(kern, g3, dim3(256), 0, st, w);         \
   }
           if (geo.so == 1 && C == 32 && t.k == 5 && geo.si == 1) SENAS_DWSW(32, 5, 1)
           else if (geo.so == 1 && C == 32 && t.k == 5 && geo.si == 2) SENAS_DWSW(32, 5, 2)
@@ -946,7 +1067,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_FAIL("dw wgrad: unsupported c_in %d k %d", C, t.k);
           const int n = C * T;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, c.stream, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(g3.x * B), n);
         }
         break;
@@ -986,10 +1107,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     c.dstate[d.n_inputs + i] = np.has_consumer ? c.scratch + np.dnode_off : nullptr;
     c.dstate_ld[d.n_inputs + i] = 8, c.touched[d.n_inputs + i] = false;
   }
+  c.S.init(a->stream);
   cudaMemsetAsync(a->grad_params, 0, sizeof(float) * d.grad_floats, (cudaStream_t)c.stream);
   const int64_t node_bytes = sizeof(float) * (int64_t)c.B * p->hw * 8;
   for (int i = d.n_nodes - 1; i >= 0; --i) {
     const NodePlan &np = p->nodes[i];
+    c.S.dep(c.S.dx_lane(d.n_inputs + i), -1);  // the node's gradient from its consumers is complete
     if (np.has_consumer && !c.touched[d.n_inputs + i])
       cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
     SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
@@ -1004,16 +1127,20 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     SENAS_TAG("node_bfin", 0, 0);
     SENAS_LAUNCH(node_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
+    c.S.fork();  // the candidate chains of this node's edges run on the lanes, concurrently with the next node's sweep
     for (int e = 0; e < d.n_edges; ++e)
       if (d.edge[e].dst == i && backward_edge(c, e)) return 1;
   }
 #ifndef SENAS_EMU
   // grouped data gradient of the NORM tcgen05 groups: dx[src] += sum over the group's edges and taps (K = 8 x edges)
-  for (const TcGroup &g2 : p->tc_groups) {
+  for (size_t gi = 0; gi < p->tc_groups.size(); ++gi) {
+    const TcGroup &g2 = p->tc_groups[gi];
     if (g2.op != SENAS_OP_NORM || !a->grad_in[g2.src]) continue;
     const EdgePlan &ep0 = p->edges[g2.edge[0]];
     const int64_t npix = (int64_t)c.B * ep0.in_h * ep0.in_w;
-    __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off);
+    __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off[gi]);
+    const int ln = c.S.pick(), dxl = c.S.dx_lane(g2.src);
+    void *st = c.S.stream(ln);
     PackDyArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.nterms = g2.nterms, pa.hw = ep0.in_h * ep0.in_w, pa.batch = c.B, pa.dst = dyb;
@@ -1028,7 +1155,8 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       ta.w[i] = (const float *)d.edge[e].param[k][0];
     }
     SENAS_TAG("pack_dy", 0, npix * (64.0 * g2.nterms + 64.0));
-    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, c.stream, pa);
+    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, st, pa);
+    c.S.dep(ln, dxl);
     Geo geo = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD);
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);
@@ -1036,7 +1164,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
     ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src], ta.accumulate = c.touched[g2.src];
     SENAS_TAG("conv_tc_dgrad", 2.0 * npix * geo.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
-    const int rc = launch_conv_tc(dyb, c.B, ta, c.stream);
+    const int rc = launch_conv_tc(dyb, c.B, ta, c.S.stream(dxl));
     if (rc) SENAS_FAIL("tcgen05 dgrad launch failed (code %d)", rc);
     c.touched[g2.src] = true;
     // weight gradients of the group from the same packed dy (pixels = GEMM-K)
@@ -1047,12 +1175,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       int ws_ci, ws_co;
       conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ws_ci, &ws_co);
       const int rcw = launch_conv_tc_wgrad(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), dyb, c.B,
-                                           ep0.in_h, ep0.in_w, gf.taps, c.scratch + p->tmp_off, dst, g2.nterms, ws_ci, ws_co,
-                                           c.stream);
+                                           ep0.in_h, ep0.in_w, gf.taps, c.tmp(ln), dst, g2.nterms, ws_ci, ws_co, st);
       if (rcw) SENAS_FAIL("tcgen05 wgrad launch failed (code %d)", rcw);
     }
   }
 #endif
+  c.S.join();
   for (int i = 0; i < d.n_inputs; ++i)
     if (a->grad_in[i] && !c.touched[i]) {
       if (a->grad_in_ld[i] != d.edge[0].c_in) SENAS_FAIL("backward: cannot zero a strided grad_in");
@@ -1068,6 +1196,10 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
 extern "C" const char *senas_version(void) { return "senas_b200 0.1 (sm_100a, fp32 exact path)"; }
 extern "C" const char *senas_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t senas_launch_count(void) { return g_launch_count; }
+extern "C" int senas_set_lanes(int n) {
+  g_lanes = n < 0 ? -1 : std::min(n, kLanes);
+  return 0;
+}
 
 // per-kernel-family timing: senas_profile(1) starts recording CUDA events around every launch,
 // senas_profile(0) stops; senas_profile_dump() synchronises the recorded events and returns one line

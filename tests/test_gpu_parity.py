@@ -226,6 +226,34 @@ def test_bit_reproducible():
     assert all(torch.equal(x, y) for x, y in zip(outs[0][3], outs[1][3]))
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_lanes_do_not_change_a_bit(mode):
+    """The side-stream lanes (senas_set_lanes) only reorder independent work: a cell's outputs and every gradient
+    are bit-identical to the strictly serial schedule (accumulations into a shared dx stay ordered on one lane)."""
+    lib = senas_b200._lib.get()
+    senas_b200.set_conv_mode(mode)
+    try:
+        torch.manual_seed(11)
+        c = senas_b200.Cell(3, 1, 32, 32, 32, 'up').to(DEV)
+        in0, in1 = torch.randn(2, 32, 64, 128, device=DEV), torch.randn(2, 32, 32, 64, device=DEV).relu()
+        wn, wc = torch.softmax(torch.randn(9, 6, device=DEV), -1), torch.softmax(torch.randn(9, 6, device=DEV), -1)
+        b = torch.softmax(torch.randn(9, device=DEV), -1)
+        outs = []
+        for lanes in (0, 8, 3):
+            lib.senas_set_lanes(lanes)
+            c.zero_grad()
+            a, bb = in0.clone().requires_grad_(True), in1.clone().requires_grad_(True)
+            o = c.nodes(a, bb, wn, wc, b)
+            o.backward(torch.sin(torch.arange(o.numel(), device=DEV, dtype=torch.float32)).view_as(o))
+            torch.cuda.synchronize()
+            outs.append([o.detach().clone(), a.grad.clone(), bb.grad.clone()] + [p.grad.clone() for p in c._ops.parameters()])
+        for other in outs[1:]:
+            assert all(torch.equal(x, y) for x, y in zip(outs[0], other))
+    finally:
+        lib.senas_set_lanes(-1)
+        senas_b200.set_conv_mode('fp32')
+
+
 def test_full_size_linearity_in_alpha():
     """BASELINE size (batch 16, 32x256x256): with batch statistics, out is linear in the alpha row:
     out(a1 + a2) == out(a1) + out(a2), and a one-hot on 'none' gives the constant BN bias."""
@@ -287,14 +315,33 @@ def test_mixed_op_bf16_tensor_core(bf16_mode, op_id, B, H, W):
         check('grad.' + n, p.grad, store[n].grad, 2e-2)
 
 
-def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode):
+def l2_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize('representable', [True, False])
+def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable):
     """Up cell with in0 128 wide: the NORM edges 0/2/5 form 3-edge tcgen05 groups (forward, grouped data gradient,
-    weight gradient with 24 real rows), the UP edges 1/3/6 (in1 64 wide) stay on the exact kernels."""
+    weight gradient with 24 real rows), the UP edges 1/3/6 (in1 64 wide) stay on the exact kernels.
+
+    A cell ends every node in a ReLU, so a forward perturbation of bf16 size flips the mask of the few elements whose
+    pre-activation is ~0 and the max-norm error of a *gradient* is then one whole summand, not a rounding error.
+    representable=True: in0 and the dense-conv weights are bf16-representable, so the tensor-core forward is exact up
+    to accumulation order (same masks) and every gradient must meet the 2e-2 max-norm gate (only dy is rounded).
+    representable=False: arbitrary fp32 operands; forward at the 2e-2 max-norm gate, gradients at 2e-2 in the L2 norm."""
     torch.manual_seed(11)
     c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
     c.apply(senas_b200.weights_init)
-    store = oracle.clone_store(c.state_dict())
     in0, in1 = torch.randn(2, 32, 16, 128), torch.randn(2, 32, 8, 64)
+    if representable:
+        in0 = in0.bfloat16().float()
+        with torch.no_grad():
+            for e in (0, 2, 5):
+                for k in (2, 3):
+                    w = c._ops[e]._ops[k][0].weight
+                    w.copy_(w.bfloat16().float())
+    store = oracle.clone_store(c.state_dict())
     wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
     b = torch.softmax(torch.randn(9), -1)
     t = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
@@ -311,12 +358,18 @@ def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode):
     lib.senas_profile(0)
     prof = senas_b200._lib.profile_dump(lib)
     assert {'conv_tc_fwd', 'conv_tc_dgrad', 'conv_tc_wgrad'} <= set(prof), sorted(prof)
-    check('cat', out, ref.detach(), 2e-2)
-    check('gin0', g[0].grad, t[0].grad, 2e-2)
-    check('gin1', g[1].grad, t[1].grad, 2e-2)
-    check('gbetas', g[4].grad, t[4].grad, 2e-2)
+    check('cat', out, ref.detach(), 1e-4 if representable else 2e-2)
+    err = max_err if representable else l2_err
+
+    def gcheck(name, got, want, tol=2e-2):
+        e = err(got, want)
+        assert e <= tol, f'{name}: {err.__name__} {e:.3e} > {tol}'
+
+    gcheck('gin0', g[0].grad, t[0].grad)
+    gcheck('gin1', g[1].grad, t[1].grad)
+    gcheck('gbetas', g[4].grad, t[4].grad)
     norm = c._norm_rows.view(-1).cpu()
-    check('gwn', g[2].grad.cpu()[norm], t[2].grad[norm], 2e-2)
-    check('gwc', g[3].grad.cpu()[~norm], t[3].grad[~norm], 2e-2)
+    gcheck('gwn', g[2].grad.cpu()[norm], t[2].grad[norm])
+    gcheck('gwc', g[3].grad.cpu()[~norm], t[3].grad[~norm])
     for n, p in c._ops.named_parameters():
-        check('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 3e-2)
+        gcheck('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 3e-2)
