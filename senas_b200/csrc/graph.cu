@@ -128,6 +128,8 @@ static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
 static const int kDwRows = 4;       // output rows per block in the sliding-window depthwise kernels
+static int gather_pix(int NC, int si, int base_w);
+static int dw_tiles_x(int C, int w) { return cdiv(w, 2 * (128 / (C / 4))); }  // dw_multi_kernel: columns per tile
 
 struct TermPlan {
   int kind = 0, k = 0, dil = 1;
@@ -278,7 +280,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           t.has_y = t.owns_y = true;
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
-          t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW);
+          t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW * gather_pix(8, geo.si, bw));
           if (t.tc) t.nblk = (ep.in_w / 128) * cdiv(ep.in_h, kTcRows);
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
@@ -289,6 +291,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
+          if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_tiles_x(C, bw) * cdiv(bh, kDwTileRows);  // dw_multi_kernel grid
           t.nblk = nblk_px;
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -296,6 +299,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int64_t pw_tmp = (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
           const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
+          if (ed.op_type == SENAS_OP_NORM)  // grouped weight gradient: one partial per block and convolution
+            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * t.nblk1 * kDwMaxItems * C * 25);
           break;
         }
         default:
@@ -539,32 +544,47 @@ static void allow_smem(K kern, size_t bytes) {
 #endif
 }
 
-static size_t gather_smem(const Geo &g, int NC) {
+// base pixels per thread of gather_mac_kernel (tile = 8 rows x 16*PIX columns): as many as the map width and the
+// shared-memory footprint of the gathered tile allow
+static int gather_pix(int NC, int si, int base_w) {
+  const int want = (NC == 8 && si == 1) ? 4 : 2;
+  int pix = 1;
+  while (pix < want && base_w >= 32 * pix) pix *= 2;
+  return pix;
+}
+static size_t gather_smem(const Geo &g, int NC, int pix) {
   const int R = (kTileH - 1) * g.si + (g.taps.max_dy - g.taps.min_dy) + 1;
-  const int Cc = (kTileW - 1) * g.si + (g.taps.max_dx - g.taps.min_dx) + 1;
+  const int Cc = (kTileW * pix - 1) * g.si + (g.taps.max_dx - g.taps.min_dx) + 1;
   return (size_t)2 * R * Cc * 16 + (size_t)g.taps.n * 8 * NC * 4;
 }
 
-template <int KC, int NC, int NPH>
+template <int KC, int NC, int NPH, int PIX>
 static void launch_gather(GatherArgs &a, const Geo &g, int B, void *stream) {
-  auto kern = gather_mac_kernel<KC, NC, NPH>;
-  const size_t smem = gather_smem(g, NC);
+  auto kern = gather_mac_kernel<KC, NC, NPH, PIX>;
+  const size_t smem = gather_smem(g, NC, PIX);
   allow_smem(kern, smem);
-  a.tiles_x = cdiv(a.base_w, kTileW);
+  a.tiles_x = cdiv(a.base_w, kTileW * PIX);
   dim3 grid(a.tiles_x * cdiv(a.base_h, kTileH), B);
   SENAS_LAUNCH(kern, grid, dim3(kTileThreads), smem, stream, a);
 }
 
 static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream) {
-  const int nph = g.taps.nphase;
-  if (KC == 32 && NC == 8 && nph == 1) launch_gather<32, 8, 1>(a, g, B, stream);
-  else if (KC == 32 && NC == 8 && nph == 4) launch_gather<32, 8, 4>(a, g, B, stream);
-  else if (KC == 8 && NC == 8 && nph == 1) launch_gather<8, 8, 1>(a, g, B, stream);
-  else if (KC == 8 && NC == 8 && nph == 4) launch_gather<8, 8, 4>(a, g, B, stream);
-  else if (KC == 8 && NC == 32 && nph == 1) launch_gather<8, 32, 1>(a, g, B, stream);
-  else if (KC == 8 && NC == 32 && nph == 4) launch_gather<8, 32, 4>(a, g, B, stream);
-  else SENAS_FAIL("no gather kernel for KC=%d NC=%d phases=%d", KC, NC, nph);
-  return 0;
+  const int nph = g.taps.nphase, pix = gather_pix(NC, g.si, a.base_w);
+#define SENAS_GATHER(KC_, NC_, NPH_)                                                       \
+  if (KC == KC_ && NC == NC_ && nph == NPH_) {                                             \
+    if (pix == 4 && NC_ == 8) launch_gather<KC_, NC_, NPH_, (NC_ == 8 ? 4 : 2)>(a, g, B, stream); \
+    else if (pix >= 2) launch_gather<KC_, NC_, NPH_, 2>(a, g, B, stream);                  \
+    else launch_gather<KC_, NC_, NPH_, 1>(a, g, B, stream);                                \
+    return 0;                                                                              \
+  }
+  SENAS_GATHER(32, 8, 1)
+  SENAS_GATHER(32, 8, 4)
+  SENAS_GATHER(8, 8, 1)
+  SENAS_GATHER(8, 8, 4)
+  SENAS_GATHER(8, 32, 1)
+  SENAS_GATHER(8, 32, 4)
+#undef SENAS_GATHER
+  SENAS_FAIL("no gather kernel for KC=%d NC=%d phases=%d", KC, NC, nph);
 }
 
 struct Call {  // per-call resolved pointers
@@ -600,6 +620,46 @@ static void conv_weight_strides(int op, int c_in, int T, int dir, int *ws_k, int
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// dep-sep candidates of NORM edges: the depthwise halves of every edge that reads `src` go out as ONE launch
+// (dw_multi_kernel: the input tile is read from HBM once for up to 6 convolutions).
+static int forward_dw_group(Call &c, int src) {
+  const senas_graph_desc_t &d = *c.d;
+  const Plan &p = *c.p;
+  DwMultiArgs a;
+  memset(&a, 0, sizeof(a));
+  int C = 0, h = 0, w = 0, nblk = 0;
+  int64_t x_ld = 0;
+  const float *x = state_ptr(c, src, &x_ld);
+  for (int e = 0; e < d.n_edges; ++e) {
+    const senas_edge_desc_t &ed = d.edge[e];
+    if (ed.src != src || ed.op_type != SENAS_OP_NORM) continue;
+    for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+      const TermPlan &t = p.edges[e].t[k];
+      if (t.kind != SENAS_KIND_DEPSEP) continue;
+      if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
+      DwItem &it = a.it[a.n++];
+      it.in = x, it.in_ld = x_ld, it.out = c.saved + t.z_off, it.out_ld = ed.c_in;
+      it.w = (const float *)ed.param[k][0], it.partials = c.scratch + t.part1_off, it.k = t.k;
+      C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk1;
+    }
+  }
+  if (a.n == 0) return 0;
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w);
+  double taps = 0;
+  for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
+  void *st = c.S.stream(c.S.pick());
+  SENAS_TAG("dw_fwd", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + a.n));
+  dim3 grid(nblk, c.B);
+  if (C == 32) {
+    auto kern = dw_multi_kernel<32, true>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  } else {
+    auto kern = dw_multi_kernel<8, true>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  }
+  return 0;
+}
+
 static int forward_edge(Call &c, int e, bool second_pass) {
   const senas_edge_desc_t &ed = c.d->edge[e];
   const EdgePlan &ep = c.p->edges[e];
@@ -677,6 +737,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         break;
       }
       case SENAS_KIND_DEPSEP: {
+        if (ed.op_type == SENAS_OP_NORM) break;  // forward_dw_group
         Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
         DwArgs a;
         a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.z = c.saved + t.z_off;
@@ -781,6 +842,8 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
 #endif
   for (int s = 0; s < d.n_nodes; ++s) {
     if (s > 0) c.S.fork();
+    for (int src = 0; src < d.n_inputs + d.n_nodes; ++src)
+      if (state_stage(d, src) == s && forward_dw_group(c, src)) return 1;
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
     c.S.join();
@@ -818,6 +881,7 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
 // ------------------------------------------------------------------------------------------------
 struct BwdCall : Call {
   const senas_bwd_args_t *a;
+  std::vector<int> dw_wait[2 + SENAS_MAX_NODES];  // lanes whose dz (NORM dep-sep candidates reading a state) must finish
   float *dstate[2 + SENAS_MAX_NODES];
   int64_t dstate_ld[2 + SENAS_MAX_NODES];
   bool touched[2 + SENAS_MAX_NODES];
@@ -992,6 +1056,10 @@ static int backward_edge(BwdCall &c, int e) {
           auto kern = pw_bwd_dz_kernel<8>;
           SENAS_LAUNCH(kern, grid_px, dim3(128), 0, st, a, c.a->training);
         }
+        if (ed.op_type == SENAS_OP_NORM) {  // data / weight gradient of the depthwise half: backward_dw_group
+          c.dw_wait[ed.src].push_back(ln);
+          break;
+        }
         DwBwdArgs w;
         memset(&w, 0, sizeof(w));
         w.dz = c.saved + t.z_off, w.z_h = p.out_h, w.z_w = p.out_w, w.x_h = ep.in_h, w.x_w = ep.in_w;
@@ -1079,6 +1147,79 @@ static int backward_edge(BwdCall &c, int e) {
   return 0;
 }
 
+// grouped data gradient + weight gradient of the depthwise halves of every NORM edge that reads `src`; runs once all
+// of those edges have produced their dz (the consumers of an input state: after the last node).
+static int backward_dw_group(BwdCall &c, int src) {
+  const senas_graph_desc_t &d = *c.d;
+  const Plan &p = *c.p;
+  DwMultiArgs a;
+  memset(&a, 0, sizeof(a));
+  int C = 0, h = 0, w = 0, nblk = 0;
+  int64_t x_ld = 0;
+  const float *x = state_ptr(c, src, &x_ld);
+  int64_t goff[kDwMaxItems];
+  for (int e = 0; e < d.n_edges; ++e) {
+    const senas_edge_desc_t &ed = d.edge[e];
+    if (ed.src != src || ed.op_type != SENAS_OP_NORM) continue;
+    for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+      const TermPlan &t = p.edges[e].t[k];
+      if (t.kind != SENAS_KIND_DEPSEP) continue;
+      if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
+      goff[a.n] = ed.grad_off[k][0];
+      DwItem &it = a.it[a.n++];
+      it.in = c.saved + t.z_off, it.in_ld = ed.c_in;  // dz (in place over z)
+      it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = 1;
+      C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk1;
+    }
+  }
+  if (a.n == 0) return 0;
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w);
+  double taps = 0;
+  for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
+  dim3 grid(nblk, c.B);
+  float *dx = c.dstate[src];
+  const int dxl = c.S.dx_lane(src), ln = c.S.pick();
+  for (int l : c.dw_wait[src]) c.S.dep(l, dxl), c.S.dep(l, ln);
+  c.dw_wait[src].clear();
+  if (dx) {
+    DwMultiArgs g = a;
+    for (int m = 0; m < g.n; ++m)
+      g.it[m].out = dx, g.it[m].out_ld = c.dstate_ld[src], g.it[m].accumulate = (m > 0 || c.touched[src]) ? 1 : 0;
+    SENAS_TAG("dw_dx", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n));
+    if (C == 32) {
+      auto kern = dw_multi_kernel<32, false>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    } else {
+      auto kern = dw_multi_kernel<8, false>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    }
+    c.touched[src] = true;
+  }
+  {
+    DwMultiArgs g = a;
+    float *tmp = c.tmp(ln);
+    void *st = c.S.stream(ln);
+    const int64_t per = (int64_t)c.B * nblk * C * 25;
+    for (int m = 0; m < g.n; ++m)
+      g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld, g.it[m].flip = 0, g.it[m].partials = tmp + m * per;
+    SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n));
+    if (C == 32) {
+      auto kern = dw_wgrad_multi_kernel<32>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
+    } else {
+      auto kern = dw_wgrad_multi_kernel<8>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
+    }
+    for (int m = 0; m < g.n; ++m) {
+      const int nn = C * g.it[m].k * g.it[m].k;
+      SENAS_TAG("reduce", 0, 0);
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(nn, 32), 1), dim3(256), 0, st, (const float *)(tmp + m * per),
+                   c.a->grad_params + goff[m], (int)(nblk * c.B), nn);
+    }
+  }
+  return 0;
+}
+
 extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a) {
   Plan *p;
   if (!a) SENAS_FAIL("null args");
@@ -1130,6 +1271,13 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     c.S.fork();  // the candidate chains of this node's edges run on the lanes, concurrently with the next node's sweep
     for (int e = 0; e < d.n_edges; ++e)
       if (d.edge[e].dst == i && backward_edge(c, e)) return 1;
+    // states whose consumers have all been processed: node i-1 (its consumers are nodes >= i), or the inputs at the end
+    if (i > 0) {
+      if (backward_dw_group(c, d.n_inputs + i - 1)) return 1;
+    } else {
+      for (int src = 0; src < d.n_inputs; ++src)
+        if (backward_dw_group(c, src)) return 1;
+    }
   }
 #ifndef SENAS_EMU
   // grouped data gradient of the NORM tcgen05 groups: dx[src] += sum over the group's edges and taps (K = 8 x edges)

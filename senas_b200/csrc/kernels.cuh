@@ -88,18 +88,22 @@ struct GatherArgs {
 
 constexpr int kTileH = 8, kTileW = 16, kTileThreads = 128;
 
-template <int KC, int NC, int NPH>
+// PIX base pixels per thread (columns tx, tx + 16, ...): every weight float4 read from shared memory feeds PIX x 4 FMAs
+// instead of 4 (the PIX = 1 version issued 18 LDS per 64 FMA and ran at ~15 % of the FMA peak); lanes keep consecutive
+// pixels, so the activation reads stay conflict-free.
+template <int KC, int NC, int NPH, int PIX>
 __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) {
   constexpr int NCH = KC / 8;
   constexpr bool kPhaseOuter = (NCH == 1);  // single chunk: one live accumulator set
   constexpr int NLIVE = kPhaseOuter ? 1 : NPH;
+  constexpr int TW = kTileW * PIX;
   SENAS_DYN_SMEM(float4, smem);
   __shared__ float s_coef[24];
   const int tid = threadIdx.x, n = blockIdx.y, tile = blockIdx.x;
-  const int by0 = (tile / a.tiles_x) * kTileH, bx0 = (tile % a.tiles_x) * kTileW;
+  const int by0 = (tile / a.tiles_x) * kTileH, bx0 = (tile % a.tiles_x) * TW;
   const int ty = tid / kTileW, tx = tid % kTileW;
   const int R = (kTileH - 1) * a.si + (a.taps.max_dy - a.taps.min_dy) + 1;
-  const int Cc = (kTileW - 1) * a.si + (a.taps.max_dx - a.taps.min_dx) + 1;
+  const int Cc = (TW - 1) * a.si + (a.taps.max_dx - a.taps.min_dx) + 1;
   const int npx = R * Cc;
   float4 *s_lo = smem, *s_hi = smem + npx;
   float *s_w = reinterpret_cast<float *>(smem + 2 * npx);
@@ -111,11 +115,13 @@ __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) 
     }
     __syncthreads();
   }
-  float acc[NLIVE][NC];
+  float acc[PIX][NLIVE][NC];
 #pragma unroll
-  for (int p = 0; p < NLIVE; ++p)
+  for (int q = 0; q < PIX; ++q)
 #pragma unroll
-    for (int i = 0; i < NC; ++i) acc[p][i] = 0.f;
+    for (int p = 0; p < NLIVE; ++p)
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[q][p][i] = 0.f;
   float st_s[8], st_q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
@@ -123,13 +129,13 @@ __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) 
   const int gy0 = by0 * a.si + a.taps.min_dy, gx0 = bx0 * a.si + a.taps.min_dx;
   const float *srcn = a.src + (int64_t)n * a.src_h * a.src_w * a.src_ld;
   const float *src2n = affine ? a.src2 + (int64_t)n * a.src_h * a.src_w * a.src2_ld : nullptr;
-  const int by = by0 + ty, bx = bx0 + tx;
-  const bool base_ok = by < a.base_h && bx < a.base_w;
+  const int by = by0 + ty;
   float *dstn = a.dst + (int64_t)n * a.dst_h * a.dst_w * a.dst_ld;
 
-  auto epilogue = [&](int ph, float *r) {
+  auto epilogue = [&](int q, int ph, float *r) {
+    const int bx = bx0 + tx + q * kTileW;
     const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
-    if (base_ok && oy < a.dst_h && ox < a.dst_w) {
+    if (by < a.base_h && bx < a.base_w && oy < a.dst_h && ox < a.dst_w) {
       float *o = dstn + ((int64_t)oy * a.dst_w + ox) * a.dst_ld;
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
@@ -178,34 +184,50 @@ __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) 
     }
     __syncthreads();
     for (int ph = 0; ph < NPH; ++ph) {
-      float *r = acc[kPhaseOuter ? 0 : ph];
+      const int pl = kPhaseOuter ? 0 : ph;
       if (kPhaseOuter && NPH > 1) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) r[i] = 0.f;
+        for (int q = 0; q < PIX; ++q)
+#pragma unroll
+          for (int i = 0; i < NC; ++i) acc[q][0][i] = 0.f;
       }
       for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
         const int idx = (ty * a.si + a.taps.dy[t] - a.taps.min_dy) * Cc + (tx * a.si + a.taps.dx[t] - a.taps.min_dx);
-        const float4 lo = s_lo[idx], hi = s_hi[idx];
-        const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        float xv[PIX][8];
+#pragma unroll
+        for (int q = 0; q < PIX; ++q) {
+          const float4 lo = s_lo[idx + q * kTileW * a.si], hi = s_hi[idx + q * kTileW * a.si];
+          xv[q][0] = lo.x, xv[q][1] = lo.y, xv[q][2] = lo.z, xv[q][3] = lo.w;
+          xv[q][4] = hi.x, xv[q][5] = hi.y, xv[q][6] = hi.z, xv[q][7] = hi.w;
+        }
         const float *wt = s_w + t * 8 * NC;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
 #pragma unroll
           for (int j = 0; j < NC; j += 4) {
             const float4 w4 = ld4(wt + kk * NC + j);
-            r[j] = fmaf(xv[kk], w4.x, r[j]);
-            r[j + 1] = fmaf(xv[kk], w4.y, r[j + 1]);
-            r[j + 2] = fmaf(xv[kk], w4.z, r[j + 2]);
-            r[j + 3] = fmaf(xv[kk], w4.w, r[j + 3]);
+#pragma unroll
+            for (int q = 0; q < PIX; ++q) {
+              float *r = acc[q][pl];
+              r[j] = fmaf(xv[q][kk], w4.x, r[j]);
+              r[j + 1] = fmaf(xv[q][kk], w4.y, r[j + 1]);
+              r[j + 2] = fmaf(xv[q][kk], w4.z, r[j + 2]);
+              r[j + 3] = fmaf(xv[q][kk], w4.w, r[j + 3]);
+            }
           }
         }
       }
-      if (kPhaseOuter) epilogue(ph, r);
+      if (kPhaseOuter) {
+#pragma unroll
+        for (int q = 0; q < PIX; ++q) epilogue(q, ph, acc[q][0]);
+      }
     }
   }
   if (!kPhaseOuter) {
 #pragma unroll
-    for (int ph = 0; ph < NPH; ++ph) epilogue(ph, acc[ph]);
+    for (int q = 0; q < PIX; ++q)
+#pragma unroll
+      for (int ph = 0; ph < NPH; ++ph) epilogue(q, ph, acc[q][ph]);
   }
   if (a.partials != nullptr) {  // uniform
     float v[16];
@@ -1719,5 +1741,227 @@ __global__ void __launch_bounds__(256) dw_sw_kernel(const float *in, int64_t in_
       for (int q = 0; q < NS; ++q) r += s_red[q][tid];
       partials[((int64_t)n * gridDim.x + blockIdx.x) * 2 * C + tid] = r;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise convolution, stride-1 geometry (NORM edges), several convolutions of ONE input per launch.
+//
+// The dep-sep candidates of the edges that read the same state (Cell edges 0/2/5 <- in0, 4/7 <- node 0, ...; k = 3
+// and k = 5 each) share their input: a block owns one spatial tile and walks the list of convolutions, so x is read
+// from HBM once (the re-reads hit L1/L2) and, for the data gradient, the shared dx tile is accumulated by ONE block
+// in list order (fixed order => bit-reproducible; one HBM write instead of a read-modify-write per candidate).
+//
+// thread = (channel quad, pair of adjacent columns); it walks down the rows of its tile keeping the K output rows
+// that are "in flight" in registers (slot = output row mod K, compile-time under a K-fold unroll), the K x K weights
+// of its 4 channels in registers, and loads each input row once: K + 1 LDG.128 for 2 * K * K * 4 FMA.
+//   out[o][bx][c] = sum_{ky,kx} in[o + ky - P][bx + kx - P][c] * w[c][ky*K + kx]        (FLIP: w index mirrored)
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwMaxItems = 8;
+constexpr int kDwTileRows = 32;
+struct DwItem {
+  const float *in;    // [B][H][W][in_ld]
+  float *out;         // [B][H][W][out_ld]
+  const float *w;     // [C][K*K]
+  float *partials;    // forward: [B][gridDim.x][2C] sums / sums of squares;  weight gradient: [B][gridDim.x][C*K*K]
+  const float *in2;   // weight gradient: dz [B][H][W][C]
+  int64_t in_ld, out_ld;
+  int32_t k, flip, accumulate, pad_;
+};
+struct DwMultiArgs {
+  DwItem it[kDwMaxItems];
+  int32_t n, H, W, tiles_x;
+};
+
+SENAS_DEVFN void fma4(float4 &a, const float4 &x, const float4 &w) {
+  a.x = fmaf(x.x, w.x, a.x), a.y = fmaf(x.y, w.y, a.y), a.z = fmaf(x.z, w.z, a.z), a.w = fmaf(x.w, w.w, a.w);
+}
+
+template <int C, int K, bool STATS>
+SENAS_DEVFN void dw_tile_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int bx, int q, float *st) {
+  constexpr int P = K / 2, NX = K + 1, T = K * K;
+  float4 w[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int ti = it.flip ? T - 1 - t : t;
+    w[t] = make_float4(__ldg(it.w + (q * 4 + 0) * T + ti), __ldg(it.w + (q * 4 + 1) * T + ti),
+                       __ldg(it.w + (q * 4 + 2) * T + ti), __ldg(it.w + (q * 4 + 3) * T + ti));
+  }
+  float4 acc[K][2];
+#pragma unroll
+  for (int s = 0; s < K; ++s) acc[s][0] = acc[s][1] = f4zero();
+  bool cok[NX];
+#pragma unroll
+  for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
+  const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
+  float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
+  const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
+  for (int i0 = 0; i0 < niter; i0 += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int i = i0 + u, rr = r_first + i;
+      if (i < niter) {
+        if (rr >= 0 && rr < H) {
+          float4 xv[NX];
+          const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * it.in_ld;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * it.in_ld) : f4zero();
+#pragma unroll
+          for (int ky = 0; ky < K; ++ky) {
+            if ((unsigned)(i - ky) < (unsigned)R) {  // output row by0 + i - ky is inside the tile
+              const int s = (u - ky + K) % K;
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx) {
+                fma4(acc[s][0], xv[kx], w[ky * K + kx]);
+                fma4(acc[s][1], xv[kx + 1], w[ky * K + kx]);
+              }
+            }
+          }
+        }
+        const int sc = (u + 1) % K;
+        if (i >= K - 1) {  // output row by0 + i - (K - 1) is complete
+          const int o = by0 + i - (K - 1);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (bx + j < W) {
+              float *op = outb + ((int64_t)o * W + bx + j) * it.out_ld;
+              float4 v = acc[sc][j];
+              if (it.accumulate) {
+                const float4 old = ld4(op);
+                v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
+              }
+              st4(op, v);
+              if (STATS) {
+                st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
+                st[4] += v.x * v.x, st[5] += v.y * v.y, st[6] += v.z * v.z, st[7] += v.w * v.w;
+              }
+            }
+          }
+        }
+        acc[sc][0] = acc[sc][1] = f4zero();
+      }
+    }
+  }
+}
+
+// grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column pairs => 256/Q columns per tile
+template <int C, bool STATS>
+__global__ void __launch_bounds__(128) dw_multi_kernel(DwMultiArgs a) {
+  constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = 2 * SLOTS;
+  __shared__ float s_red[STATS ? 128 : 1][8];
+  const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+  const int bx = tx * NCB + 2 * slot, by0 = ty * kDwTileRows, by1 = min(by0 + kDwTileRows, a.H);
+  const bool active = bx < a.W;
+  for (int m = 0; m < a.n; ++m) {
+    const DwItem &it = a.it[m];
+    float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      if (it.k == 5) dw_tile_rows<C, 5, STATS>(it, n, a.H, a.W, by0, by1, bx, q, st);
+      else dw_tile_rows<C, 3, STATS>(it, n, a.H, a.W, by0, by1, bx, q, st);
+    }
+    if (STATS) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[tid][j] = st[j];
+      __syncthreads();
+      if (tid < 2 * C) {
+        const int c = tid % C, which = tid / C;
+        float r = 0.f;
+        for (int s = 0; s < SLOTS; ++s) r += s_red[s * Q + c / 4][which * 4 + (c & 3)];
+        it.partials[((int64_t)n * gridDim.x + blockIdx.x) * 2 * C + tid] = r;
+      }
+    }
+  }
+}
+
+// weight gradients of several depthwise convolutions of one input (stride-1 geometry):
+//   dW[c][ky*K + kx] = sum_{o, bx} x[o + ky - P][bx + kx - P][c] * dz[o][bx][c]
+// same thread mapping and row walk as dw_tile_rows, with the K most recent dz rows in registers; the K*K*4
+// accumulators of a thread are combined over the tile's column pairs with shuffles + shared memory (fixed order).
+template <int C, int K>
+SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int bx, int q, bool active,
+                               float *s_part, int nblk_idx) {
+  constexpr int P = K / 2, NX = K + 1, T = K * K, Q = C / 4;
+  float4 acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = f4zero();
+  if (active) {
+    float4 dzv[K][2];
+#pragma unroll
+    for (int s = 0; s < K; ++s) dzv[s][0] = dzv[s][1] = f4zero();
+    bool cok[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
+    const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
+    const float *dzb = it.in2 + (int64_t)n * H * W * C + q * 4;
+    const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
+    for (int i0 = 0; i0 < niter; i0 += K) {
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        const int i = i0 + u, rr = r_first + i;
+        if (i < niter) {
+          // dz row entering the window: output row by0 + i (slot u)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            dzv[u][j] = (i < R && bx + j < W) ? ld4(dzb + ((int64_t)(by0 + i) * W + bx + j) * C) : f4zero();
+          if (rr >= 0 && rr < H) {
+            float4 xv[NX];
+            const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * it.in_ld;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * it.in_ld) : f4zero();
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              if ((unsigned)(i - ky) < (unsigned)R) {
+                const int s = (u - ky + K) % K;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                  fma4(acc[ky * K + kx], xv[kx], dzv[s][0]);
+                  fma4(acc[ky * K + kx], xv[kx + 1], dzv[s][1]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // combine: lanes of a warp that hold the same quad (lane % Q), then the 4 warps through shared memory
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int m = Q; m < 32; m <<= 1) {
+      acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, m), acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, m);
+      acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, m), acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, m);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // s_part free
+  if (lane < Q) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float *o = s_part + warp * (C * 25) + (lane * 4) * T + t;
+      o[0] = acc[t].x, o[T] = acc[t].y, o[2 * T] = acc[t].z, o[3 * T] = acc[t].w;
+    }
+  }
+  __syncthreads();
+  float *out = it.partials + (int64_t)nblk_idx * C * T;
+  for (int o = threadIdx.x; o < C * T; o += 128)
+    out[o] = (s_part[o] + s_part[C * 25 + o]) + (s_part[2 * C * 25 + o] + s_part[3 * C * 25 + o]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(128) dw_wgrad_multi_kernel(DwMultiArgs a) {
+  constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = 2 * SLOTS;
+  __shared__ float s_part[4 * C * 25];
+  const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+  const int bx = tx * NCB + 2 * slot, by0 = ty * kDwTileRows, by1 = min(by0 + kDwTileRows, a.H);
+  const bool active = bx < a.W;
+  const int nblk_idx = n * gridDim.x + blockIdx.x;
+  for (int m = 0; m < a.n; ++m) {
+    const DwItem &it = a.it[m];
+    if (it.k == 5) dw_wgrad_rows<C, 5>(it, n, a.H, a.W, by0, by1, bx, q, active, s_part, nblk_idx);
+    else dw_wgrad_rows<C, 3>(it, n, a.H, a.W, by0, by1, bx, q, active, s_part, nblk_idx);
   }
 }

@@ -168,6 +168,12 @@ class StemConvBn(nn.Sequential):
     def __init__(self, c_in, c_ot, kernel_size):
         super().__init__(_weight(c_in, c_ot, kernel_size, 1, 1, False, 0), nn.BatchNorm2d(c_ot))
 
+    def forward(self, x):
+        # a 1-channel input is NCHW and NHWC at once and cuDNN then answers in NCHW, which sends the whole head of the
+        # network (this BatchNorm at 256 x 256, the max-pool, stem1) down the slow NCHW kernels (measured: 16 ms of a
+        # 230 ms step in cudnn::bn_*_1C11 alone); pin the activation layout the cells use.
+        return self[1](self[0](x).contiguous(memory_format=torch.channels_last))
+
 
 class ShrinkBlock(nn.Module):
     def __init__(self, c_in, c_ot):
@@ -198,7 +204,7 @@ class _AvgPool2dNCHW(nn.AvgPool2d):
     scripts/diag_pool.py), and the rest of the network runs channels_last."""
 
     def forward(self, x):
-        return super().forward(x.contiguous())
+        return super().forward(x.contiguous()).contiguous(memory_format=torch.channels_last)
 
 
 def build_rectify(c_in, c_ot, cell_type):

@@ -130,3 +130,34 @@ def test_patch_reference_classes_emulated(emu):
     assert list(new_cell.state_dict().keys()) == list(ref_cell.state_dict().keys())
     for k, v in ref_cell.state_dict().items():
         assert torch.allclose(new_cell.state_dict()[k].float(), v.float(), rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize('op_id,c_in,B,H,W', [(3, 32, 1, 36, 70), (3, 8, 1, 34, 66), (2, 32, 2, 12, 68), (1, 32, 2, 6, 34)])
+def test_mixed_op_wide_maps_emulated(emu, op_id, c_in, B, H, W):
+    """Maps wider than the golden fixtures: several pixels per thread in the gather-MAC tiles (PIX = 2 / 4), more than
+    one row / column tile in the grouped depthwise kernels, ragged right and bottom edges.  Checked against the oracle."""
+    import senas_oracle as oracle
+    import senas_b200
+    from helpers import OP_BY_ID, OP_NAME
+    torch.manual_seed(7 + op_id + c_in)
+    m = senas_b200.MixedOp(c_in, 8, OP_BY_ID[op_id])
+    m.apply(senas_b200.weights_init)
+    for mod in m.modules():  # BN bias 0 puts the SE block's hidden ReLU exactly on its kink (h = W1 . beta = 0)
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    store = oracle.clone_store(m.state_dict())
+    x = torch.randn(B, c_in, H, W)
+    alpha = torch.softmax(torch.randn(6), -1)
+    xo, ao = x.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], xo, ao, True)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    runner = GraphRunner([m._edge(0, 0)], n_inputs=1, n_nodes=1, node_relu=False, lib=emu)
+    r = run_graph_raw(runner, [x], alpha.view(1, 6), None, gout, True)
+    check('out', r['out'], ref.detach())
+    check('gx', r['g_ins'][0], xo.grad)
+    check('galpha', r['g_alpha'].view(-1), ao.grad)
+    names = {id(p): n for n, p in m.named_parameters()}
+    for p, gp in zip(runner.params, r['g_params']):
+        check('grad.' + names[id(p)], gp, store[names[id(p)]].grad)
