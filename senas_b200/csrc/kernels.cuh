@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) 
       s_w[i] = __ldg(a.w + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)(ch * 8 + kk) * a.ws_k + (int64_t)nn * a.ws_n);
     }
     __syncthreads();
+#pragma unroll
     for (int ph = 0; ph < NPH; ++ph) {
       const int pl = kPhaseOuter ? 0 : ph;
       if (kPhaseOuter && NPH > 1) {
