@@ -1797,24 +1797,37 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, int n, int H, int W, int by0, in
   const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
   float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
   const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
-  for (int i0 = 0; i0 < niter; i0 += K) {
+  const int64_t in_ld = it.in_ld;
+  // input row of iteration i -> xv (left untouched when the row is outside the image: its FMAs are skipped)
+  auto ldrow = [&](int i, float4(&xv)[NX]) {
+    const int rr = r_first + i;
+    if (i < niter && rr >= 0 && rr < H) {
+      const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
 #pragma unroll
-    for (int u = 0; u < K; ++u) {
+      for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
+    }
+  };
+  float4 xa[NX], xb[NX];  // double buffer: the row of iteration i + 1 is in flight while row i is consumed
+#pragma unroll
+  for (int j = 0; j < NX; ++j) xa[j] = xb[j] = f4zero();
+  ldrow(0, xa);
+  for (int i0 = 0; i0 < niter; i0 += 2 * K) {
+#pragma unroll
+    for (int u = 0; u < 2 * K; ++u) {
       const int i = i0 + u, rr = r_first + i;
+      float4(&cur)[NX] = (u & 1) ? xb : xa;
+      float4(&nxt)[NX] = (u & 1) ? xa : xb;
       if (i < niter) {
+        ldrow(i + 1, nxt);
         if (rr >= 0 && rr < H) {
-          float4 xv[NX];
-          const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * it.in_ld;
-#pragma unroll
-          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * it.in_ld) : f4zero();
 #pragma unroll
           for (int ky = 0; ky < K; ++ky) {
             if ((unsigned)(i - ky) < (unsigned)R) {  // output row by0 + i - ky is inside the tile
-              const int s = (u - ky + K) % K;
+              const int s = (u - ky + 2 * K) % K;
 #pragma unroll
               for (int kx = 0; kx < K; ++kx) {
-                fma4(acc[s][0], xv[kx], w[ky * K + kx]);
-                fma4(acc[s][1], xv[kx + 1], w[ky * K + kx]);
+                fma4(acc[s][0], cur[kx], w[ky * K + kx]);
+                fma4(acc[s][1], cur[kx + 1], w[ky * K + kx]);
               }
             }
           }
@@ -1897,32 +1910,48 @@ SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, i
     const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
     const float *dzb = it.in2 + (int64_t)n * H * W * C + q * 4;
     const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
-    for (int i0 = 0; i0 < niter; i0 += K) {
+    const int64_t in_ld = it.in_ld;
+    auto ldrow = [&](int i, float4(&xv)[NX]) {
+      const int rr = r_first + i;
+      if (i < niter && rr >= 0 && rr < H) {
+        const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
 #pragma unroll
-      for (int u = 0; u < K; ++u) {
+        for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
+      }
+    };
+    auto lddz = [&](int i, float4(&d)[2]) {  // dz of output row by0 + i (zero past the tile)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        d[j] = (i < R && bx + j < W) ? ld4(dzb + ((int64_t)(by0 + i) * W + bx + j) * C) : f4zero();
+    };
+    float4 xa[NX], xb[NX], dnext[2];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xa[j] = xb[j] = f4zero();
+    ldrow(0, xa);
+    lddz(0, dzv[0]);
+    for (int i0 = 0; i0 < niter; i0 += 2 * K) {
+#pragma unroll
+      for (int u = 0; u < 2 * K; ++u) {
         const int i = i0 + u, rr = r_first + i;
+        float4(&cur)[NX] = (u & 1) ? xb : xa;
+        float4(&nxt)[NX] = (u & 1) ? xa : xb;
         if (i < niter) {
-          // dz row entering the window: output row by0 + i (slot u)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            dzv[u][j] = (i < R && bx + j < W) ? ld4(dzb + ((int64_t)(by0 + i) * W + bx + j) * C) : f4zero();
+          ldrow(i + 1, nxt);
+          lddz(i + 1, dnext);  // enters slot (u + 1) % K, which still holds the oldest row during this iteration
           if (rr >= 0 && rr < H) {
-            float4 xv[NX];
-            const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * it.in_ld;
-#pragma unroll
-            for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * it.in_ld) : f4zero();
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
               if ((unsigned)(i - ky) < (unsigned)R) {
-                const int s = (u - ky + K) % K;
+                const int s = (u - ky + 2 * K) % K;
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                  fma4(acc[ky * K + kx], xv[kx], dzv[s][0]);
-                  fma4(acc[ky * K + kx], xv[kx + 1], dzv[s][1]);
+                  fma4(acc[ky * K + kx], cur[kx], dzv[s][0]);
+                  fma4(acc[ky * K + kx], cur[kx + 1], dzv[s][1]);
                 }
               }
             }
           }
+          dzv[(u + 1) % K][0] = dnext[0], dzv[(u + 1) % K][1] = dnext[1];
         }
       }
     }

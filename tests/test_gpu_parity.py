@@ -205,7 +205,11 @@ def test_fixed_seed_search_genotype():
     assert np.allclose(losses[:1], g['losses'][:1], rtol=2e-5), (losses, g['losses'])
     assert np.allclose(losses, g['losses'], rtol=5e-4), (losses, g['losses'])
     for n in ARCH:
-        assert (getattr(m, n).detach().cpu() - torch.from_numpy(g['arch.' + n])).abs().max() < 2e-4, n
+        # Adam's bias-corrected updates are +-lr in the first step and at most lr in the second whatever the gradient
+        # magnitude, so an entry whose noise-level gradient changes sign in both steps ends 4e-4 away; the gradient
+        # itself is gated above (5e-2 of the largest entry) and the decisions are gated by the genotype below.
+        d = (getattr(m, n).detach().cpu() - torch.from_numpy(g['arch.' + n])).abs()
+        assert d.max() < 4.5e-4 and (d > 2e-4).float().mean() < 0.1, (n, d.max().item(), (d > 2e-4).float().mean().item())
     assert repr(m.genotype()) == str(g['genotype'])
 
 
