@@ -129,7 +129,16 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
 static const int kDwRows = 4;       // output rows per block in the sliding-window depthwise kernels
 static int gather_pix(int NC, int si, int base_w);
-static int dw_tiles_x(int C, int w) { return cdiv(w, 2 * (128 / (C / 4))); }  // dw_multi_kernel: columns per tile
+// grouped depthwise kernels: columns per tile (forward / data gradient: 2 per thread; weight gradient: 1 per thread) and
+// rows per tile, the largest of 32/16/8/4 that still gives the 148 SMs at least four blocks each
+static int dw_tiles_x(int C, int w, bool wgrad) { return cdiv(w, (wgrad ? 1 : 2) * (128 / (C / 4))); }
+static int dw_rows(int C, int B, int h, int w, bool wgrad) {
+  const int tx = dw_tiles_x(C, w, wgrad);
+  for (int r = 32; r > 4; r /= 2)
+    if (tx * cdiv(h, r) * B >= 4 * 148) return r;
+  return 4;
+}
+static int dw_nblk(int C, int B, int h, int w, bool wgrad) { return dw_tiles_x(C, w, wgrad) * cdiv(h, dw_rows(C, B, h, w, wgrad)); }
 
 struct TermPlan {
   int kind = 0, k = 0, dil = 1;
@@ -291,7 +300,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
-          if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_tiles_x(C, bw) * cdiv(bh, kDwTileRows);  // dw_multi_kernel grid
+          if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false);  // dw_multi_kernel grid
           t.nblk = nblk_px;
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -300,7 +309,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           if (ed.op_type == SENAS_OP_NORM)  // grouped weight gradient: one partial per block and convolution
-            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * t.nblk1 * kDwMaxItems * C * 25);
+            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * dw_nblk(C, B, bh, bw, true) * kDwMaxItems * C * 25);
           break;
         }
         default:
@@ -644,7 +653,7 @@ static int forward_dw_group(Call &c, int src) {
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w);
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, false), a.tile_rows = dw_rows(C, c.B, h, w, false);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   void *st = c.S.stream(c.S.pick());
@@ -1173,7 +1182,7 @@ static int backward_dw_group(BwdCall &c, int src) {
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w);
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, false), a.tile_rows = dw_rows(C, c.B, h, w, false);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   dim3 grid(nblk, c.B);
@@ -1199,6 +1208,9 @@ static int backward_dw_group(BwdCall &c, int src) {
     DwMultiArgs g = a;
     float *tmp = c.tmp(ln);
     void *st = c.S.stream(ln);
+    g.tiles_x = dw_tiles_x(C, w, true), g.tile_rows = dw_rows(C, c.B, h, w, true);
+    nblk = dw_nblk(C, c.B, h, w, true);
+    grid = dim3(nblk, c.B);
     const int64_t per = (int64_t)c.B * nblk * C * 25;
     for (int m = 0; m < g.n; ++m)
       g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld, g.it[m].flip = 0, g.it[m].partials = tmp + m * per;

@@ -1759,7 +1759,6 @@ __global__ void __launch_bounds__(256) dw_sw_kernel(const float *in, int64_t in_
 //   out[o][bx][c] = sum_{ky,kx} in[o + ky - P][bx + kx - P][c] * w[c][ky*K + kx]        (FLIP: w index mirrored)
 // ------------------------------------------------------------------------------------------------
 constexpr int kDwMaxItems = 8;
-constexpr int kDwTileRows = 32;
 struct DwItem {
   const float *in;    // [B][H][W][in_ld]
   float *out;         // [B][H][W][out_ld]
@@ -1771,23 +1770,20 @@ struct DwItem {
 };
 struct DwMultiArgs {
   DwItem it[kDwMaxItems];
-  int32_t n, H, W, tiles_x;
+  int32_t n, H, W, tiles_x, tile_rows, pad_;
 };
 
 SENAS_DEVFN void fma4(float4 &a, const float4 &x, const float4 &w) {
   a.x = fmaf(x.x, w.x, a.x), a.y = fmaf(x.y, w.y, a.y), a.z = fmaf(x.z, w.z, a.z), a.w = fmaf(x.w, w.w, a.w);
 }
 
+// The first version kept the K x K x 4 weights in registers (222-254 registers, 8 warps per SM): ncu showed it
+// latency-bound (issue slots 21 % active, FMA pipe 13 %) while filling the register file, so nothing could run beside
+// it.  Weights now sit in shared memory as [tap][C] (one conflict-free LDS.128 per tap and row, 8 FMAs each).
 template <int C, int K, bool STATS>
-SENAS_DEVFN void dw_tile_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int bx, int q, float *st) {
-  constexpr int P = K / 2, NX = K + 1, T = K * K;
-  float4 w[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int ti = it.flip ? T - 1 - t : t;
-    w[t] = make_float4(__ldg(it.w + (q * 4 + 0) * T + ti), __ldg(it.w + (q * 4 + 1) * T + ti),
-                       __ldg(it.w + (q * 4 + 2) * T + ti), __ldg(it.w + (q * 4 + 3) * T + ti));
-  }
+SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int bx, int q,
+                              float *st) {
+  constexpr int P = K / 2, NX = K + 1;
   float4 acc[K][2];
 #pragma unroll
   for (int s = 0; s < K; ++s) acc[s][0] = acc[s][1] = f4zero();
@@ -1796,38 +1792,28 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, int n, int H, int W, int by0, in
   for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
   const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
   float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
+  const float *wq = s_w + q * 4;
   const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
   const int64_t in_ld = it.in_ld;
-  // input row of iteration i -> xv (left untouched when the row is outside the image: its FMAs are skipped)
-  auto ldrow = [&](int i, float4(&xv)[NX]) {
-    const int rr = r_first + i;
-    if (i < niter && rr >= 0 && rr < H) {
-      const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
+  for (int i0 = 0; i0 < niter; i0 += K) {
 #pragma unroll
-      for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
-    }
-  };
-  float4 xa[NX], xb[NX];  // double buffer: the row of iteration i + 1 is in flight while row i is consumed
-#pragma unroll
-  for (int j = 0; j < NX; ++j) xa[j] = xb[j] = f4zero();
-  ldrow(0, xa);
-  for (int i0 = 0; i0 < niter; i0 += 2 * K) {
-#pragma unroll
-    for (int u = 0; u < 2 * K; ++u) {
+    for (int u = 0; u < K; ++u) {
       const int i = i0 + u, rr = r_first + i;
-      float4(&cur)[NX] = (u & 1) ? xb : xa;
-      float4(&nxt)[NX] = (u & 1) ? xa : xb;
       if (i < niter) {
-        ldrow(i + 1, nxt);
         if (rr >= 0 && rr < H) {
+          float4 xv[NX];
+          const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
 #pragma unroll
           for (int ky = 0; ky < K; ++ky) {
             if ((unsigned)(i - ky) < (unsigned)R) {  // output row by0 + i - ky is inside the tile
-              const int s = (u - ky + 2 * K) % K;
+              const int s = (u - ky + K) % K;
 #pragma unroll
               for (int kx = 0; kx < K; ++kx) {
-                fma4(acc[s][0], cur[kx], w[ky * K + kx]);
-                fma4(acc[s][1], cur[kx + 1], w[ky * K + kx]);
+                const float4 wv = ld4(wq + (ky * K + kx) * C);
+                fma4(acc[s][0], xv[kx], wv);
+                fma4(acc[s][1], xv[kx + 1], wv);
               }
             }
           }
@@ -1858,24 +1844,33 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, int n, int H, int W, int by0, in
   }
 }
 
-// grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column pairs => 256/Q columns per tile
+// grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column pairs => 256/Q columns per tile,
+// tile_rows rows (chosen by the host so that the grid fills the 148 SMs several times over)
 template <int C, bool STATS>
 __global__ void __launch_bounds__(128) dw_multi_kernel(DwMultiArgs a) {
   constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = 2 * SLOTS;
   __shared__ float s_red[STATS ? 128 : 1][8];
+  __shared__ float4 s_w4[25 * C / 4];
+  float *s_w = reinterpret_cast<float *>(s_w4);
   const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
   const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
-  const int bx = tx * NCB + 2 * slot, by0 = ty * kDwTileRows, by1 = min(by0 + kDwTileRows, a.H);
+  const int bx = tx * NCB + 2 * slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
   const bool active = bx < a.W;
   for (int m = 0; m < a.n; ++m) {
     const DwItem &it = a.it[m];
+    const int T = it.k * it.k;
+    __syncthreads();  // previous item done with s_w / s_red
+    for (int i = tid; i < T * C; i += 128) {
+      const int c = i % C, t = i / C;
+      s_w[i] = __ldg(it.w + c * T + (it.flip ? T - 1 - t : t));
+    }
+    __syncthreads();
     float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (active) {
-      if (it.k == 5) dw_tile_rows<C, 5, STATS>(it, n, a.H, a.W, by0, by1, bx, q, st);
-      else dw_tile_rows<C, 3, STATS>(it, n, a.H, a.W, by0, by1, bx, q, st);
+      if (it.k == 5) dw_tile_rows<C, 5, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
+      else dw_tile_rows<C, 3, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
     }
     if (STATS) {
-      __syncthreads();
 #pragma unroll
       for (int j = 0; j < 8; ++j) s_red[tid][j] = st[j];
       __syncthreads();
@@ -1891,67 +1886,47 @@ __global__ void __launch_bounds__(128) dw_multi_kernel(DwMultiArgs a) {
 
 // weight gradients of several depthwise convolutions of one input (stride-1 geometry):
 //   dW[c][ky*K + kx] = sum_{o, bx} x[o + ky - P][bx + kx - P][c] * dz[o][bx][c]
-// same thread mapping and row walk as dw_tile_rows, with the K most recent dz rows in registers; the K*K*4
-// accumulators of a thread are combined over the tile's column pairs with shuffles + shared memory (fixed order).
+// thread = (channel quad, column); same row walk, with the K most recent dz values of its column in registers; the
+// K*K*4 accumulators of a thread are combined over the tile's columns with shuffles + shared memory (fixed order).
 template <int C, int K>
 SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int bx, int q, bool active,
                                float *s_part, int nblk_idx) {
-  constexpr int P = K / 2, NX = K + 1, T = K * K, Q = C / 4;
+  constexpr int P = K / 2, T = K * K, Q = C / 4;
   float4 acc[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = f4zero();
   if (active) {
-    float4 dzv[K][2];
+    float4 dzv[K];
 #pragma unroll
-    for (int s = 0; s < K; ++s) dzv[s][0] = dzv[s][1] = f4zero();
-    bool cok[NX];
+    for (int s = 0; s < K; ++s) dzv[s] = f4zero();
+    bool cok[K];
 #pragma unroll
-    for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
+    for (int j = 0; j < K; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
     const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
     const float *dzb = it.in2 + (int64_t)n * H * W * C + q * 4;
     const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
     const int64_t in_ld = it.in_ld;
-    auto ldrow = [&](int i, float4(&xv)[NX]) {
-      const int rr = r_first + i;
-      if (i < niter && rr >= 0 && rr < H) {
-        const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
+    for (int i0 = 0; i0 < niter; i0 += K) {
 #pragma unroll
-        for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
-      }
-    };
-    auto lddz = [&](int i, float4(&d)[2]) {  // dz of output row by0 + i (zero past the tile)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        d[j] = (i < R && bx + j < W) ? ld4(dzb + ((int64_t)(by0 + i) * W + bx + j) * C) : f4zero();
-    };
-    float4 xa[NX], xb[NX], dnext[2];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) xa[j] = xb[j] = f4zero();
-    ldrow(0, xa);
-    lddz(0, dzv[0]);
-    for (int i0 = 0; i0 < niter; i0 += 2 * K) {
-#pragma unroll
-      for (int u = 0; u < 2 * K; ++u) {
+      for (int u = 0; u < K; ++u) {
         const int i = i0 + u, rr = r_first + i;
-        float4(&cur)[NX] = (u & 1) ? xb : xa;
-        float4(&nxt)[NX] = (u & 1) ? xa : xb;
         if (i < niter) {
-          ldrow(i + 1, nxt);
-          lddz(i + 1, dnext);  // enters slot (u + 1) % K, which still holds the oldest row during this iteration
+          // dz row entering the window: output row by0 + i (slot u)
+          dzv[u] = i < R ? ld4(dzb + ((int64_t)(by0 + i) * W + bx) * C) : f4zero();
           if (rr >= 0 && rr < H) {
+            float4 xv[K];
+            const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
+#pragma unroll
+            for (int j = 0; j < K; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
               if ((unsigned)(i - ky) < (unsigned)R) {
-                const int s = (u - ky + 2 * K) % K;
+                const int s = (u - ky + K) % K;
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                  fma4(acc[ky * K + kx], cur[kx], dzv[s][0]);
-                  fma4(acc[ky * K + kx], cur[kx + 1], dzv[s][1]);
-                }
+                for (int kx = 0; kx < K; ++kx) fma4(acc[ky * K + kx], xv[kx], dzv[s]);
               }
             }
           }
-          dzv[(u + 1) % K][0] = dnext[0], dzv[(u + 1) % K][1] = dnext[1];
         }
       }
     }
@@ -1980,13 +1955,14 @@ SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, i
     out[o] = (s_part[o] + s_part[C * 25 + o]) + (s_part[2 * C * 25 + o] + s_part[3 * C * 25 + o]);
 }
 
+// grid = (tiles_x * tiles_y, B), block = 128: Q quads x 128/Q columns, tile_rows rows
 template <int C>
 __global__ void __launch_bounds__(128) dw_wgrad_multi_kernel(DwMultiArgs a) {
-  constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = 2 * SLOTS;
+  constexpr int Q = C / 4, SLOTS = 128 / Q;
   __shared__ float s_part[4 * C * 25];
   const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
   const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
-  const int bx = tx * NCB + 2 * slot, by0 = ty * kDwTileRows, by1 = min(by0 + kDwTileRows, a.H);
+  const int bx = tx * SLOTS + slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
   const bool active = bx < a.W;
   const int nblk_idx = n * gridDim.x + blockIdx.x;
   for (int m = 0; m < a.n; ++m) {
