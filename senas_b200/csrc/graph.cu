@@ -301,7 +301,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
           if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false);  // dw_multi_kernel grid
-          t.nblk = nblk_px;
+          t.nblk = cdiv(HW, kPwPx);  // pw_fwd_kernel grid
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
           t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C), t.psum1_off = take(sc, (int64_t)B * 2 * C);
@@ -690,14 +690,14 @@ static int forward_edge(Call &c, int e, bool second_pass) {
       a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
       a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
       a.wpw = (const float *)ed.param[k][6], a.partials = part;
-      dim3 grid(cdiv(p.hw, 128), B);
+      dim3 grid(cdiv(p.hw, kPwPx), B);
       SENAS_TAG("pw_fwd", 2.0 * B * p.hw * C * 8, 4.0 * B * p.hw * (C + 8));
       if (C == 32) {
         auto kern = pw_fwd_kernel<32>;
-        SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+        SENAS_LAUNCH(kern, grid, dim3(256), 0, st, a);
       } else {
         auto kern = pw_fwd_kernel<8>;
-        SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+        SENAS_LAUNCH(kern, grid, dim3(256), 0, st, a);
       }
       continue;
     }
@@ -1044,10 +1044,10 @@ static int backward_edge(BwdCall &c, int e) {
         a.bn1_coef = coef1;
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
         if (C == 32) {
-          auto kern = pw_bwd_cc_kernel<32, 1>;
+          auto kern = pw_bwd_q_kernel<32, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         } else {
-          auto kern = pw_bwd_cc_kernel<8, 1>;
+          auto kern = pw_bwd_q_kernel<8, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
         SENAS_TAG("reduce", 0, 0);
@@ -1057,13 +1057,12 @@ static int backward_edge(BwdCall &c, int e) {
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums1, C, (float)B * (float)HW, a.g1,
                      a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
-        dim3 grid_px(cdiv(HW, 128), B);
         if (C == 32) {
-          auto kern = pw_bwd_dz_kernel<32>;
-          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, st, a, c.a->training);
+          auto kern = pw_bwd_q_kernel<32, 2>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         } else {
-          auto kern = pw_bwd_dz_kernel<8>;
-          SENAS_LAUNCH(kern, grid_px, dim3(128), 0, st, a, c.a->training);
+          auto kern = pw_bwd_q_kernel<8, 2>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
         if (ed.op_type == SENAS_OP_NORM) {  // data / weight gradient of the depthwise half: backward_dw_group
           c.dw_wait[ed.src].push_back(ln);

@@ -445,46 +445,87 @@ struct PwArgs {
   float *partials;   // [B][gridDim.x][16]
 };
 
+// LP = C/4 lanes share a pixel: lane l loads channels 4l..4l+3 as one float4 (a warp reads 512 contiguous bytes), applies
+// BN1 + ReLU, multiplies its 4 x 8 slice of W_pw, and a transpose-reduce over the LP lanes (7 shuffles for C = 32)
+// leaves output channel l (C = 32) / channels 4l..4l+3 (C = 8) in lane l, so the y store is coalesced too.  (The
+// thread-per-pixel version read its own 128-byte line with 8 loads: 8 x the L1 wavefronts for the same bytes.)
+constexpr int kPwPx = 512;  // pixels per block
 template <int C>
-__global__ void __launch_bounds__(128) pw_fwd_kernel(PwArgs a) {
-  __shared__ float s_sc[C], s_sh[C];
-  __shared__ float s_w[C * 8];  // [ci][co]
-  const int tid = threadIdx.x, n = blockIdx.y;
-  if (tid < C) {
-    const float sc = a.g1[tid] * a.istd1[tid];
-    s_sc[tid] = sc, s_sh[tid] = a.b1[tid] - a.mean1[tid] * sc;
+__global__ void __launch_bounds__(256) pw_fwd_kernel(PwArgs a) {
+  constexpr int LP = C / 4, PPW = 32 / LP, NOUT = 8 / LP, UN = 4;
+  __shared__ float s_red[8][16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+  const int l = lane % LP, sub = lane / LP;
+  float sc[4], sh[4], w[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = l * 4 + j;
+    sc[j] = a.g1[c] * a.istd1[c], sh[j] = a.b1[c] - a.mean1[c] * sc[j];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) w[j][co] = __ldg(a.wpw + co * C + c);
   }
-  for (int i = tid; i < C * 8; i += 128) s_w[i] = __ldg(a.wpw + (i & 7) * C + (i >> 3));
-  __syncthreads();
-  const int p = blockIdx.x * 128 + tid;
-  float v[16];
+  float ssum[NOUT], ssq[NOUT];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = 0.f;
-  if (p < a.hw) {
-    const float *zp = a.z + ((int64_t)n * a.hw + p) * C;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < NOUT; ++j) ssum[j] = ssq[j] = 0.f;
+  const int p_begin = blockIdx.x * kPwPx, p_end = min(p_begin + kPwPx, a.hw);
+  const int per_warp = kPwPx / 8;
+  const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
+  const float *zn = a.z + (int64_t)n * a.hw * C + l * 4;
+  float *yn = a.y + (int64_t)n * a.hw * 8;
+  for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
+    float4 zv[UN];
 #pragma unroll
-    for (int c4 = 0; c4 < C; c4 += 4) {
-      const float4 zv = ld4(zp + c4);
-      const float r[4] = {fmaxf(fmaf(zv.x, s_sc[c4], s_sh[c4]), 0.f), fmaxf(fmaf(zv.y, s_sc[c4 + 1], s_sh[c4 + 1]), 0.f),
-                          fmaxf(fmaf(zv.z, s_sc[c4 + 2], s_sh[c4 + 2]), 0.f),
-                          fmaxf(fmaf(zv.w, s_sc[c4 + 3], s_sh[c4 + 3]), 0.f)};
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      zv[u] = p < w_end ? ld4(zn + (int64_t)p * C) : f4zero();
+    }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 w0 = ld4(s_w + (c4 + k) * 8), w1 = ld4(s_w + (c4 + k) * 8 + 4);
-        acc[0] = fmaf(r[k], w0.x, acc[0]), acc[1] = fmaf(r[k], w0.y, acc[1]);
-        acc[2] = fmaf(r[k], w0.z, acc[2]), acc[3] = fmaf(r[k], w0.w, acc[3]);
-        acc[4] = fmaf(r[k], w1.x, acc[4]), acc[5] = fmaf(r[k], w1.y, acc[5]);
-        acc[6] = fmaf(r[k], w1.z, acc[6]), acc[7] = fmaf(r[k], w1.w, acc[7]);
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      const float r[4] = {fmaxf(fmaf(zv[u].x, sc[0], sh[0]), 0.f), fmaxf(fmaf(zv[u].y, sc[1], sh[1]), 0.f),
+                          fmaxf(fmaf(zv[u].z, sc[2], sh[2]), 0.f), fmaxf(fmaf(zv[u].w, sc[3], sh[3]), 0.f)};
+      float v[8];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) v[co] = r[0] * w[0][co];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+#pragma unroll
+        for (int co = 0; co < 8; ++co) v[co] = fmaf(r[j], w[j][co], v[co]);
+      // transpose-reduce over the LP lanes of the pixel (fixed order)
+#pragma unroll
+      for (int m = LP / 2, nk = 4; m >= 1; m >>= 1, nk >>= 1) {
+        const bool hi = (lane & m) != 0;
+#pragma unroll
+        for (int j = 0; j < nk; ++j) {
+          const float send = hi ? v[j] : v[j + nk], keep = hi ? v[j + nk] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      if (p < w_end) {
+        float *yp = yn + (int64_t)p * 8 + l * NOUT;
+        if (NOUT == 4) st4(yp, make_float4(v[0], v[1], v[2], v[3]));
+        else yp[0] = v[0];
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) ssum[j] += v[j], ssq[j] += v[j] * v[j];
       }
     }
-    float *yp = a.y + ((int64_t)n * a.hw + p) * 8;
-    st4(yp, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    st4(yp + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = acc[j], v[8 + j] = acc[j] * acc[j];
   }
-  block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+  // statistics: combine the pixel groups of a warp (lanes with equal l), then the 8 warps, in fixed order
+#pragma unroll
+  for (int m = LP; m < 32; m <<= 1)
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j)
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], m), ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], m);
+  if (lane < LP) {
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) s_red[warp][l * NOUT + j] = ssum[j], s_red[warp][8 + l * NOUT + j] = ssq[j];
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float r = 0.f;
+    for (int wv = 0; wv < 8; ++wv) r += s_red[wv][tid];
+    a.partials[((int64_t)n * gridDim.x + blockIdx.x) * 16 + tid] = r;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1969,5 +2010,124 @@ __global__ void __launch_bounds__(128) dw_wgrad_multi_kernel(DwMultiArgs a) {
     const DwItem &it = a.it[m];
     if (it.k == 5) dw_wgrad_rows<C, 5>(it, n, a.H, a.W, by0, by1, bx, q, active, s_part, nblk_idx);
     else dw_wgrad_rows<C, 3>(it, n, a.H, a.W, by0, by1, bx, q, active, s_part, nblk_idx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dep-sep pointwise backward, quad layout (same as pw_fwd_kernel): LP = C/4 lanes share a pixel, lane l owns channels
+// 4l..4l+3 of z (one coalesced float4 per lane), the 8 dy values of the pixel are computed once by the group and
+// broadcast with shuffles, W_pw[:, 4l..4l+3] lives in registers.
+//   PASS 1: per-channel sums of du and du*zhat and dW_pw partials ([10C] per block);   PASS 2: dz in place over z.
+// ------------------------------------------------------------------------------------------------
+template <int C, int PASS>
+__global__ void __launch_bounds__(256) pw_bwd_q_kernel(PwBwdArgs a, int px_per_block, int training) {
+  constexpr int LP = C / 4, PPW = 32 / LP, NDY = 8 / LP, UN = 4;
+  __shared__ float s_part[PASS == 1 ? 8 : 1][PASS == 1 ? 10 * C : 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+  const int l = lane % LP, sub = lane / LP;
+  float sc[4], sh[4], mean1[4], istd1[4], wq[8][4], k0[4], k1[4], k2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = l * 4 + j;
+    mean1[j] = a.mean1[c], istd1[j] = a.istd1[c];
+    sc[j] = a.g1[c] * istd1[j], sh[j] = a.b1[c] - mean1[j] * sc[j];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) wq[co][j] = __ldg(a.wpw + co * C + c);
+    k0[j] = k1[j] = k2[j] = 0.f;
+    if (PASS == 2) k0[j] = a.bn1_coef[c], k1[j] = a.bn1_coef[C + c], k2[j] = a.bn1_coef[2 * C + c];
+  }
+  float cA[NDY], cB[NDY], cC[NDY];
+#pragma unroll
+  for (int j = 0; j < NDY; ++j) {
+    const int co = l * NDY + j;
+    cA[j] = a.coefA[n * 8 + co], cB[j] = a.coefB[n * 8 + co], cC[j] = a.coefC[n * 8 + co];
+  }
+  float s_du[4], s_duz[4], dw[8][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s_du[j] = s_duz[j] = 0.f;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) dw[co][j] = 0.f;
+  }
+  const int p_begin = blockIdx.x * px_per_block, p_end = min(p_begin + px_per_block, a.hw);
+  const int per_warp = (px_per_block + 7) / 8;
+  const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
+  float *zn = a.z + (int64_t)n * a.hw * C + l * 4;
+  const float *gn = a.gm + (int64_t)n * a.hw * 8 + l * NDY, *yn = a.y + (int64_t)n * a.hw * 8 + l * NDY;
+  for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
+    float4 zv[UN];
+    float dyl[UN][NDY];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      const bool ok = p < w_end;
+      const int pp = ok ? p : w_begin;
+      zv[u] = ld4(zn + (int64_t)pp * C);
+      if (NDY == 4) {
+        const float4 g4 = ld4(gn + (int64_t)pp * 8), y4 = ld4(yn + (int64_t)pp * 8);
+        dyl[u][0] = cA[0] * g4.x + cB[0] * y4.x + cC[0];
+        dyl[u][1 % NDY] = cA[1 % NDY] * g4.y + cB[1 % NDY] * y4.y + cC[1 % NDY];
+        dyl[u][2 % NDY] = cA[2 % NDY] * g4.z + cB[2 % NDY] * y4.z + cC[2 % NDY];
+        dyl[u][3 % NDY] = cA[3 % NDY] * g4.w + cB[3 % NDY] * y4.w + cC[3 % NDY];
+      } else {
+        dyl[u][0] = cA[0] * gn[(int64_t)pp * 8] + cB[0] * yn[(int64_t)pp * 8] + cC[0];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      const bool ok = p < w_end;
+      float dy[8];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) dy[co] = __shfl_sync(0xffffffffu, dyl[u][co % NDY], sub * LP + co / NDY);
+      const float z[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+      float dzo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float uu = fmaf(z[j], sc[j], sh[j]);
+        float dr = 0.f;
+#pragma unroll
+        for (int co = 0; co < 8; ++co) dr = fmaf(dy[co], wq[co][j], dr);
+        const float du = (uu > 0.f && ok) ? dr : 0.f;
+        const float zhat = (z[j] - mean1[j]) * istd1[j];
+        if (PASS == 1) {
+          const float r = ok ? fmaxf(uu, 0.f) : 0.f;
+          s_du[j] += du, s_duz[j] += du * zhat;
+#pragma unroll
+          for (int co = 0; co < 8; ++co) dw[co][j] = fmaf(dy[co], r, dw[co][j]);
+        } else {
+          dzo[j] = training ? k0[j] * (du - k1[j] - zhat * k2[j]) : k0[j] * du;
+        }
+      }
+      if (PASS == 2 && ok) st4(zn + (int64_t)p * C, make_float4(dzo[0], dzo[1], dzo[2], dzo[3]));
+    }
+  }
+  if (PASS == 1) {
+    // combine the PPW pixel groups of a warp (lanes with equal l), then the 8 warps, in fixed order
+#pragma unroll
+    for (int m = LP; m < 32; m <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s_du[j] += __shfl_xor_sync(0xffffffffu, s_du[j], m), s_duz[j] += __shfl_xor_sync(0xffffffffu, s_duz[j], m);
+#pragma unroll
+        for (int co = 0; co < 8; ++co) dw[co][j] += __shfl_xor_sync(0xffffffffu, dw[co][j], m);
+      }
+    }
+    if (lane < LP) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = l * 4 + j;
+        s_part[warp][c] = s_du[j], s_part[warp][C + c] = s_duz[j];
+#pragma unroll
+        for (int co = 0; co < 8; ++co) s_part[warp][2 * C + co * C + c] = dw[co][j];
+      }
+    }
+    __syncthreads();
+    float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
+    for (int o = tid; o < 10 * C; o += 256) {
+      float r = 0.f;
+      for (int wv = 0; wv < 8; ++wv) r += s_part[wv][o];
+      out[o] = r;
+    }
   }
 }

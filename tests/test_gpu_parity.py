@@ -209,7 +209,7 @@ def test_fixed_seed_search_genotype():
         # magnitude, so an entry whose noise-level gradient changes sign in both steps ends 4e-4 away; the gradient
         # itself is gated above (5e-2 of the largest entry) and the decisions are gated by the genotype below.
         d = (getattr(m, n).detach().cpu() - torch.from_numpy(g['arch.' + n])).abs()
-        assert d.max() < 4.5e-4 and (d > 2e-4).float().mean() < 0.1, (n, d.max().item(), (d > 2e-4).float().mean().item())
+        assert d.max() < 4.5e-4 and (d > 2.5e-4).sum() <= max(1, d.numel() // 10), (n, d.max().item(), (d > 2.5e-4).sum().item())
     assert repr(m.genotype()) == str(g['genotype'])
 
 
