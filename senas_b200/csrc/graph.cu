@@ -961,7 +961,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_AD_DW(32, AD_UP)
           const int n = 8 * C;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, st, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(grid.x * B), n);
         }
         break;
@@ -1051,7 +1051,7 @@ static int backward_edge(BwdCall &c, int e) {
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
         SENAS_TAG("reduce", 0, 0);
-        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, 32), 1), dim3(256), 0, st, (const float *)tmp, sums1,
+        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp, sums1,
                      (int)(nblk_cc * B), 10 * C);
         SENAS_TAG("pw_bfin", 0, 0);
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums1, C, (float)B * (float)HW, a.g1,
@@ -1143,7 +1143,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_FAIL("dw wgrad: unsupported c_in %d k %d", C, t.k);
           const int n = C * T;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, 32), 1), dim3(256), 0, st, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(g3.x * B), n);
         }
         break;
@@ -1224,7 +1224,7 @@ static int backward_dw_group(BwdCall &c, int src) {
     for (int m = 0; m < g.n; ++m) {
       const int nn = C * g.it[m].k * g.it[m].k;
       SENAS_TAG("reduce", 0, 0);
-      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(nn, 32), 1), dim3(256), 0, st, (const float *)(tmp + m * per),
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(nn, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)(tmp + m * per),
                    c.a->grad_params + goff[m], (int)(nblk * c.B), nn);
     }
   }
@@ -1273,11 +1273,13 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     {
       const int V = (1 + np.nterms) * 8;
       SENAS_TAG("reduce", 0, 0);
-      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(V, 32), c.B), dim3(256), 0, c.stream,
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(V, kRowsReduceCols), c.B), dim3(256), 0, c.stream,
                    (const float *)(c.scratch + np.bpart_off), c.scratch + np.bsum_off, np.nblk, V);
     }
     SENAS_TAG("node_bfin", 0, 0);
-    SENAS_LAUNCH(node_bfin_kernel, dim3(1), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
+    int n_in = 0;
+    for (int e = 0; e < d.n_edges; ++e) n_in += d.edge[e].dst == i;
+    SENAS_LAUNCH(node_bfin_kernel, dim3(n_in), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
     c.S.fork();  // the candidate chains of this node's edges run on the lanes, concurrently with the next node's sweep
     for (int e = 0; e < d.n_edges; ++e)

@@ -355,11 +355,29 @@ SENAS_DEVFN float block_rows_sum(const float *src, int rows, int V, int col) {
   return t;
 }
 
-// dst[group][V] = sum over rows of src[group][rows][V];  grid = (ceil(V/32), groups), block = 256
+// dst[group][V] = sum over rows of src[group][rows][V];  grid = (ceil(V/8), groups), block = 256 = 32 row lanes x 8
+// columns (a 32-byte sector per row and block): V is a few hundred at most, so 32 columns per block left the reduction of
+// a few thousand partial rows to ~10-25 blocks.  Fixed order: lane r sums rows r, r+32, ...; lanes combined 0..31.
+constexpr int kRowsReduceCols = 8;
 __global__ void __launch_bounds__(256) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const float t = block_rows_sum(src + (int64_t)blockIdx.y * rows * V, rows, V, col);
-  if (threadIdx.x < 32 && col < V) dst[(int64_t)blockIdx.y * V + col] = t;
+  __shared__ float s_rr[32][kRowsReduceCols + 1];
+  const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3, col = blockIdx.x * kRowsReduceCols + cl;
+  const float *p = src + (int64_t)blockIdx.y * rows * V + col;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+  if (col < V) {
+    int b = rl;
+    for (; b + 96 < rows; b += 128) {
+      r0 += p[(int64_t)b * V], r1 += p[(int64_t)(b + 32) * V], r2 += p[(int64_t)(b + 64) * V], r3 += p[(int64_t)(b + 96) * V];
+    }
+    for (; b < rows; b += 32) r0 += p[(int64_t)b * V];
+  }
+  s_rr[rl][cl] = (r0 + r1) + (r2 + r3);
+  __syncthreads();
+  if (threadIdx.x < kRowsReduceCols && col < V) {
+    float t = 0.f;
+    for (int r = 0; r < 32; ++r) t += s_rr[r][threadIdx.x];
+    dst[(int64_t)blockIdx.y * V + col] = t;
+  }
 }
 
 // dst[widx_t*ws_t + ci*ws_k + co*ws_n] = sum_blk partials[blk][t][ci][co];  grid = ceil(T*KC*8/32), block = 256
@@ -1032,7 +1050,9 @@ __global__ void __launch_bounds__(128) node_bstats_kernel(const NodeDesc *nodes,
   }
 }
 
-// backward finalize for one node: reductions, parameter / alpha / beta gradients, dy coefficient tables
+// backward finalize for one node: reductions, parameter / alpha / beta gradients, dy coefficient tables.
+// grid = incoming edges of the node (the terms of different edges are independent; this kernel sits on the critical path
+// of every node's backward, 3 per cell, and took ~50 us as a single block walking up to 24 terms)
 __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, int node, Bases bases, const float *alpha,
                                                         const float *beta, float *g_alpha, float *g_beta, float *g_params,
                                                         int batch, int training) {
@@ -1042,15 +1062,17 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
   __shared__ float s_S1[128 * 8], s_S2[128 * 8];  // [n][c], batch <= 128
   __shared__ float s_u[128 * 8], s_dh[128];
   __shared__ float s_T[8], s_dg[8], s_db[8];
-  __shared__ float s_gbeta[4];
+  __shared__ float s_gbeta;
+  const int my_edge = nd.edges[blockIdx.x];
   const int tid = threadIdx.x, total = batch * 8, V = (1 + nd.nterms) * 8;
   const float *bsum = scratch + nd.bsum_off;
   const float M = (float)batch * (float)nd.hw;
-  if (tid < 4) s_gbeta[tid] = 0.f;
+  if (tid == 0) s_gbeta = 0.f;
   for (int i = tid; i < total; i += 128) s_S1[i] = bsum[(int64_t)(i >> 3) * V + (i & 7)];
   __syncthreads();
   for (int ti = 0; ti < nd.nterms; ++ti) {
     const TermDesc &t = nd.t[ti];
+    if (t.edge != my_edge) continue;  // block-uniform
     const float w = alpha[t.edge * 6 + t.cand], be = beta ? beta[t.edge] : 1.f, kappa = w * be;
     const bool se = t.kind == 5;
     for (int i = tid; i < total; i += 128)
@@ -1102,8 +1124,7 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
       float Ts = 0.f;
       for (int c = 0; c < 8; ++c) Ts += s_T[c];
       g_alpha[t.edge * 6 + t.cand] = be * Ts;
-      for (int k = 0; k < nd.nedges; ++k)
-        if (nd.edges[k] == t.edge) s_gbeta[k] += w * Ts;
+      s_gbeta += w * Ts;
     }
     if (t.has_y) {
       float *cf = scratch + t.coef_off;
@@ -1121,7 +1142,7 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
     }
     __syncthreads();
   }
-  if (g_beta != nullptr && tid < nd.nedges) g_beta[nd.edges[tid]] = s_gbeta[tid];
+  if (g_beta != nullptr && tid == 0) g_beta[my_edge] = s_gbeta;
 }
 
 // ------------------------------------------------------------------------------------------------
