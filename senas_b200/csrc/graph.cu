@@ -129,9 +129,9 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
 static const int kDwRows = 4;       // output rows per block in the sliding-window depthwise kernels
 static int gather_pix(int NC, int si, int base_w);
-// grouped depthwise kernels: columns per tile (forward / data gradient: 2 per thread; weight gradient: 1 per thread) and
+// grouped depthwise kernels: columns per tile (forward / data gradient: kDwCols per thread; weight gradient: 1 per thread) and
 // rows per tile, the largest of 32/16/8/4 that still gives the 148 SMs at least four blocks each
-static int dw_tiles_x(int C, int w, bool wgrad) { return cdiv(w, (wgrad ? 1 : 2) * (128 / (C / 4))); }
+static int dw_tiles_x(int C, int w, bool wgrad) { return cdiv(w, (wgrad ? 1 : kDwCols) * (128 / (C / 4))); }
 static int dw_rows(int C, int B, int h, int w, bool wgrad) {
   const int tx = dw_tiles_x(C, w, wgrad);
   for (int r = 32; r > 4; r /= 2)

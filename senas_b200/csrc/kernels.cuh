@@ -1853,13 +1853,19 @@ SENAS_DEVFN void fma4(float4 &a, const float4 &x, const float4 &w) {
 // The first version kept the K x K x 4 weights in registers (222-254 registers, 8 warps per SM): ncu showed it
 // latency-bound (issue slots 21 % active, FMA pipe 13 %) while filling the register file, so nothing could run beside
 // it.  Weights now sit in shared memory as [tap][C] (one conflict-free LDS.128 per tap and row, 8 FMAs each).
-template <int C, int K, bool STATS>
+// ncu (profiles/): a 128-bit shared-memory load costs ~2.6 LSU wavefronts even when the quarter-warps read the same 128
+// bytes, so with 2 columns per thread the 25 weight loads of a 5x5 row step were 65 % of the LSU traffic and the kernel
+// sat at 54 % of the L1/LSU pipe with the FMA pipe at 26 %.  NCOL = 4 columns per thread halves the weight traffic per
+// FMA; the read-modify-write of a shared dx (data gradient) is issued before the FMAs of the step that completes the row.
+template <int C, int K, int NCOL, bool STATS>
 SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int bx, int q,
                               float *st) {
-  constexpr int P = K / 2, NX = K + 1;
-  float4 acc[K][2];
+  constexpr int P = K / 2, NX = K + NCOL - 1;
+  float4 acc[K][NCOL];
 #pragma unroll
-  for (int s = 0; s < K; ++s) acc[s][0] = acc[s][1] = f4zero();
+  for (int s = 0; s < K; ++s)
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) acc[s][j] = f4zero();
   bool cok[NX];
 #pragma unroll
   for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
@@ -1868,11 +1874,19 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
   const float *wq = s_w + q * 4;
   const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
   const int64_t in_ld = it.in_ld;
+  const bool rmw = it.accumulate != 0;
   for (int i0 = 0; i0 < niter; i0 += K) {
 #pragma unroll
     for (int u = 0; u < K; ++u) {
       const int i = i0 + u, rr = r_first + i;
       if (i < niter) {
+        const int o = by0 + i - (K - 1);  // output row completed by this step (when i >= K - 1)
+        float4 old[NCOL];
+        if (rmw && i >= K - 1) {
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j)
+            old[j] = bx + j < W ? ld4(outb + ((int64_t)o * W + bx + j) * it.out_ld) : f4zero();
+        }
         if (rr >= 0 && rr < H) {
           float4 xv[NX];
           const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
@@ -1885,24 +1899,20 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
 #pragma unroll
               for (int kx = 0; kx < K; ++kx) {
                 const float4 wv = ld4(wq + (ky * K + kx) * C);
-                fma4(acc[s][0], xv[kx], wv);
-                fma4(acc[s][1], xv[kx + 1], wv);
+#pragma unroll
+                for (int j = 0; j < NCOL; ++j) fma4(acc[s][j], xv[kx + j], wv);
               }
             }
           }
         }
         const int sc = (u + 1) % K;
-        if (i >= K - 1) {  // output row by0 + i - (K - 1) is complete
-          const int o = by0 + i - (K - 1);
+        if (i >= K - 1) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < NCOL; ++j) {
             if (bx + j < W) {
               float *op = outb + ((int64_t)o * W + bx + j) * it.out_ld;
               float4 v = acc[sc][j];
-              if (it.accumulate) {
-                const float4 old = ld4(op);
-                v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
-              }
+              if (rmw) v.x += old[j].x, v.y += old[j].y, v.z += old[j].z, v.w += old[j].w;
               st4(op, v);
               if (STATS) {
                 st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
@@ -1911,23 +1921,25 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
             }
           }
         }
-        acc[sc][0] = acc[sc][1] = f4zero();
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) acc[sc][j] = f4zero();
       }
     }
   }
 }
 
-// grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column pairs => 256/Q columns per tile,
-// tile_rows rows (chosen by the host so that the grid fills the 148 SMs several times over)
+// grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column groups of kDwCols => 512/Q columns
+// per tile, tile_rows rows (chosen by the host so that the grid fills the 148 SMs several times over)
+constexpr int kDwCols = 4;
 template <int C, bool STATS>
-__global__ void __launch_bounds__(128) dw_multi_kernel(DwMultiArgs a) {
-  constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = 2 * SLOTS;
+__global__ void __launch_bounds__(128, 3) dw_multi_kernel(DwMultiArgs a) {
+  constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = kDwCols * SLOTS;
   __shared__ float s_red[STATS ? 128 : 1][8];
   __shared__ float4 s_w4[25 * C / 4];
   float *s_w = reinterpret_cast<float *>(s_w4);
   const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
   const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
-  const int bx = tx * NCB + 2 * slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
+  const int bx = tx * NCB + kDwCols * slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
   const bool active = bx < a.W;
   for (int m = 0; m < a.n; ++m) {
     const DwItem &it = a.it[m];
@@ -1940,8 +1952,8 @@ __global__ void __launch_bounds__(128) dw_multi_kernel(DwMultiArgs a) {
     __syncthreads();
     float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (active) {
-      if (it.k == 5) dw_tile_rows<C, 5, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
-      else dw_tile_rows<C, 3, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
+      if (it.k == 5) dw_tile_rows<C, 5, kDwCols, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
+      else dw_tile_rows<C, 3, kDwCols, STATS>(it, s_w, n, a.H, a.W, by0, by1, bx, q, st);
     }
     if (STATS) {
 #pragma unroll
