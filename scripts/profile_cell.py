@@ -9,12 +9,13 @@ import senas_b200
 mode = sys.argv[1] if len(sys.argv) > 1 else 'bf16'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+res = int(sys.argv[4]) if len(sys.argv) > 4 else 256   # node resolution of the up cell (in0 res x res, in1 res/2)
 senas_b200.exact_fp32(); senas_b200.set_conv_mode(mode)
 torch.manual_seed(0)
 dev = 'cuda:0'
 c = senas_b200.Cell(3, 1, 32, 32, 32, 'up'); c.apply(senas_b200.weights_init); c = c.to(dev)
-in0 = torch.randn(B, 32, 256, 256, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-in1 = torch.randn(B, 32, 128, 128, device=dev).relu().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+in0 = torch.randn(B, 32, res, res, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+in1 = torch.randn(B, 32, res // 2, res // 2, device=dev).relu().contiguous(memory_format=torch.channels_last).requires_grad_(True)
 wn, wc = torch.softmax(torch.randn(9, 6, device=dev), -1), torch.softmax(torch.randn(9, 6, device=dev), -1)
 b = torch.softmax(torch.randn(9, device=dev), -1)
 lib = senas_b200._lib.get()

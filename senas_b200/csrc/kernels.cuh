@@ -1930,9 +1930,9 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
 
 // grid = (tiles_x * tiles_y, B), block = 128:  Q = C/4 channel quads x (128/Q) column groups of kDwCols => 512/Q columns
 // per tile, tile_rows rows (chosen by the host so that the grid fills the 148 SMs several times over)
-constexpr int kDwCols = 4;
+constexpr int kDwCols = 2;
 template <int C, bool STATS>
-__global__ void __launch_bounds__(128, 3) dw_multi_kernel(DwMultiArgs a) {
+__global__ void __launch_bounds__(128, 4) dw_multi_kernel(DwMultiArgs a) {
   constexpr int Q = C / 4, SLOTS = 128 / Q, NCB = kDwCols * SLOTS;
   __shared__ float s_red[STATS ? 128 : 1][8];
   __shared__ float4 s_w4[25 * C / 4];
