@@ -42,6 +42,7 @@ struct TcConvArgs {
   int32_t H, W, Ho, Wo, so;
   int32_t rows_per_cta, row_chunks;
   int32_t P, S;                  // staged pixels per row (even), ring slots
+  int32_t img_mul, img_add;      // image index of the TMA source = n * img_mul + img_add (phase-major packed dy of UP)
   TapTable taps;
 };
 
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
         const int slot = idx & (a.S - 1), use = idx / a.S;
         if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
         mbar_expect_tx(&full[slot], row_bytes);
-        tma_load_5d(rows + (size_t)slot * row_bytes, &tmap, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n);
+        tma_load_5d(rows + (size_t)slot * row_bytes, &tmap, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n * a.img_mul + a.img_add);
       }
     }
   } else if (warp == 1) {
@@ -323,13 +324,22 @@ struct PackDyArgs {
   const float *gm[kTcMaxTerms], *y[kTcMaxTerms], *coef[kTcMaxTerms];  // coef: [3][B][8]
   int64_t y_ld[kTcMaxTerms];
   int32_t nterms, hw, batch;
+  int32_t up_h, up_w;  // > 0: UP edges -- gm / y live on the (2 up_h) x (2 up_w) output grid and dst is phase-major
+                       // [B][4 phases][up_h][up_w][32], each phase a dense image on the input grid (hw = up_h * up_w)
   __nv_bfloat16 *dst;
 };
 __global__ void __launch_bounds__(256) pack_dy_kernel(PackDyArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x, total = (int64_t)a.batch * a.hw * 4;
+  const int64_t phases = a.up_h > 0 ? 4 : 1;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x, total = (int64_t)a.batch * phases * a.hw * 4;
   if (i >= total) return;
-  const int64_t pix = i >> 2;
-  const int g = (int)(i & 3), n = (int)(pix / a.hw);
+  const int64_t dpix = i >> 2;  // destination pixel
+  const int g = (int)(i & 3), n = (int)(dpix / (phases * a.hw));
+  int64_t pix = dpix;           // source pixel (same image geometry unless UP)
+  if (a.up_h > 0) {
+    const int64_t r = dpix - (int64_t)n * 4 * a.hw;
+    const int ph = (int)(r / a.hw), ij = (int)(r - (int64_t)ph * a.hw), ii = ij / a.up_w, jj = ij - ii * a.up_w;
+    pix = ((int64_t)n * 2 * a.up_h + 2 * ii + (ph >> 1)) * (2 * a.up_w) + 2 * jj + (ph & 1);
+  }
   __align__(16) __nv_bfloat16 v[8];
   if (g < a.nterms) {
     const float4 glo = ld4(a.gm[g] + pix * 8), ghi = ld4(a.gm[g] + pix * 8 + 4);
@@ -343,7 +353,7 @@ __global__ void __launch_bounds__(256) pack_dy_kernel(PackDyArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(0.f);
   }
-  *reinterpret_cast<uint4 *>(a.dst + pix * 32 + g * 8) = *reinterpret_cast<const uint4 *>(v);
+  *reinterpret_cast<uint4 *>(a.dst + dpix * 32 + g * 8) = *reinterpret_cast<const uint4 *>(v);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -358,6 +368,7 @@ constexpr int kTcDySlots = 4;
 struct TcWgradArgs {
   int32_t H, W, rows_per_cta, row_chunks, P, S;
   int32_t t_begin, t_count;  // taps [t_begin, t_begin + t_count) of the table
+  int32_t dy_img_mul, dy_img_add;  // image index of the dy rows = n * dy_img_mul + dy_img_add
   float *partials;           // [B * gridDim.x][t_count][32 ci][32 m]
   TapTable taps;
 };
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
         const int ds = it & (kTcDySlots - 1), duse = it / kTcDySlots;
         if (duse > 0) mbar_wait(&dempty[ds], (uint32_t)((duse - 1) & 1));
         mbar_expect_tx(&dfull[ds], dy_bytes);
-        tma_load_5d(dyr + (size_t)ds * dy_bytes, &tmap_dy, &dfull[ds], 0, x0, r, 0, n);
+        tma_load_5d(dyr + (size_t)ds * dy_bytes, &tmap_dy, &dfull[ds], 0, x0, r, 0, n * a.dy_img_mul + a.dy_img_add);
       }
     }
   } else if (warp == 1) {
@@ -512,6 +523,7 @@ static size_t tc_smem_bytes(const TcConvArgs &a) {
 // xb: dense bf16 NHWC [B][H][W][32].  Returns 0 on success, 1 when the geometry cannot run here (caller falls back
 // to the exact fp32 kernel of the same family, still on the GPU), 2 on a driver error.
 static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *stream) {
+  if (a.img_mul == 0) a.img_mul = 1;
   PFN_tmapEncodeTiled enc = tc_encode_fn();
   if (!enc) return 2;
   const int span_x = a.taps.max_dx - a.taps.min_dx, span_y = a.taps.max_dy - a.taps.min_dy;
@@ -522,7 +534,7 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
   const size_t smem = tc_smem_bytes(a);
   if (smem > 220 * 1024) return 1;
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, 4, (cuuint64_t)B};
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, 4, (cuuint64_t)B * a.img_mul};
   const cuuint64_t gstr[4] = {64, (cuuint64_t)a.W * 64, 16, (cuuint64_t)a.H * a.W * 64};
   const cuuint32_t box[5] = {8, (cuuint32_t)a.P, 1, 4, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -551,24 +563,27 @@ static int tc_encode(CUtensorMap *tmap, const __nv_bfloat16 *p, int B, int H, in
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
 }
 
-// wgrad of one NORM group: two launches of <= 13 taps each + reductions.  partials: >= B*ctas*13*1024 floats.
+// wgrad of one group over taps [t0, t1) of `taps`: launches of <= 13 taps each + reductions.  partials: >= B*ctas*13*1024
+// floats.  dy rows come from image n * dy_mul + dy_add of dyb (NORM: 1, 0; UP: 4, phase).
 static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dyb, int B, int H, int W, const TapTable &taps,
-                                float *partials, float *const *dst, int nterms, int ws_ci, int ws_co, void *stream) {
+                                int t0, int t1, int dy_mul, int dy_add, float *partials, float *const *dst, int nterms,
+                                int ws_ci, int ws_co, void *stream) {
   TcWgradArgs a;
   memset(&a, 0, sizeof(a));
   a.H = H, a.W = W, a.rows_per_cta = 32, a.row_chunks = (H + 31) / 32, a.taps = taps, a.partials = partials;
+  a.dy_img_mul = dy_mul, a.dy_img_add = dy_add;
   a.P = (kTcM + taps.max_dx - taps.min_dx + 1) & ~1, a.S = 16;
   const size_t smem = (size_t)a.S * a.P * 64 + (size_t)(kTcDySlots + 1) * 8192 + (size_t)(2 * a.S + 2 * kTcDySlots + 2) * 8 + 64;
   CUtensorMap mx, md;
-  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B, H, W, 128)) return 2;
+  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B * dy_mul, H, W, 128)) return 2;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
     attr_smem = smem;
   }
   dim3 grid((W / kTcM) * a.row_chunks, B);
-  for (int tb = 0; tb < taps.n; tb += kTcWTaps) {
-    a.t_begin = tb, a.t_count = std::min(kTcWTaps, taps.n - tb);
+  for (int tb = t0; tb < t1; tb += kTcWTaps) {
+    a.t_begin = tb, a.t_count = std::min(kTcWTaps, t1 - tb);
     SENAS_TAG("conv_tc_wgrad", 2.0 * B * H * W * a.t_count * 32 * 8 * nterms, 4.0 * B * H * W * 32);
     SENAS_LAUNCH(conv_tc_wgrad_kernel, grid, dim3(kTcThreads), smem, stream, mx, md, a);
     TcWgradReduceArgs ra;

@@ -255,8 +255,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     }
     for (auto &g2 : p->tc_groups) {
       if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
-      if (g2.op == SENAS_OP_NORM)
-        tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / kTcM) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
+      tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / kTcM) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
     }
   }
 #endif
@@ -343,8 +342,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
   }
   p->dyb_off.assign(p->tc_groups.size(), -1);
   for (size_t gi = 0; gi < p->tc_groups.size(); ++gi) {  // one packed-dy buffer per NORM group (groups run concurrently)
-    const TcGroup &g2 = p->tc_groups[gi];
-    if (g2.op == SENAS_OP_NORM) p->dyb_off[gi] = take(sc, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
+    const TcGroup &g2 = p->tc_groups[gi];  // UP: dy lives on the 2x grid, packed phase-major (4 images per sample)
+    p->dyb_off[gi] = take(sc, (int64_t)B * ih[g2.src] * iw[g2.src] * 16 * (g2.op == SENAS_OP_UP ? 4 : 1));
   }
   tmp_need = align4(tmp_need);
   p->tmp_off = take(sc, tmp_need * kLanes);  // one slice per general lane
@@ -968,7 +967,7 @@ static int backward_edge(BwdCall &c, int e) {
       }
       case SENAS_KIND_CONV:
       case SENAS_KIND_SE_CONV: {
-        if (dx && !(t.tc && ed.op_type == SENAS_OP_NORM)) {  // NORM tcgen05 groups: data gradient at the end of backward
+        if (dx && !t.tc) {  // tcgen05 groups: data gradient at the end of backward
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_DGRAD);
           GatherArgs a;
           memset(&a, 0, sizeof(a));
@@ -985,7 +984,7 @@ static int backward_edge(BwdCall &c, int e) {
           if (launch_gather_any(a, geo, 8, C, B, sdx)) return 1;
           c.touched[ed.src] = true;
         }
-        if (ed.grad_off[k][0] >= 0 && !(t.tc && ed.op_type == SENAS_OP_NORM && c.a->grad_in[ed.src])) {
+        if (ed.grad_off[k][0] >= 0 && !(t.tc && c.a->grad_in[ed.src])) {
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           WgradArgs a;
           memset(&a, 0, sizeof(a));
@@ -1293,10 +1292,14 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     }
   }
 #ifndef SENAS_EMU
-  // grouped data gradient of the NORM tcgen05 groups: dx[src] += sum over the group's edges and taps (K = 8 x edges)
+  // grouped data gradient + weight gradient of the tcgen05 groups: dx[src] += sum over the group's edges and taps
+  // (GEMM-K = 8 x edges).  NORM: one conv over the packed dy.  UP (ConvTranspose2d as 4 output phases on the input grid,
+  // y_ph[i] = sum_{t in ph} x[i + d_t] W_t): dy is packed phase-major, and each phase is an ordinary stride-1 problem on
+  // the input grid -- dx[i] += sum_{t in ph} dy_ph[i - d_t] W_t^T,  dW_t = sum_i x[i + d_t]^T dy_ph(t)[i].
   for (size_t gi = 0; gi < p->tc_groups.size(); ++gi) {
     const TcGroup &g2 = p->tc_groups[gi];
-    if (g2.op != SENAS_OP_NORM || !a->grad_in[g2.src]) continue;
+    if (!a->grad_in[g2.src]) continue;
+    const bool up = g2.op == SENAS_OP_UP;
     const EdgePlan &ep0 = p->edges[g2.edge[0]];
     const int64_t npix = (int64_t)c.B * ep0.in_h * ep0.in_w;
     __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off[gi]);
@@ -1305,6 +1308,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     PackDyArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.nterms = g2.nterms, pa.hw = ep0.in_h * ep0.in_w, pa.batch = c.B, pa.dst = dyb;
+    if (up) pa.up_h = ep0.in_h, pa.up_w = ep0.in_w;
     TcConvArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.nterms = g2.nterms, ta.mode = 1;
@@ -1315,29 +1319,56 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       pa.coef[i] = c.scratch + t.coef_off;
       ta.w[i] = (const float *)d.edge[e].param[k][0];
     }
-    SENAS_TAG("pack_dy", 0, npix * (64.0 * g2.nterms + 64.0));
-    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, st, pa);
+    const int nph = up ? 4 : 1;
+    SENAS_TAG("pack_dy", 0, npix * nph * (64.0 * g2.nterms + 64.0));
+    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * nph * 4 + 255) / 256)), dim3(256), 0, st, pa);
     c.S.dep(ln, dxl);
-    Geo geo = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD);
+    const Geo gf = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);
     ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = ep0.in_h, ta.Wo = ep0.in_w, ta.so = 1;
-    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
-    ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src], ta.accumulate = c.touched[g2.src];
-    SENAS_TAG("conv_tc_dgrad", 2.0 * npix * geo.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
-    const int rc = launch_conv_tc(dyb, c.B, ta, c.S.stream(dxl));
-    if (rc) SENAS_FAIL("tcgen05 dgrad launch failed (code %d)", rc);
-    c.touched[g2.src] = true;
+    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32);
+    ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src];
+    for (int ph = 0; ph < nph; ++ph) {
+      if (up) {  // mirrored taps of this output phase, as a single-phase table on the input grid
+        const int t0 = gf.taps.pstart[ph], t1 = gf.taps.pstart[ph + 1];
+        if (t1 == t0) continue;
+        TapTable tt;
+        memset(&tt, 0, sizeof(tt));
+        tt.n = t1 - t0, tt.nphase = 1;
+        tt.min_dy = tt.min_dx = 1000, tt.max_dy = tt.max_dx = -1000;
+        for (int t = t0; t < t1; ++t) {
+          const int q = t - t0, dy = -gf.taps.dy[t], dx = -gf.taps.dx[t];
+          tt.dy[q] = (int8_t)dy, tt.dx[q] = (int8_t)dx, tt.widx[q] = gf.taps.widx[t], tt.phase[q] = 0;
+          tt.min_dy = std::min(tt.min_dy, dy), tt.max_dy = std::max(tt.max_dy, dy);
+          tt.min_dx = std::min(tt.min_dx, dx), tt.max_dx = std::max(tt.max_dx, dx);
+        }
+        tt.pstart[0] = 0;
+        for (int q = 1; q <= 4; ++q) tt.pstart[q] = tt.n;
+        ta.taps = tt, ta.img_mul = 4, ta.img_add = ph;
+      } else {
+        ta.taps = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD).taps, ta.img_mul = 1, ta.img_add = 0;
+      }
+      ta.accumulate = c.touched[g2.src];
+      SENAS_TAG("conv_tc_dgrad", 2.0 * npix * ta.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
+      const int rc = launch_conv_tc(dyb, c.B, ta, c.S.stream(dxl));
+      if (rc) SENAS_FAIL("tcgen05 dgrad launch failed (code %d)", rc);
+      c.touched[g2.src] = true;
+    }
     // weight gradients of the group from the same packed dy (pixels = GEMM-K)
     {
-      Geo gf = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
       float *dst[kTcMaxTerms] = {nullptr, nullptr, nullptr, nullptr};
       for (int i = 0; i < g2.nterms; ++i) dst[i] = a->grad_params + d.edge[g2.edge[i]].grad_off[g2.cand[i]][0];
       int ws_ci, ws_co;
       conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ws_ci, &ws_co);
-      const int rcw = launch_conv_tc_wgrad(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), dyb, c.B,
-                                           ep0.in_h, ep0.in_w, gf.taps, c.tmp(ln), dst, g2.nterms, ws_ci, ws_co, st);
-      if (rcw) SENAS_FAIL("tcgen05 wgrad launch failed (code %d)", rcw);
+      const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]);
+      for (int ph = 0; ph < nph; ++ph) {
+        const int t0 = up ? gf.taps.pstart[ph] : 0, t1 = up ? gf.taps.pstart[ph + 1] : gf.taps.n;
+        if (t1 == t0) continue;
+        const int rcw = launch_conv_tc_wgrad(xb, dyb, c.B, ep0.in_h, ep0.in_w, gf.taps, t0, t1, up ? 4 : 1, up ? ph : 0,
+                                             c.tmp(ln), dst, g2.nterms, ws_ci, ws_co, st);
+        if (rcw) SENAS_FAIL("tcgen05 wgrad launch failed (code %d)", rcw);
+      }
     }
   }
 #endif

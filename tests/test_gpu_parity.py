@@ -328,8 +328,8 @@ def l2_err(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize('representable', [True, False])
-def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable):
+@pytest.mark.parametrize('representable,w0', [(True, 128), (False, 128), (True, 256)])
+def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable, w0):
     """Up cell with in0 128 wide: the NORM edges 0/2/5 form 3-edge tcgen05 groups (forward, grouped data gradient,
     weight gradient with 24 real rows), the UP edges 1/3/6 (in1 64 wide) stay on the exact kernels.
 
@@ -343,14 +343,17 @@ def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable):
     torch.manual_seed(11)
     c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
     c.apply(senas_b200.weights_init)
-    in0, in1 = torch.randn(2, 32, 16, 128), torch.randn(2, 32, 8, 64)
+    # w0 = 256: in1 is 128 wide, so the UP edges 1/3/6 run on tcgen05 too (forward phases, phase-major data / weight gradient)
+    in0, in1 = torch.randn(2, 32, 16, w0), torch.randn(2, 32, 8, w0 // 2)
     if representable:
-        in0 = in0.bfloat16().float()
+        in0, in1 = in0.bfloat16().float(), in1.bfloat16().float()
         with torch.no_grad():
-            for e in (0, 2, 5):
-                for k in (2, 3):
-                    w = c._ops[e]._ops[k][0].weight
-                    w.copy_(w.bfloat16().float())
+            convs = [(e, k) for e in (0, 2, 5) for k in (2, 3)]
+            if w0 == 256:
+                convs += [(e, k) for e in (1, 3, 6) for k in (1, 2, 3)]
+            for e, k in convs:
+                w = c._ops[e]._ops[k][0].weight
+                w.copy_(w.bfloat16().float())
     store = oracle.clone_store(c.state_dict())
     wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
     b = torch.softmax(torch.randn(9), -1)
