@@ -43,6 +43,7 @@ struct TcConvArgs {
   int32_t rows_per_cta, row_chunks;
   int32_t P, S;                  // staged pixels per row (even), ring slots
   int32_t img_mul, img_add;      // image index of the TMA source = n * img_mul + img_add (phase-major packed dy of UP)
+  int32_t M;                     // pixels per MMA = strip width: 128, or 64 for maps that are a multiple of 64 wide only
   TapTable taps;
 };
 
@@ -128,9 +129,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y;
   const int xseg = blockIdx.x / a.row_chunks, chunk = blockIdx.x - xseg * a.row_chunks;
-  const int x0 = xseg * kTcM;
+  const int x0 = xseg * a.M;
   const int r0 = chunk * a.rows_per_cta, r_end = min(r0 + a.rows_per_cta, a.H);
   const int T = a.taps.n, NPH = a.taps.nphase;
+  // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 32, M = 128 or 64
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(a.M >> 4) << 24);
   const uint32_t row_bytes = (uint32_t)a.P * 64u;
   unsigned char *rows = smem;
   unsigned char *wsm = smem + (size_t)a.S * row_bytes;  // [T][4 k-chunks][32 n][8 k] bf16
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
             const uint32_t alo = a_lo_base + (((uint32_t)it + trow) & smask) * row16 + tcol;
             const uint32_t blo = b_lo_base + (uint32_t)t * 128u;
             if (leader) {
-              umma_bf16(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, kTcIdesc, acc);
-              umma_bf16(d, ((uint64_t)hi << 32) | (alo + a_khalf), ((uint64_t)hi << 32) | (blo + 64u), kTcIdesc, 1u);
+              umma_bf16(d, ((uint64_t)hi << 32) | alo, ((uint64_t)hi << 32) | blo, idesc, acc);
+              umma_bf16(d, ((uint64_t)hi << 32) | (alo + a_khalf), ((uint64_t)hi << 32) | (blo + 64u), idesc, 1u);
             }
             acc = 1;
           }
@@ -238,7 +241,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   } else {
     // ===== epilogue: TMEM -> registers -> y (fp32) + statistics =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int px = x0 + q * 32 + lane;
+    // M = 128: accumulator row m sits in TMEM lane m.  M = 64: rows 16q..16q+15 sit in lanes 0..15 of quarter q.
+    const bool lane_ok = a.M == 128 || lane < 16;
+    const int px = x0 + (a.M == 128 ? q * 32 : q * 16) + lane;
     int it = 0;
     for (int r = r0; r < r_end; ++r, ++it) {
       const int buf = it & 1;
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
         }
         const int oy = r * a.so + (ph >> 1), ox = px * a.so + (ph & 1);
         if (a.mode == 1) {
+          if (!lane_ok) continue;
           float *o = a.out32 + (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.out_ld;
 #pragma unroll
           for (int j = 0; j < kTcN; j += 4) {
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
             }
             st4(o + j, u);
           }
-        } else if (px < a.W && oy < a.Ho && ox < a.Wo) {
+        } else if (lane_ok && px < a.W && oy < a.Ho && ox < a.Wo) {
           const int64_t pix = ((int64_t)n * a.Ho + oy) * a.Wo + ox;
 #pragma unroll
           for (int g = 0; g < kTcMaxTerms; ++g) {
@@ -367,6 +373,7 @@ constexpr int kTcWTaps = 13;
 constexpr int kTcDySlots = 4;
 struct TcWgradArgs {
   int32_t H, W, rows_per_cta, row_chunks, P, S;
+  int32_t Wt;                // strip width in pixels (= GEMM-K per row): 128 or 64
   int32_t t_begin, t_count;  // taps [t_begin, t_begin + t_count) of the table
   int32_t dy_img_mul, dy_img_add;  // image index of the dy rows = n * dy_img_mul + dy_img_add
   float *partials;           // [B * gridDim.x][t_count][32 ci][32 m]
@@ -382,9 +389,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y;
   const int xseg = blockIdx.x / a.row_chunks, chunk = blockIdx.x - xseg * a.row_chunks;
-  const int x0 = xseg * kTcM;
+  const int x0 = xseg * a.Wt;
   const int r0 = chunk * a.rows_per_cta, r_end = min(r0 + a.rows_per_cta, a.H);
-  const uint32_t row_bytes = (uint32_t)a.P * 64u, dy_bytes = 128u * 64u;
+  const uint32_t row_bytes = (uint32_t)a.P * 64u, dy_bytes = (uint32_t)a.Wt * 64u;
   unsigned char *rows = smem;                                          // x ring: S slots
   unsigned char *dyr = smem + (size_t)a.S * row_bytes;                 // dy ring: kTcDySlots slots + 1 pad slot
   uint64_t *bars = reinterpret_cast<uint64_t *>(dyr + (size_t)(kTcDySlots + 1) * dy_bytes);
@@ -424,7 +431,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
     }
   } else if (warp == 1) {
     {  // ===== MMA issuer (warp-uniform loop, elected lane issues; see the forward kernel)
-      const uint32_t hi_a = ((128u * 16u) >> 4) | (1u << 14);               // SBO = dy plane stride (128 px * 16 B)
+      const uint32_t hi_a = (((uint32_t)a.Wt * 16u) >> 4) | (1u << 14);     // SBO = dy plane stride (Wt px * 16 B)
+      const int kks = a.Wt >> 4;                                            // MMAs per row: 16 pixels each
       const uint32_t hi_b = (((uint32_t)a.P * 16u) >> 4) | (1u << 14);      // SBO = x plane stride
       const uint32_t lbo = (128u >> 4) << 16;                               // LBO = 8 pixels * 16 B
       const uint32_t a_base = ((smem_u32(dyr) >> 4) & 0x3FFF) | lbo, b_base = ((smem_u32(rows) >> 4) & 0x3FFF) | lbo;
@@ -447,8 +455,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
           const uint32_t blo0 = b_base + (((uint32_t)it + trow) & smask) * row16 + tcol;
           const uint32_t d = tmem_base + (uint32_t)t * 32u;
           if (leader) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)  // 16 pixels per MMA
+#pragma unroll 4
+            for (int kk = 0; kk < kks; ++kk)  // 16 pixels per MMA
               umma_bf16(d, ((uint64_t)hi_a << 32) | (alo0 + (uint32_t)kk * 16u), ((uint64_t)hi_b << 32) | (blo0 + (uint32_t)kk * 16u),
                         kTcIdescW, (it > 0 || kk > 0) ? 1u : 0u);
           }
@@ -527,10 +535,12 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
   PFN_tmapEncodeTiled enc = tc_encode_fn();
   if (!enc) return 2;
   const int span_x = a.taps.max_dx - a.taps.min_dx, span_y = a.taps.max_dy - a.taps.min_dy;
-  a.P = (kTcM + span_x + 1) & ~1;
+  a.M = tc_strip(a.W);
+  if (a.M == 0) return 1;
+  a.P = (a.M + span_x + 1) & ~1;
   a.S = 16;  // power of two (cheap slot arithmetic in the single-thread issue loop)
   if (span_y + 4 > a.S) return 1;
-  if (a.P > 256 || a.W % kTcM != 0) return 1;
+  if (a.P > 256) return 1;
   const size_t smem = tc_smem_bytes(a);
   if (smem > 220 * 1024) return 1;
   CUtensorMap tmap;
@@ -547,7 +557,7 @@ static int launch_conv_tc(const __nv_bfloat16 *xb, int B, TcConvArgs a, void *st
     if (cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
     attr_smem = smem;
   }
-  dim3 grid((a.W / kTcM) * a.row_chunks, B);
+  dim3 grid((a.W / a.M) * a.row_chunks, B);
   SENAS_LAUNCH(conv_tc_fwd_kernel, grid, dim3(kTcThreads), smem, stream, tmap, a);
   return 0;
 }
@@ -572,16 +582,18 @@ static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dy
   memset(&a, 0, sizeof(a));
   a.H = H, a.W = W, a.rows_per_cta = 32, a.row_chunks = (H + 31) / 32, a.taps = taps, a.partials = partials;
   a.dy_img_mul = dy_mul, a.dy_img_add = dy_add;
-  a.P = (kTcM + taps.max_dx - taps.min_dx + 1) & ~1, a.S = 16;
+  a.Wt = tc_strip(W);
+  if (a.Wt == 0) return 1;
+  a.P = (a.Wt + taps.max_dx - taps.min_dx + 1) & ~1, a.S = 16;
   const size_t smem = (size_t)a.S * a.P * 64 + (size_t)(kTcDySlots + 1) * 8192 + (size_t)(2 * a.S + 2 * kTcDySlots + 2) * 8 + 64;
   CUtensorMap mx, md;
-  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B * dy_mul, H, W, 128)) return 2;
+  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B * dy_mul, H, W, a.Wt)) return 2;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;
     attr_smem = smem;
   }
-  dim3 grid((W / kTcM) * a.row_chunks, B);
+  dim3 grid((W / a.Wt) * a.row_chunks, B);
   for (int tb = t0; tb < t1; tb += kTcWTaps) {
     a.t_begin = tb, a.t_count = std::min(kTcWTaps, t1 - tb);
     SENAS_TAG("conv_tc_wgrad", 2.0 * B * H * W * a.t_count * 32 * 8 * nterms, 4.0 * B * H * W * 32);

@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "kernels.cuh"
+// strip width (= MMA M) of the tcgen05 kernels for a map of width w: 128, else 64, else 0 (not on the tensor-core path)
+static int tc_strip(int w) { return w % 128 == 0 ? 128 : (w % 64 == 0 ? 64 : 0); }
 #include "conv_tc.cuh"
 
 #ifdef SENAS_EMU
@@ -231,13 +233,14 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     for (int e = 0; e < d.n_edges; ++e) {
       const senas_edge_desc_t &ed = d.edge[e];
       if (ed.src >= d.n_inputs || ed.c_in != 32 || ed.op_type == SENAS_OP_DOWN) continue;
-      if (p->edges[e].in_w % kTcM != 0) continue;
+      const int strip = tc_strip(p->edges[e].in_w);
+      if (strip == 0) continue;
       for (int k = 0; k < SENAS_MAX_CAND; ++k) {
         if (ed.kind[k] != SENAS_KIND_CONV && ed.kind[k] != SENAS_KIND_SE_CONV) continue;
         Geo geo = make_geo(ed.ksize[k], ed.dilation[k], ed.op_type, DIR_FWD);
         TcConvArgs probe;
         probe.taps = geo.taps;
-        probe.P = (kTcM + geo.taps.max_dx - geo.taps.min_dx + 1) & ~1;
+        probe.P = (strip + geo.taps.max_dx - geo.taps.min_dx + 1) & ~1;
         probe.S = 16;
         if (geo.taps.max_dy - geo.taps.min_dy + 4 > probe.S || probe.P > 256 || tc_smem_bytes(probe) > 220 * 1024) continue;
         TcGroup *grp = nullptr;
@@ -255,7 +258,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     }
     for (auto &g2 : p->tc_groups) {
       if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
-      tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / kTcM) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
+      tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / tc_strip(iw[g2.src])) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
     }
   }
 #endif
@@ -289,7 +292,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW * gather_pix(8, geo.si, bw));
-          if (t.tc) t.nblk = (ep.in_w / 128) * cdiv(ep.in_h, kTcRows);
+          if (t.tc) t.nblk = (ep.in_w / tc_strip(ep.in_w)) * cdiv(ep.in_h, kTcRows);
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
           break;

@@ -295,7 +295,8 @@ def bf16_mode():
     senas_b200.set_conv_mode('fp32')
 
 
-@pytest.mark.parametrize('op_id,B,H,W', [(3, 2, 24, 128), (1, 2, 10, 128), (3, 1, 40, 256)])
+@pytest.mark.parametrize('op_id,B,H,W', [(3, 2, 24, 128), (1, 2, 10, 128), (3, 1, 40, 256), (3, 2, 24, 64), (1, 2, 10, 64),
+                                          (3, 1, 9, 192)])
 def test_mixed_op_bf16_tensor_core(bf16_mode, op_id, B, H, W):
     torch.manual_seed(200 + op_id + H)
     m = senas_b200.MixedOp(32, 8, OP_BY_ID[op_id])
@@ -328,7 +329,7 @@ def l2_err(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize('representable,w0', [(True, 128), (False, 128), (True, 256)])
+@pytest.mark.parametrize('representable,w0', [(True, 128), (False, 128), (True, 256), (True, 64)])
 def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable, w0):
     """Up cell with in0 128 wide: the NORM edges 0/2/5 form 3-edge tcgen05 groups (forward, grouped data gradient,
     weight gradient with 24 real rows), the UP edges 1/3/6 (in1 64 wide) stay on the exact kernels.
@@ -349,7 +350,7 @@ def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable, w0):
         in0, in1 = in0.bfloat16().float(), in1.bfloat16().float()
         with torch.no_grad():
             convs = [(e, k) for e in (0, 2, 5) for k in (2, 3)]
-            if w0 == 256:
+            if w0 >= 128:  # in1 at least 64 wide: UP groups on tcgen05 (M = 64 strips when not a multiple of 128)
                 convs += [(e, k) for e in (1, 3, 6) for k in (1, 2, 3)]
             for e, k in convs:
                 w = c._ops[e]._ops[k][0].weight
