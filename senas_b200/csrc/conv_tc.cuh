@@ -580,7 +580,8 @@ static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dy
                                 int ws_ci, int ws_co, void *stream) {
   TcWgradArgs a;
   memset(&a, 0, sizeof(a));
-  a.H = H, a.W = W, a.rows_per_cta = 32, a.row_chunks = (H + 31) / 32, a.taps = taps, a.partials = partials;
+  a.H = H, a.W = W, a.rows_per_cta = tc_rows(H, W, B, taps.max_dy - taps.min_dy);
+  a.row_chunks = (H + a.rows_per_cta - 1) / a.rows_per_cta, a.taps = taps, a.partials = partials;
   a.dy_img_mul = dy_mul, a.dy_img_add = dy_add;
   a.Wt = tc_strip(W);
   if (a.Wt == 0) return 1;

@@ -16,6 +16,21 @@
 #include "kernels.cuh"
 // strip width (= MMA M) of the tcgen05 kernels for a map of width w: 128, else 64, else 0 (not on the tensor-core path)
 static int tc_strip(int w) { return w % 128 == 0 ? 128 : (w % 64 == 0 ? 64 : 0); }
+// rows of a strip per CTA of the tcgen05 kernels: a CTA loads (rows + span_y) input rows, the grid runs in waves of 148
+// CTAs -- pick the row count whose (waves x rows loaded per CTA) is smallest (at most 592 CTAs: one partial each).
+static int tc_rows(int H, int W, int B, int span_y) {
+  const int strips = W / tc_strip(W);
+  int best_rows = H, best_cost = 1 << 30;
+  for (int chunks = 1; chunks <= H; ++chunks) {
+    const int rows = (H + chunks - 1) / chunks;
+    if ((rows - 1) * chunks >= H) continue;  // same as a smaller chunk count
+    const int ctas = strips * chunks * B;
+    if (ctas > 592 && chunks > 1) break;
+    const int cost = ((ctas + 147) / 148) * (rows + span_y + 3);
+    if (cost < best_cost) best_cost = cost, best_rows = rows;
+  }
+  return best_rows;
+}
 #include "conv_tc.cuh"
 
 #ifdef SENAS_EMU
@@ -258,11 +273,10 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     }
     for (auto &g2 : p->tc_groups) {
       if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
-      tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * (iw[g2.src] / tc_strip(iw[g2.src])) * cdiv(ih[g2.src], 32) * kTcWTaps * 1024);
+      tmp_need = std::max<int64_t>(tmp_need, (int64_t)std::max(592, B * (iw[g2.src] / tc_strip(iw[g2.src]))) * kTcWTaps * 1024);
     }
   }
 #endif
-  const int kTcRows = 32;
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
     EdgePlan &ep = p->edges[e];
@@ -292,7 +306,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW * gather_pix(8, geo.si, bw));
-          if (t.tc) t.nblk = (ep.in_w / tc_strip(ep.in_w)) * cdiv(ep.in_h, kTcRows);
+          if (t.tc) t.nblk = (ep.in_w / tc_strip(ep.in_w)) * cdiv(ep.in_h, tc_rows(ep.in_h, ep.in_w, B, geo.taps.max_dy - geo.taps.min_dy));
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
           break;
@@ -843,7 +857,8 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ta.ws_k, &ta.ws_n);
     ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = p->out_h, ta.Wo = p->out_w, ta.so = geo.so;
-    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32), ta.taps = geo.taps;
+    ta.rows_per_cta = tc_rows(ep0.in_h, ep0.in_w, c.B, geo.taps.max_dy - geo.taps.min_dy);
+    ta.row_chunks = cdiv(ep0.in_h, ta.rows_per_cta), ta.taps = geo.taps;
     SENAS_TAG("conv_tc_fwd", 2.0 * c.B * ep0.in_h * ep0.in_w * geo.taps.n * 32 * 8 * g2.nterms,
               2.0 * c.B * ep0.in_h * ep0.in_w * 32 + 4.0 * c.B * p->hw * 8 * g2.nterms);
     const int rc = launch_conv_tc(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), c.B, ta,
@@ -1330,7 +1345,6 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);
     ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = ep0.in_h, ta.Wo = ep0.in_w, ta.so = 1;
-    ta.rows_per_cta = 32, ta.row_chunks = cdiv(ep0.in_h, 32);
     ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src];
     for (int ph = 0; ph < nph; ++ph) {
       if (up) {  // mirrored taps of this output phase, as a single-phase table on the input grid
@@ -1352,6 +1366,8 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       } else {
         ta.taps = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD).taps, ta.img_mul = 1, ta.img_add = 0;
       }
+      ta.rows_per_cta = tc_rows(ep0.in_h, ep0.in_w, c.B, ta.taps.max_dy - ta.taps.min_dy);
+      ta.row_chunks = cdiv(ep0.in_h, ta.rows_per_cta);
       ta.accumulate = c.touched[g2.src];
       SENAS_TAG("conv_tc_dgrad", 2.0 * npix * ta.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
       const int rc = launch_conv_tc(dyb, c.B, ta, c.S.stream(dxl));
