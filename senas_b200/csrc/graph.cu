@@ -292,12 +292,16 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           break;
         case SENAS_KIND_IDENTITY:
           t.has_y = true, t.owns_y = (C != 8);
-          t.nblk = nblk_px;
+          t.nblk = C == 32 ? cdiv(HW, kPwPx) : nblk_px;  // 32 channels: quad-layout 1x1 (pw_fwd_kernel<32, true>)
+          if (C == 32) tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(HW, kPwPx) * 8 * C);
           if (C != 8) tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(HW, 128 * kPxTilesPerBlock) * 8 * C);
           break;
         case SENAS_KIND_AVG_POOL:
         case SENAS_KIND_UP_SAMPLE:
           t.has_y = t.owns_y = true, t.nblk = nblk_px;
+          if (t.kind == SENAS_KIND_UP_SAMPLE && C == 32)  // low-resolution u / du (8 channels) + dW partials
+            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * ep.in_h * ep.in_w * 8 +
+                                                       (int64_t)B * cdiv(ep.in_h * ep.in_w, kPwPx) * 8 * C);
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(std::max(HW, ep.in_h * ep.in_w), 128 * kPxTilesPerBlock) * 8 * C);
           break;
         case SENAS_KIND_CONV:
@@ -699,20 +703,21 @@ static int forward_edge(Call &c, int e, bool second_pass) {
     if (t.kind == SENAS_KIND_NONE || (second_pass && t.kind != SENAS_KIND_DEPSEP) ||
         (!second_pass && t.tc && (t.kind == SENAS_KIND_CONV || t.kind == SENAS_KIND_SE_CONV)))
       continue;
-    void *st = c.S.stream(c.S.pick());  // candidates of a stage are independent: one lane each
+    const int ln = c.S.pick();  // candidates of a stage are independent: one lane each (with its tmp slice)
+    void *st = c.S.stream(ln);
     if (second_pass) {
       PwArgs a;
-      a.z = c.saved + t.z_off, a.hw = p.hw, a.y = y;
+      a.z = c.saved + t.z_off, a.z_ld = C, a.hw = p.hw, a.y = y;
       a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
       a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
       a.wpw = (const float *)ed.param[k][6], a.partials = part;
       dim3 grid(cdiv(p.hw, kPwPx), B);
       SENAS_TAG("pw_fwd", 2.0 * B * p.hw * C * 8, 4.0 * B * p.hw * (C + 8));
       if (C == 32) {
-        auto kern = pw_fwd_kernel<32>;
+        auto kern = pw_fwd_kernel<32, false>;
         SENAS_LAUNCH(kern, grid, dim3(256), 0, st, a);
       } else {
-        auto kern = pw_fwd_kernel<8>;
+        auto kern = pw_fwd_kernel<8, false>;
         SENAS_LAUNCH(kern, grid, dim3(256), 0, st, a);
       }
       continue;
@@ -727,6 +732,24 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.y = y, a.o_h = p.out_h, a.o_w = p.out_w;
         a.w = (const float *)ed.param[k][0], a.partials = part;
         if ((C != 8) != (a.w != nullptr)) SENAS_FAIL("edge %d candidate %d: 1x1 weight does not match c_in", e, k);
+        if (C == 32 && t.kind != SENAS_KIND_AVG_POOL) {  // quad-layout 1x1 on the input grid (+ 8-channel upsample)
+          const bool up = t.kind == SENAS_KIND_UP_SAMPLE;
+          const int in_px = ep.in_h * ep.in_w;
+          PwArgs pa;
+          memset(&pa, 0, sizeof(pa));
+          pa.z = x, pa.z_ld = x_ld, pa.hw = in_px, pa.wpw = a.w;
+          pa.y = up ? c.tmp(ln) : y, pa.partials = up ? nullptr : part;
+          SENAS_TAG("adapter_fwd", 2.0 * B * in_px * C * 8, 4.0 * B * (in_px * C + p.hw * 8));
+          auto kern = pw_fwd_kernel<32, true>;
+          SENAS_LAUNCH(kern, dim3(cdiv(in_px, kPwPx), B), dim3(256), 0, st, pa);
+          if (up) {
+            Up8Args ua;
+            ua.u = c.tmp(ln), ua.y = y, ua.h = ep.in_h, ua.w = ep.in_w, ua.partials = part;
+            SENAS_TAG("adapter_fwd", 0, 0);
+            SENAS_LAUNCH(up8_fwd_kernel, dim3(cdiv(p.hw, 128), B), dim3(128), 0, st, ua);
+          }
+          break;
+        }
         dim3 grid(cdiv(p.hw, 128), B);
 #define SENAS_AD_FWD(CC, KK)                                   \
   {                                                            \
@@ -949,6 +972,32 @@ static int backward_edge(BwdCall &c, int e) {
         a.partials = tmp;
         const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
         const int in_px = ep.in_h * ep.in_w;
+        if (C == 32 && kk != AD_POOL) {  // one quad-layout sweep over the input grid: dx += W^T.dy and dW partials
+          const bool up = kk == AD_UP, want_dw = ed.grad_off[k][0] >= 0;
+          float *du = tmp, *dwp = tmp + (up ? (int64_t)B * in_px * 8 : 0);
+          if (up) {
+            SENAS_TAG("adapter_dx", 0, 4.0 * B * HW * 16);
+            SENAS_LAUNCH(up8_bwd_kernel, dim3(cdiv(in_px, 128), B), dim3(128), 0, st, a, du);
+          }
+          LinBwdArgs la;
+          memset(&la, 0, sizeof(la));
+          la.x = x, la.x_ld = x_ld, la.gm = up ? du : gm, la.y = y, la.w = a.w, la.hw = in_px;
+          if (!up) la.coefA = cA, la.coefB = cB, la.coefC = cC;
+          la.dx = dx, la.dx_ld = dx_ld, la.accumulate = c.touched[ed.src], la.partials = want_dw ? dwp : nullptr;
+          const int nb = cdiv(in_px, kPwPx);
+          c.S.dep(ln, dxl);  // (du ready; also orders the use of this lane's tmp slice)
+          SENAS_TAG("adapter_dx", 4.0 * B * in_px * C * 8, 4.0 * B * (in_px * 3 * C + (up ? in_px : HW) * 16));
+          auto kern = lin_bwd_q_kernel<32>;
+          SENAS_LAUNCH(kern, dim3(nb, B), dim3(256), 0, sdx, la, kPwPx);
+          if (dx) c.touched[ed.src] = true;
+          c.S.dep(dxl, ln);
+          if (want_dw) {
+            SENAS_TAG("reduce", 0, 0);
+            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(8 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)dwp,
+                         gp + ed.grad_off[k][0], nb * B, 8 * C);
+          }
+          break;
+        }
         if (dx) {
           dim3 grid(cdiv(in_px, 128), B);
 #define SENAS_AD_DX(CC, KK)                                    \

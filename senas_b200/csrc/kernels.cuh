@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(128) dw_fwd_kernel(DwArgs a) {
 // pointwise half: y = W_pw . relu(BN1(z)), statistics of y.  thread = pixel.
 struct PwArgs {
   const float *z;
+  int64_t z_ld;  // floats between pixels of z (C for the dep-sep intermediate; the state's pixel stride for adapters)
   int32_t hw;
   float *y;  // [B][hw][8]
   const float *mean1, *istd1, *g1, *b1;
@@ -468,7 +469,8 @@ struct PwArgs {
 // leaves output channel l (C = 32) / channels 4l..4l+3 (C = 8) in lane l, so the y store is coalesced too.  (The
 // thread-per-pixel version read its own 128-byte line with 8 loads: 8 x the L1 wavefronts for the same bytes.)
 constexpr int kPwPx = 512;  // pixels per block
-template <int C>
+// PLAIN: no BN1 / ReLU in front (the 1x1 of an identity / up_sample AdapterBlock); partials may then be null (no statistics).
+template <int C, bool PLAIN>
 __global__ void __launch_bounds__(256) pw_fwd_kernel(PwArgs a) {
   constexpr int LP = C / 4, PPW = 32 / LP, NOUT = 8 / LP, UN = 4;
   __shared__ float s_red[8][16];
@@ -478,7 +480,8 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(PwArgs a) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = l * 4 + j;
-    sc[j] = a.g1[c] * a.istd1[c], sh[j] = a.b1[c] - a.mean1[c] * sc[j];
+    sc[j] = 1.f, sh[j] = 0.f;
+    if (!PLAIN) sc[j] = a.g1[c] * a.istd1[c], sh[j] = a.b1[c] - a.mean1[c] * sc[j];
 #pragma unroll
     for (int co = 0; co < 8; ++co) w[j][co] = __ldg(a.wpw + co * C + c);
   }
@@ -488,20 +491,23 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(PwArgs a) {
   const int p_begin = blockIdx.x * kPwPx, p_end = min(p_begin + kPwPx, a.hw);
   const int per_warp = kPwPx / 8;
   const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
-  const float *zn = a.z + (int64_t)n * a.hw * C + l * 4;
+  const float *zn = a.z + (int64_t)n * a.hw * a.z_ld + l * 4;
   float *yn = a.y + (int64_t)n * a.hw * 8;
   for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
     float4 zv[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int p = p0 + u * PPW + sub;
-      zv[u] = p < w_end ? ld4(zn + (int64_t)p * C) : f4zero();
+      zv[u] = p < w_end ? ld4(zn + (int64_t)p * a.z_ld) : f4zero();
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int p = p0 + u * PPW + sub;
-      const float r[4] = {fmaxf(fmaf(zv[u].x, sc[0], sh[0]), 0.f), fmaxf(fmaf(zv[u].y, sc[1], sh[1]), 0.f),
-                          fmaxf(fmaf(zv[u].z, sc[2], sh[2]), 0.f), fmaxf(fmaf(zv[u].w, sc[3], sh[3]), 0.f)};
+      float r[4] = {zv[u].x, zv[u].y, zv[u].z, zv[u].w};
+      if (!PLAIN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = fmaxf(fmaf(r[j], sc[j], sh[j]), 0.f);
+      }
       float v[8];
 #pragma unroll
       for (int co = 0; co < 8; ++co) v[co] = r[0] * w[0][co];
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(PwArgs a) {
     for (int j = 0; j < NOUT; ++j) s_red[warp][l * NOUT + j] = ssum[j], s_red[warp][8 + l * NOUT + j] = ssq[j];
   }
   __syncthreads();
-  if (tid < 16) {
+  if (tid < 16 && a.partials != nullptr) {
     float r = 0.f;
     for (int wv = 0; wv < 8; ++wv) r += s_red[wv][tid];
     a.partials[((int64_t)n * gridDim.x + blockIdx.x) * 16 + tid] = r;
@@ -2169,6 +2175,170 @@ __global__ void __launch_bounds__(256, 2) pw_bwd_q_kernel(PwBwdArgs a, int px_pe
     __syncthreads();
     float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 10 * C;
     for (int o = tid; o < 10 * C; o += 256) {
+      float r = 0.f;
+      for (int wv = 0; wv < 8; ++wv) r += s_part[wv][o];
+      out[o] = r;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// AdapterBlock with a 1x1 conv on 32 channels (identity on NORM edges, up_sample on UP edges), quad layout.
+// up_sample: the 1x1 conv commutes with the bilinear interpolation (both linear), so the conv runs on the LOW-resolution
+// grid (u = W.x, pw_fwd_kernel<C, true>) and only 8 channels are interpolated (up8_fwd_kernel: y, statistics); backward
+// mirrors it: du = bilinear^T(dy) once (up8_bwd_kernel), then dx += W^T.du and dW = sum du (x) x in ONE sweep over the
+// low-resolution grid (lin_bwd_q_kernel) -- the first version gathered the 4x4 dy window twice per input pixel.
+// ------------------------------------------------------------------------------------------------
+struct Up8Args {
+  const float *u;  // [B][h][w][8] low resolution
+  float *y;        // [B][2h][2w][8]
+  int32_t h, w;
+  float *partials;  // [B][gridDim.x][16]
+};
+__global__ void __launch_bounds__(128) up8_fwd_kernel(Up8Args a) {
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x, oh = 2 * a.h, ow = 2 * a.w;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (p < oh * ow) {
+    const int oy = p / ow, ox = p - oy * ow;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up_src(oy, a.h, y0, y1, ly);
+    up_src(ox, a.w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float *un = a.u + (int64_t)n * a.h * a.w * 8;
+    const float *p00 = un + ((int64_t)y0 * a.w + x0) * 8, *p01 = un + ((int64_t)y0 * a.w + x1) * 8;
+    const float *p10 = un + ((int64_t)y1 * a.w + x0) * 8, *p11 = un + ((int64_t)y1 * a.w + x1) * 8;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c += 4) {
+      const float4 q0 = ld4(p00 + c), q1 = ld4(p01 + c), q2 = ld4(p10 + c), q3 = ld4(p11 + c);
+      acc[c] = w00 * q0.x + w01 * q1.x + w10 * q2.x + w11 * q3.x;
+      acc[c + 1] = w00 * q0.y + w01 * q1.y + w10 * q2.y + w11 * q3.y;
+      acc[c + 2] = w00 * q0.z + w01 * q1.z + w10 * q2.z + w11 * q3.z;
+      acc[c + 3] = w00 * q0.w + w01 * q1.w + w10 * q2.w + w11 * q3.w;
+    }
+    float *yp = a.y + ((int64_t)n * oh * ow + p) * 8;
+    st4(yp, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(yp + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j], v[8 + j] = acc[j] * acc[j];
+  }
+  block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+}
+
+// du[B][x_h][x_w][8] = bilinear^T(dy), dy = A*gm + B*y + C on the output grid.  thread = low-resolution pixel.
+__global__ void __launch_bounds__(128) up8_bwd_kernel(AdapterBwdArgs a, float *du) {
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= a.x_h * a.x_w) return;
+  const int iy = p / a.x_w, ix = p - iy * a.x_w;
+  float s[8];
+  adapter_gather_dy<AD_UP>(a, n, iy, ix, s);
+  float *o = du + ((int64_t)n * a.x_h * a.x_w + p) * 8;
+  st4(o, make_float4(s[0], s[1], s[2], s[3]));
+  st4(o + 4, make_float4(s[4], s[5], s[6], s[7]));
+}
+
+struct LinBwdArgs {
+  const float *x;  // [B][hw][x_ld]
+  int64_t x_ld;
+  const float *gm, *y;  // affine: dy = A*gm + B*y + C (gm, y: [B][hw][8]);  plain (coefA == null): dy = gm
+  const float *coefA, *coefB, *coefC;
+  const float *w;  // [8][C]
+  float *dx;       // [B][hw][dx_ld], (+)=; null to skip
+  int64_t dx_ld;
+  int32_t accumulate, hw;
+  float *partials;  // [B][gridDim.x][8C] (co-major), null to skip the weight gradient
+};
+template <int C>
+__global__ void __launch_bounds__(256, 2) lin_bwd_q_kernel(LinBwdArgs a, int px_per_block) {
+  constexpr int LP = C / 4, PPW = 32 / LP, NDY = 8 / LP, UN = 2;
+  __shared__ float s_part[8][8 * C];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+  const int l = lane % LP, sub = lane / LP;
+  const bool affine = a.coefA != nullptr;
+  float wq[8][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int co = 0; co < 8; ++co) wq[co][j] = __ldg(a.w + co * C + l * 4 + j);
+  float cA[NDY], cB[NDY], cC[NDY];
+#pragma unroll
+  for (int j = 0; j < NDY; ++j) {
+    const int co = l * NDY + j;
+    cA[j] = affine ? a.coefA[n * 8 + co] : 1.f, cB[j] = affine ? a.coefB[n * 8 + co] : 0.f;
+    cC[j] = affine ? a.coefC[n * 8 + co] : 0.f;
+  }
+  float dw[8][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int co = 0; co < 8; ++co) dw[co][j] = 0.f;
+  const int p_begin = blockIdx.x * px_per_block, p_end = min(p_begin + px_per_block, a.hw);
+  const int per_warp = (px_per_block + 7) / 8;
+  const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
+  const float *xn = a.x + (int64_t)n * a.hw * a.x_ld + l * 4;
+  const float *gn = a.gm + (int64_t)n * a.hw * 8 + l * NDY;
+  const float *yn = affine ? a.y + (int64_t)n * a.hw * 8 + l * NDY : gn;
+  float *dxn = a.dx ? a.dx + (int64_t)n * a.hw * a.dx_ld + l * 4 : nullptr;
+  for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
+    float4 xv[UN], ov[UN];
+    float dyl[UN][NDY];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      const bool ok = p < w_end;
+      const int pp = ok ? p : w_begin;
+      xv[u] = ld4(xn + (int64_t)pp * a.x_ld);
+      ov[u] = (dxn && a.accumulate) ? ld4(dxn + (int64_t)pp * a.dx_ld) : f4zero();
+      if (NDY == 4) {
+        const float4 g4 = ld4(gn + (int64_t)pp * 8), y4 = affine ? ld4(yn + (int64_t)pp * 8) : f4zero();
+        dyl[u][0] = cA[0] * g4.x + cB[0] * y4.x + cC[0];
+        dyl[u][1 % NDY] = cA[1 % NDY] * g4.y + cB[1 % NDY] * y4.y + cC[1 % NDY];
+        dyl[u][2 % NDY] = cA[2 % NDY] * g4.z + cB[2 % NDY] * y4.z + cC[2 % NDY];
+        dyl[u][3 % NDY] = cA[3 % NDY] * g4.w + cB[3 % NDY] * y4.w + cC[3 % NDY];
+      } else {
+        dyl[u][0] = cA[0] * gn[(int64_t)pp * 8] + (affine ? cB[0] * yn[(int64_t)pp * 8] : 0.f) + cC[0];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int p = p0 + u * PPW + sub;
+      const bool ok = p < w_end;
+      float dy[8];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) dy[co] = __shfl_sync(0xffffffffu, dyl[u][co % NDY], sub * LP + co / NDY);
+      const float xx[4] = {ok ? xv[u].x : 0.f, ok ? xv[u].y : 0.f, ok ? xv[u].z : 0.f, ok ? xv[u].w : 0.f};
+      float dr[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+          dr[j] = fmaf(dy[co], wq[co][j], dr[j]);
+          dw[co][j] = fmaf(dy[co], xx[j], dw[co][j]);
+        }
+      }
+      if (dxn && ok) st4(dxn + (int64_t)p * a.dx_ld, make_float4(dr[0], dr[1], dr[2], dr[3]));
+    }
+  }
+  if (a.partials != nullptr) {
+#pragma unroll
+    for (int m = LP; m < 32; m <<= 1)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int co = 0; co < 8; ++co) dw[co][j] += __shfl_xor_sync(0xffffffffu, dw[co][j], m);
+    if (lane < LP) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int co = 0; co < 8; ++co) s_part[warp][co * C + l * 4 + j] = dw[co][j];
+    }
+    __syncthreads();
+    float *out = a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 8 * C;
+    for (int o = tid; o < 8 * C; o += 256) {
       float r = 0.f;
       for (int wv = 0; wv < 8; ++wv) r += s_part[wv][o];
       out[o] = r;
