@@ -321,6 +321,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
           if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false);  // dw_multi_kernel grid
+          if (ed.op_type == SENAS_OP_UP) t.nblk1 = dw_nblk(C, B, bh, bw, true);     // dw_up_multi_kernel grid (input grid)
           t.nblk = cdiv(HW, kPwPx);  // pw_fwd_kernel grid
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -328,7 +329,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int64_t pw_tmp = (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
           const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
-          if (ed.op_type == SENAS_OP_NORM)  // grouped weight gradient: one partial per block and convolution
+          if (ed.op_type != SENAS_OP_DOWN)  // grouped weight gradient: one partial per block and convolution
             tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * dw_nblk(C, B, bh, bw, true) * kDwMaxItems * C * 25);
           break;
         }
@@ -657,11 +658,13 @@ static int forward_dw_group(Call &c, int src) {
   DwMultiArgs a;
   memset(&a, 0, sizeof(a));
   int C = 0, h = 0, w = 0, nblk = 0;
+  bool up = false;  // every edge that reads a state has the same op type (cell.py:76-90)
   int64_t x_ld = 0;
   const float *x = state_ptr(c, src, &x_ld);
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || ed.op_type != SENAS_OP_NORM) continue;
+    if (ed.src != src || ed.op_type == SENAS_OP_DOWN) continue;
+    up = ed.op_type == SENAS_OP_UP;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
       if (t.kind != SENAS_KIND_DEPSEP) continue;
@@ -673,13 +676,17 @@ static int forward_dw_group(Call &c, int src) {
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, false), a.tile_rows = dw_rows(C, c.B, h, w, false);
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, up), a.tile_rows = dw_rows(C, c.B, h, w, up);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   void *st = c.S.stream(c.S.pick());
-  SENAS_TAG("dw_fwd", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + a.n));
+  SENAS_TAG("dw_fwd", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + a.n * (up ? 4 : 1)));
   dim3 grid(nblk, c.B);
-  if (C == 32) {
+  if (up) {
+    if (C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
+    auto kern = dw_up_multi_kernel<32, 0>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  } else if (C == 32) {
     auto kern = dw_multi_kernel<32, true>;
     SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
   } else {
@@ -785,7 +792,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         break;
       }
       case SENAS_KIND_DEPSEP: {
-        if (ed.op_type == SENAS_OP_NORM) break;  // forward_dw_group
+        if (ed.op_type != SENAS_OP_DOWN) break;  // forward_dw_group
         Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
         DwArgs a;
         a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.z = c.saved + t.z_off;
@@ -1130,7 +1137,7 @@ static int backward_edge(BwdCall &c, int e) {
           auto kern = pw_bwd_q_kernel<8, 2>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
-        if (ed.op_type == SENAS_OP_NORM) {  // data / weight gradient of the depthwise half: backward_dw_group
+        if (ed.op_type != SENAS_OP_DOWN) {  // data / weight gradient of the depthwise half: backward_dw_group
           c.dw_wait[ed.src].push_back(ln);
           break;
         }
@@ -1229,12 +1236,14 @@ static int backward_dw_group(BwdCall &c, int src) {
   DwMultiArgs a;
   memset(&a, 0, sizeof(a));
   int C = 0, h = 0, w = 0, nblk = 0;
+  bool up = false;
   int64_t x_ld = 0;
   const float *x = state_ptr(c, src, &x_ld);
   int64_t goff[kDwMaxItems];
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || ed.op_type != SENAS_OP_NORM) continue;
+    if (ed.src != src || ed.op_type == SENAS_OP_DOWN) continue;
+    up = ed.op_type == SENAS_OP_UP;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
       if (t.kind != SENAS_KIND_DEPSEP) continue;
@@ -1242,15 +1251,16 @@ static int backward_dw_group(BwdCall &c, int src) {
       goff[a.n] = ed.grad_off[k][0];
       DwItem &it = a.it[a.n++];
       it.in = c.saved + t.z_off, it.in_ld = ed.c_in;  // dz (in place over z)
-      it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = 1;
+      it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = up ? 0 : 1;
       C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk1;
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, false), a.tile_rows = dw_rows(C, c.B, h, w, false);
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, up), a.tile_rows = dw_rows(C, c.B, h, w, up);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   dim3 grid(nblk, c.B);
+  if (up && C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
   float *dx = c.dstate[src];
   const int dxl = c.S.dx_lane(src), ln = c.S.pick();
   for (int l : c.dw_wait[src]) c.S.dep(l, dxl), c.S.dep(l, ln);
@@ -1259,8 +1269,11 @@ static int backward_dw_group(BwdCall &c, int src) {
     DwMultiArgs g = a;
     for (int m = 0; m < g.n; ++m)
       g.it[m].out = dx, g.it[m].out_ld = c.dstate_ld[src], g.it[m].accumulate = (m > 0 || c.touched[src]) ? 1 : 0;
-    SENAS_TAG("dw_dx", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n));
-    if (C == 32) {
+    SENAS_TAG("dw_dx", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
+    if (up) {
+      auto kern = dw_up_multi_kernel<32, 1>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    } else if (C == 32) {
       auto kern = dw_multi_kernel<32, false>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
     } else {
@@ -1279,8 +1292,11 @@ static int backward_dw_group(BwdCall &c, int src) {
     const int64_t per = (int64_t)c.B * nblk * C * 25;
     for (int m = 0; m < g.n; ++m)
       g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld, g.it[m].flip = 0, g.it[m].partials = tmp + m * per;
-    SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n));
-    if (C == 32) {
+    SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
+    if (up) {
+      auto kern = dw_up_wgrad_multi_kernel<32>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
+    } else if (C == 32) {
       auto kern = dw_wgrad_multi_kernel<32>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
     } else {

@@ -2345,3 +2345,193 @@ __global__ void __launch_bounds__(256, 2) lin_bwd_q_kernel(LinBwdArgs a, int px_
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise transposed convolution (UP edges: ConvTranspose2d k, stride 2, pad k/2, output_padding 1, groups = C),
+// several convolutions of ONE input per launch, on the input grid.  Per axis kernel index kk reaches output parity
+// p(kk) = (P + kk) & 1 from input offset d(kk) = (p + P - kk) / 2, i.e. output o = 2 i + kk - P:
+//   forward : z[2i + py(ky)][2j + px(kx)] += x[i + d(ky)][j + d(kx)] * w[ky][kx]     (4 output pixels per input pixel)
+//   dx      : dx[i][j] (+)= sum_{ky,kx} dz[2i + ky - P][2j + kx - P] * w[ky][kx]     (stride-2 gather)
+//   dW      : dW[ky][kx] = sum_{i,j} x[i + d(ky)][j + d(kx)] * dz[2i + py(ky)][2j + px(kx)]
+// thread = (channel quad, input column); same tiling, smem weight layout and item list as dw_multi_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+SENAS_DEVFN constexpr int up_par(int kk) { return (K / 2 + kk) & 1; }
+template <int K>
+SENAS_DEVFN constexpr int up_off(int kk) { return (up_par<K>(kk) + K / 2 - kk) / 2; }  // in {-1, 0, 1}
+
+// x window rows i-1, i, i+1 and columns j-1, j, j+1 (zero outside the image) -> xw[3][3]
+SENAS_DEVFN void up_load_window(const float *inb, int64_t in_ld, int H, int W, int i, int j, float4 (&xw)[3][3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = i + r - 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int ix = j + c - 1;
+      xw[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ld4(inb + ((int64_t)iy * W + ix) * in_ld) : f4zero();
+    }
+  }
+}
+
+template <int C, int K, bool STATS>
+SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q,
+                                float *st) {
+  const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
+  float *outb = it.out + (int64_t)n * 4 * H * W * C + q * 4;  // z: [2H][2W][C]
+  const float *wq = s_w + q * 4;
+  for (int i = by0; i < by1; ++i) {
+    float4 xw[3][3];
+    up_load_window(inb, it.in_ld, H, W, i, j, xw);
+    float4 acc[2][2];
+    acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = f4zero();
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx)
+        fma4(acc[up_par<K>(ky)][up_par<K>(kx)], xw[up_off<K>(ky) + 1][up_off<K>(kx) + 1], ld4(wq + (ky * K + kx) * C));
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const float4 v = acc[py][px];
+        st4(outb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * C, v);
+        if (STATS) {
+          st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
+          st[4] += v.x * v.x, st[5] += v.y * v.y, st[6] += v.z * v.z, st[7] += v.w * v.w;
+        }
+      }
+  }
+}
+
+template <int C, int K>
+SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q) {
+  constexpr int P = K / 2;
+  const float *dzb = it.in + (int64_t)n * 4 * H * W * C + q * 4;  // dz: [2H][2W][C]
+  float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
+  const float *wq = s_w + q * 4;
+  const int OH = 2 * H, OW = 2 * W;
+  for (int i = by0; i < by1; ++i) {
+    float *op = outb + ((int64_t)i * W + j) * it.out_ld;
+    float4 acc = it.accumulate ? ld4(op) : f4zero();
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int oy = 2 * i + ky - P;
+      if (oy < 0 || oy >= OH) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ox = 2 * j + kx - P;
+        if (ox < 0 || ox >= OW) continue;
+        fma4(acc, ld4(dzb + ((int64_t)oy * OW + ox) * C), ld4(wq + (ky * K + kx) * C));
+      }
+    }
+    st4(op, acc);
+  }
+}
+
+// MODE 0: forward with statistics, 1: data gradient.  grid = (tiles_x * tiles_y, B), block = 128 = Q quads x 128/Q columns
+template <int C, int MODE>
+__global__ void __launch_bounds__(128) dw_up_multi_kernel(DwMultiArgs a) {
+  constexpr int Q = C / 4, SLOTS = 128 / Q;
+  __shared__ float s_red[MODE == 0 ? 128 : 1][8];
+  __shared__ float4 s_w4[25 * C / 4];
+  float *s_w = reinterpret_cast<float *>(s_w4);
+  const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+  const int j = tx * SLOTS + slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
+  const bool active = j < a.W;
+  for (int m = 0; m < a.n; ++m) {
+    const DwItem &it = a.it[m];
+    const int T = it.k * it.k;
+    __syncthreads();
+    for (int i = tid; i < T * C; i += 128) {
+      const int c = i % C, t = i / C;
+      s_w[i] = __ldg(it.w + c * T + t);
+    }
+    __syncthreads();
+    float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      if (MODE == 0) {
+        if (it.k == 5) dw_up_fwd_rows<C, 5, true>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
+        else dw_up_fwd_rows<C, 3, true>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
+      } else {
+        if (it.k == 5) dw_up_dx_rows<C, 5>(it, s_w, n, a.H, a.W, by0, by1, j, q);
+        else dw_up_dx_rows<C, 3>(it, s_w, n, a.H, a.W, by0, by1, j, q);
+      }
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) s_red[tid][jj] = st[jj];
+      __syncthreads();
+      if (tid < 2 * C) {
+        const int c = tid % C, which = tid / C;
+        float r = 0.f;
+        for (int s = 0; s < SLOTS; ++s) r += s_red[s * Q + c / 4][which * 4 + (c & 3)];
+        it.partials[((int64_t)n * gridDim.x + blockIdx.x) * 2 * C + tid] = r;
+      }
+    }
+  }
+}
+
+// weight gradient of the same group; partial layout [C][K*K] per block like dw_wgrad_multi_kernel
+template <int C, int K>
+SENAS_DEVFN void dw_up_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int j, int q, bool active,
+                                  float *s_part, int nblk_idx) {
+  constexpr int T = K * K, Q = C / 4;
+  float4 acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = f4zero();
+  if (active) {
+    const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
+    const float *dzb = it.in2 + (int64_t)n * 4 * H * W * C + q * 4;
+    for (int i = by0; i < by1; ++i) {
+      float4 xw[3][3], dz[2][2];
+      up_load_window(inb, it.in_ld, H, W, i, j, xw);
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) dz[py][px] = ld4(dzb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * C);
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+          fma4(acc[ky * K + kx], xw[up_off<K>(ky) + 1][up_off<K>(kx) + 1], dz[up_par<K>(ky)][up_par<K>(kx)]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int m = Q; m < 32; m <<= 1) {
+      acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, m), acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, m);
+      acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, m), acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, m);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane < Q) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float *o = s_part + warp * (C * 25) + (lane * 4) * T + t;
+      o[0] = acc[t].x, o[T] = acc[t].y, o[2 * T] = acc[t].z, o[3 * T] = acc[t].w;
+    }
+  }
+  __syncthreads();
+  float *out = it.partials + (int64_t)nblk_idx * C * T;
+  for (int o = threadIdx.x; o < C * T; o += 128)
+    out[o] = (s_part[o] + s_part[C * 25 + o]) + (s_part[2 * C * 25 + o] + s_part[3 * C * 25 + o]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(128) dw_up_wgrad_multi_kernel(DwMultiArgs a) {
+  constexpr int Q = C / 4, SLOTS = 128 / Q;
+  __shared__ float s_part[4 * C * 25];
+  const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+  const int j = tx * SLOTS + slot, by0 = ty * a.tile_rows, by1 = min(by0 + a.tile_rows, a.H);
+  const bool active = j < a.W;
+  const int nblk_idx = n * gridDim.x + blockIdx.x;
+  for (int m = 0; m < a.n; ++m) {
+    const DwItem &it = a.it[m];
+    if (it.k == 5) dw_up_wgrad_rows<C, 5>(it, n, a.H, a.W, by0, by1, j, q, active, s_part, nblk_idx);
+    else dw_up_wgrad_rows<C, 3>(it, n, a.H, a.W, by0, by1, j, q, active, s_part, nblk_idx);
+  }
+}
