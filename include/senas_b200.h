@@ -148,6 +148,10 @@ int64_t senas_launch_count(void);
  * events on the caller's stream; a captured step becomes a DAG).  0 = strictly serial on the caller's stream,
  * negative = default (environment variable SENAS_LANES, else 8).  Results are bit-identical for every setting. */
 int senas_set_lanes(int n);
+/* lane set used by the following calls of this process (default 0).  A host that runs independent graphs concurrently
+ * on different streams gives each stream its own slot (and its own scratch buffer) so that their lanes do not
+ * serialise against each other; one host thread drives the library, so the selection is process-global. */
+int senas_set_slot(int slot);
 /* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
  * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
  * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */

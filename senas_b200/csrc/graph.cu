@@ -479,22 +479,27 @@ static const int kPersistBlocks = 148 * 6;
 static int g_lanes = -1;                          // -1: read SENAS_LANES on first use (default kLanes); 0: serial
 
 #ifndef SENAS_EMU
-constexpr int kEventPool = 4096;
+constexpr int kEventPool = 2048;
 struct LaneSet {
   cudaStream_t s[kAllLanes];
   cudaEvent_t ev[kEventPool];
   int next_ev = 0;
 };
-static LaneSet *lanes_for_current_device() {
-  static std::map<int, LaneSet *> sets;
+// one lane set per (device, slot): cells that the host runs concurrently on different streams (independent cells of one
+// level of the UNet++ triangle, senas_b200/supernet.py) select different slots (senas_set_slot) so that they do not
+// queue behind each other on shared lanes.  Slots, not stream handles, so that warm-up and capture share the sets.
+static int g_slot = 0;
+static LaneSet *lanes_for(int slot) {
+  static std::map<std::pair<int, int>, LaneSet *> sets;
   int dev = 0;
   cudaGetDevice(&dev);
-  auto it = sets.find(dev);
+  const auto key = std::make_pair(dev, slot);
+  auto it = sets.find(key);
   if (it != sets.end()) return it->second;
   LaneSet *ls = new LaneSet();
   for (int i = 0; i < kAllLanes; ++i) cudaStreamCreateWithFlags(&ls->s[i], cudaStreamNonBlocking);
   for (int i = 0; i < kEventPool; ++i) cudaEventCreateWithFlags(&ls->ev[i], cudaEventDisableTiming);
-  sets[dev] = ls;
+  sets[key] = ls;
   return ls;
 }
 #endif
@@ -514,7 +519,7 @@ struct Sched {
       g_lanes = e ? std::max(0, std::min(kLanes, atoi(e))) : kLanes;
     }
     n = g_prof_on ? 0 : g_lanes;  // per-kernel timing wants serial launches
-    if (n > 0) ls = lanes_for_current_device();
+    if (n > 0) ls = lanes_for(g_slot);
 #endif
   }
   void *stream(int lane) const {
@@ -1472,6 +1477,14 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
 extern "C" const char *senas_version(void) { return "senas_b200 0.1 (sm_100a, fp32 exact path)"; }
 extern "C" const char *senas_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t senas_launch_count(void) { return g_launch_count; }
+extern "C" int senas_set_slot(int slot) {
+#ifndef SENAS_EMU
+  g_slot = slot < 0 ? 0 : slot;
+#else
+  (void)slot;
+#endif
+  return 0;
+}
 extern "C" int senas_set_lanes(int n) {
   g_lanes = n < 0 ? -1 : std::min(n, kLanes);
   return 0;

@@ -76,12 +76,25 @@ def get_conv_mode():
     return 'bf16' if _flags['tc_bf16'] else 'fp32'
 
 
-def scratch_for(device, nbytes):
-    """One grow-only scratch buffer per device, shared by every graph on the stream."""
-    buf = _scratch.get(device)
+_slot = [0]
+
+
+def set_slot(slot):
+    """Select the lane set / scratch buffer of the following fused calls (see ``senas_set_slot``): a host that runs
+    independent cells concurrently on different CUDA streams gives every stream its own slot."""
+    _slot[0] = int(slot)
+
+
+def get_slot():
+    return _slot[0]
+
+
+def scratch_for(device, nbytes, slot=0):
+    """One grow-only scratch buffer per (device, slot), shared by every graph that runs in that slot."""
+    buf = _scratch.get((device, slot))
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-        _scratch[device] = buf
+        _scratch[(device, slot)] = buf
     return buf
 
 
@@ -165,14 +178,14 @@ class GraphRunner:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
 
-    def forward(self, ins, alpha, beta, training):
+    def forward(self, ins, alpha, beta, training, slot=0):
         B = ins[0].shape[0]
         hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
         info = self.plan(B, hs, ws)
         out = torch.empty((B, 8 * self.n_nodes, info.out_h, info.out_w), dtype=torch.float32, device=self.device,
                           memory_format=torch.channels_last)
         saved = torch.empty(info.saved_bytes, dtype=torch.uint8, device=self.device)
-        scratch = scratch_for(self.device, info.scratch_bytes)
+        scratch = scratch_for(self.device, info.scratch_bytes, slot)
         a = _lib.FwdArgs()
         a.batch, a.training = B, int(training)
         for i, t in enumerate(ins):
@@ -180,14 +193,15 @@ class GraphRunner:
         a.alpha, a.beta = alpha.data_ptr(), (beta.data_ptr() if beta is not None else None)
         a.out, a.out_ld = out.data_ptr(), out.shape[1]
         a.saved, a.scratch, a.stream = saved.data_ptr(), scratch.data_ptr(), self._stream()
+        self.lib.senas_set_slot(slot)
         _lib.check(self.lib, self.lib.senas_graph_forward(self.handle, C.byref(a)))
         return out, saved
 
-    def backward(self, ins, alpha, beta, out, grad_out, saved, training, need_in):
+    def backward(self, ins, alpha, beta, out, grad_out, saved, training, need_in, slot=0):
         B = ins[0].shape[0]
         hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
         info = self.plan(B, hs, ws)
-        scratch = scratch_for(self.device, info.scratch_bytes)
+        scratch = scratch_for(self.device, info.scratch_bytes, slot)
         n_edges = len(self.edges)
         g_alpha = torch.empty((n_edges, 6), dtype=torch.float32, device=self.device)
         g_beta = torch.empty((n_edges,), dtype=torch.float32, device=self.device) if beta is not None else None
@@ -207,6 +221,7 @@ class GraphRunner:
         a.grad_alpha = g_alpha.data_ptr()
         a.grad_beta = g_beta.data_ptr() if g_beta is not None else None
         a.grad_params, a.stream = g_params.data_ptr(), self._stream()
+        self.lib.senas_set_slot(slot)
         _lib.check(self.lib, self.lib.senas_graph_backward(self.handle, C.byref(a)))
         return g_ins, g_alpha, g_beta, g_params
 
@@ -221,7 +236,7 @@ class GraphRunner:
                                         any(p.requires_grad for p in self.params)):
             in1 = ins[1] if len(ins) > 1 else None
             return _GraphFn.apply(self, training, alpha, beta, ins[0], in1, *self.params)
-        out, _ = self.forward(ins, alpha, beta, training)
+        out, _ = self.forward(ins, alpha, beta, training, _slot[0])
         return out
 
 
@@ -229,7 +244,8 @@ class _GraphFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, training, alpha, beta, in0, in1, *params):
         ins = [in0] if in1 is None else [in0, in1]
-        out, saved = runner.forward(ins, alpha, beta, training)
+        ctx.slot = _slot[0]  # backward runs on the same stream (autograd) and must use the same lane set / scratch
+        out, saved = runner.forward(ins, alpha, beta, training, ctx.slot)
         ctx.runner, ctx.training, ctx.saved_buf, ctx.has_in1 = runner, training, saved, in1 is not None
         ctx.has_beta = beta is not None
         ctx.save_for_backward(alpha, beta, in0, in1, out)
@@ -244,7 +260,7 @@ class _GraphFn(torch.autograd.Function):
         ins = [in0] if in1 is None else [in0, in1]
         need_in = [ctx.needs_input_grad[4]] + ([ctx.needs_input_grad[5]] if in1 is not None else [])
         g_ins, g_alpha, g_beta, g_params = runner.backward(ins, alpha, beta, out, _nhwc(grad_out.float()),
-                                                           ctx.saved_buf, ctx.training, need_in)
+                                                           ctx.saved_buf, ctx.training, need_in, ctx.slot)
         ctx.saved_buf = None  # the library overwrote parts of it (dz in place of z)
         if _grad_sink[0] is not None:
             _grad_sink[0](runner, g_params)

@@ -32,8 +32,13 @@ class GraphedSearchStep:
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
-                 force_segments=False, capture_error_mode='global'):
+                 force_segments=False, capture_error_mode='global', concurrent_cells=True):
         self.static = [t.clone() for t in example]
+        # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
+        # small latency-bound cells with the large one of the level (senas_b200/supernet.py)
+        net = getattr(model, 'net', None)
+        if net is not None and hasattr(net, 'concurrent_cells'):
+            net.concurrent_cells = bool(concurrent_cells)
         self.model, self.criterion, self.w_opt, self.a_opt = model, criterion, w_opt, a_opt
         self.grad_clip, self.group = grad_clip, group
         self.world = dist.get_world_size(group) if group is not None else 1

@@ -61,27 +61,69 @@ class SenasSearch(nn.Module):
             self.blocks.append(row)
         self.head_block = nn.ModuleList([Head(meta_node_num, dd, c, widths[-1][0], nclass)])
 
+    # ``concurrent_cells``: the up cells (i, j) of one level i of the nested triangle depend only on level i - 1, so
+    # they are independent of each other; when set (GraphedSearchStep does), every level runs its cells on separate
+    # CUDA streams (cell j = 0, the largest, on the caller's stream), each with its own lane set / scratch slot, so that
+    # the small latency-bound cells hide under the large one in the captured graph.  Same operations on the same data:
+    # results do not depend on the setting.
+    concurrent_cells = False
+
+    def _cell_stream(self, j, device):
+        pool = self.__dict__.setdefault('_cell_streams', {})
+        key = (str(device), j)
+        if key not in pool:
+            pool[key] = torch.cuda.Stream(device=device)
+        return pool[key]
+
     def forward(self, x, alpha_dn_nm, alpha_up_nm, alpha_dn, alpha_up, beta_dn, beta_up, gamma):
+        from . import fused
         if x.dim() == 4:
             x = x.contiguous(memory_format=torch.channels_last)
+        depth = self._depth
         s0 = self.stem0(x)
-        cell_out = [self.stem1(s0)]
-        for j in range(1, self._depth):
-            prev = s0 if j == 1 else cell_out[-2]
-            cell_out.append(self.blocks[0][j](prev, cell_out[-1], alpha_dn_nm, alpha_dn, beta_dn))
-        for j in reversed(range(self._depth - 1)):
-            for i in range(1, self._depth - j):
-                ides = list(range(j, i + j))
+        # out[i][j]: output of cell (i, j); row 0 is the down path.  The reference (senas_search.py:87-107) walks
+        # j = depth-2 .. 0 outside and i inside while overwriting cell_out[i + j]; cell (i, j) reads cell_out[j .. i+j-1]
+        # = out[0..i-1][j] and cell_out[i + j] = out[i-1][j+1], which the level-by-level walk below provides unchanged.
+        out = [[self.stem1(s0)]]
+        for j in range(1, depth):
+            prev = s0 if j == 1 else out[0][-2]
+            out[0].append(self.blocks[0][j](prev, out[0][-1], alpha_dn_nm, alpha_dn, beta_dn))
+        side = self.concurrent_cells and x.is_cuda
+        for i in range(1, depth):
+            cur = torch.cuda.current_stream(x.device) if side else None
+            row, joins = [], []
+            for j in range(depth - i):
                 gidx = [sum(range(k + j)) + j for k in range(1, i)]
-                parts = [cell_out[ides[0]]]
-                for k, g in enumerate(gidx):
-                    parts.append(cell_out[ides[k]] * gamma[g][0] + cell_out[ides[k + 1]] * gamma[g][1])
-                in0 = torch.cat(parts, dim=1)
-                cell_out[i + j] = self.blocks[i][j](in0, cell_out[i + j], alpha_up_nm, alpha_up, beta_up)
+                st = self._cell_stream(j, x.device) if (side and j > 0) else None
+                if st is not None:
+                    st.wait_stream(cur)
+                    fused.set_slot(j)
+                try:
+                    with (torch.cuda.stream(st) if st is not None else _nullctx()):
+                        parts = [out[0][j]]
+                        for k, g in enumerate(gidx):
+                            parts.append(out[k][j] * gamma[g][0] + out[k + 1][j] * gamma[g][1])
+                        in0 = torch.cat(parts, dim=1)
+                        row.append(self.blocks[i][j](in0, out[i - 1][j + 1], alpha_up_nm, alpha_up, beta_up))
+                finally:
+                    if st is not None:
+                        fused.set_slot(0)
+                        joins.append(st)
+            for st in joins:
+                cur.wait_stream(st)
+            out.append(row)
         head = self.head_block[-1]
         if self._supervision:
-            return [head(s0, ot, alpha_up_nm, alpha_up, beta_up) for ot in cell_out]
-        return [head(s0, cell_out[-1], alpha_up_nm, alpha_up, beta_up)]
+            return [head(s0, out[i][0] if i else out[0][0], alpha_up_nm, alpha_up, beta_up) for i in range(depth)]
+        return [head(s0, out[depth - 1][0], alpha_up_nm, alpha_up, beta_up)]
+
+
+class _nullctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 class NAS(nn.Module):

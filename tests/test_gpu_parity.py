@@ -393,3 +393,26 @@ def test_cell_bf16_tensor_core_groups_three_edges(bf16_mode, representable, w0):
         if not representable:
             break  # parameter gradients of this variant are dominated by the flipped masks (see docstring)
         gcheck('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 6e-2 if 'excitation' in n else 3e-2)
+
+
+def test_concurrent_cells_same_result():
+    """Independent cells of one level on separate CUDA streams (SenasSearch.concurrent_cells, used by the captured step)
+    only change the schedule: same loss, same gradients as the serial walk."""
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 1, 64, 64, generator=gen).to(DEV)
+    y = (torch.rand(2, 64, 64, generator=gen) > 0.8).long().to(DEV)
+    res = []
+    for conc in (False, True, True):
+        m = _new_nas().to(DEV).train()
+        m.net.concurrent_cells = conc
+        loss = oracle.dice_ce_loss(m(x)[-1], y)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((loss.item(), {n: p.grad.detach().clone() for n, p in m.named_parameters()}))
+    assert res[0][0] == res[1][0] == res[2][0], [r[0] for r in res]
+    for n in res[0][1]:
+        # the fused cells are bit-reproducible; cuDNN's weight gradients in the stock blocks are not (atomics)
+        tol = 0.0 if '._ops.' in n else 1e-4
+        assert max_err(res[1][1][n], res[0][1][n]) <= tol, n
+        assert max_err(res[2][1][n], res[0][1][n]) <= tol, n
