@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the captured step is a DAG over ~60 streams (lanes x concurrent cells): give the device as many hardware queues as it has
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 # algorithmic work per image (SURVEY.md section 8d / BASELINE.md section 3), search step = 2 x (fwd + bwd)
 STEP_GFLOP_PER_IMG = 176.0          # whole supernet

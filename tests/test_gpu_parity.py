@@ -412,7 +412,7 @@ def test_concurrent_cells_same_result():
         res.append((loss.item(), {n: p.grad.detach().clone() for n, p in m.named_parameters()}))
     assert res[0][0] == res[1][0] == res[2][0], [r[0] for r in res]
     for n in res[0][1]:
-        # the fused cells are bit-reproducible; cuDNN's weight gradients in the stock blocks are not (atomics)
-        tol = 0.0 if '._ops.' in n else 1e-4
-        assert max_err(res[1][1][n], res[0][1][n]) <= tol, n
-        assert max_err(res[2][1][n], res[0][1][n]) <= tol, n
+        # the fused cells are bit-reproducible, but cuDNN's backward in the stock blocks between them is not (atomics),
+        # so run-to-run differences of ~1e-7 reach every gradient whatever the schedule
+        assert max_err(res[1][1][n], res[0][1][n]) <= 1e-4, n
+        assert max_err(res[2][1][n], res[0][1][n]) <= 1e-4, n
