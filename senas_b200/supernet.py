@@ -92,11 +92,13 @@ class SenasSearch(nn.Module):
         for i in range(1, depth):
             cur = torch.cuda.current_stream(x.device) if side else None
             row, joins = [], []
+            if side:  # fork every side stream BEFORE cell j = 0 is enqueued on the caller's stream
+                for j in range(1, depth - i):
+                    self._cell_stream(j, x.device).wait_stream(cur)
             for j in range(depth - i):
                 gidx = [sum(range(k + j)) + j for k in range(1, i)]
                 st = self._cell_stream(j, x.device) if (side and j > 0) else None
                 if st is not None:
-                    st.wait_stream(cur)
                     fused.set_slot(j)
                 try:
                     with (torch.cuda.stream(st) if st is not None else _nullctx()):
