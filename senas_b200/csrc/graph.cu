@@ -354,11 +354,11 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
       delete p;
       SENAS_FAIL("node %d has %d terms (max %d)", i, nterms, kMaxTerms);
     }
-    np.nblk = nblk_px;
+    np.nblk = cdiv(HW, kBstatsPx);  // node_bstats_kernel grid
     np.bias_off = take(sc, B * 8);
     np.gm_off = take(sc, (int64_t)B * HW * 8);
     np.dnode_off = np.has_consumer ? take(sc, (int64_t)B * HW * 8) : -1;
-    np.bpart_off = take(sc, (int64_t)B * nblk_px * (1 + nterms) * 8);
+    np.bpart_off = take(sc, (int64_t)B * np.nblk * (1 + nterms) * 8);
     np.bsum_off = take(sc, (int64_t)B * (1 + nterms) * 8);
     np.nterms = nterms;
   }
@@ -1233,9 +1233,8 @@ static int backward_edge(BwdCall &c, int e) {
   return 0;
 }
 
-// grouped data gradient + weight gradient of the depthwise halves of every NORM edge that reads `src`; runs once all
-// of those edges have produced their dz (the consumers of an input state: after the last node).
-static int backward_dw_group(BwdCall &c, int src) {
+// data gradient + weight gradient of the depthwise halves (k3 + k5) of one NORM / UP edge, as one launch each
+static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   const senas_graph_desc_t &d = *c.d;
   const Plan &p = *c.p;
   DwMultiArgs a;
@@ -1247,7 +1246,7 @@ static int backward_dw_group(BwdCall &c, int src) {
   int64_t goff[kDwMaxItems];
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || ed.op_type == SENAS_OP_DOWN) continue;
+    if (ed.src != src || e != only_edge || ed.op_type == SENAS_OP_DOWN) continue;
     up = ed.op_type == SENAS_OP_UP;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
@@ -1355,7 +1354,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     if (np.has_consumer && !c.touched[d.n_inputs + i])
       cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
     SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
-    SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
+    SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(256), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
                  d.node_relu);
     {
       const int V = (1 + np.nterms) * 8;
@@ -1369,14 +1368,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     SENAS_LAUNCH(node_bfin_kernel, dim3(n_in), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
     c.S.fork();  // the candidate chains of this node's edges run on the lanes, concurrently with the next node's sweep
-    for (int e = 0; e < d.n_edges; ++e)
-      if (d.edge[e].dst == i && backward_edge(c, e)) return 1;
-    // states whose consumers have all been processed: node i-1 (its consumers are nodes >= i), or the inputs at the end
-    if (i > 0) {
-      if (backward_dw_group(c, d.n_inputs + i - 1)) return 1;
-    } else {
-      for (int src = 0; src < d.n_inputs; ++src)
-        if (backward_dw_group(c, src)) return 1;
+    // the depthwise halves (k3 + k5) of an edge go out together as soon as the edge's dz exist: waiting for all edges
+    // of a state (as the forward does to share the x reads) would leave the whole group in the tail of the call
+    for (int e = 0; e < d.n_edges; ++e) {
+      if (d.edge[e].dst != i) continue;
+      if (backward_edge(c, e)) return 1;
+      if (backward_dw_group(c, d.edge[e].src, e)) return 1;
     }
   }
 #ifndef SENAS_EMU

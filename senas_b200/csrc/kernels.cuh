@@ -1021,49 +1021,64 @@ __global__ void __launch_bounds__(128) node_combine_kernel(const NodeDesc *nodes
 // backward: node statistics sweep
 //   gm = (g_out[node] + d_node) * relu'  ->  scratch;  per block: S1 = sum gm, S2_t = sum gm * yhat_t
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+// lane = (pixel of a 4-pixel step, channel): every load is one coalesced 128-byte line per warp; a warp owns 128
+// consecutive pixels, computes gm for them once (kept in registers), then streams the terms one after the other, so the
+// only reductions are 2 shuffles per term and ONE shared-memory combine per block (the first version did a block-wide
+// reduction with two barriers per term and pixel tile).   grid = (ceil(hw / 1024), B), block = 256.
+constexpr int kBstatsPx = 1024;
+__global__ void __launch_bounds__(256) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+  constexpr int STEPS = kBstatsPx / 8 / 4;  // 4-pixel steps per warp
   const NodeDesc &nd = nodes[node];
   float *scratch = bases.p[SP_SCRATCH];
   const float *saved = bases.p[SP_SAVED];
-  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
-  const bool ok = p < nd.hw;
-  const int64_t pix = (int64_t)n * nd.hw + (ok ? p : 0);
-  float g[8];
+  __shared__ float s_part[8][(1 + kMaxTerms) * 8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c = lane & 7, pg = lane >> 3, n = blockIdx.y;
+  const int p0 = blockIdx.x * kBstatsPx + warp * (kBstatsPx / 8);
+  const int64_t base = (int64_t)n * nd.hw;
+  float g[STEPS];
+  float s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  if (ok) {
-    const float *gp = bases.p[SP_GOUT] + pix * bases.ld[SP_GOUT] + nd.node * 8;
-    float4 lo = ld4(gp), hi = ld4(gp + 4);
-    if (nd.dnode_off >= 0) {
-      const float4 a = ld4(scratch + nd.dnode_off + pix * 8), b = ld4(scratch + nd.dnode_off + pix * 8 + 4);
-      lo.x += a.x, lo.y += a.y, lo.z += a.z, lo.w += a.w, hi.x += b.x, hi.y += b.y, hi.z += b.z, hi.w += b.w;
+  for (int s = 0; s < STEPS; ++s) {
+    const int p = p0 + s * 4 + pg;
+    float v = 0.f;
+    if (p < nd.hw) {
+      const int64_t pix = base + p;
+      v = bases.p[SP_GOUT][pix * bases.ld[SP_GOUT] + nd.node * 8 + c];
+      if (nd.dnode_off >= 0) v += scratch[nd.dnode_off + pix * 8 + c];
+      if (relu && !(bases.p[SP_OUT][pix * bases.ld[SP_OUT] + nd.node * 8 + c] > 0.f)) v = 0.f;
+      scratch[nd.gm_off + pix * 8 + c] = v;
     }
-    if (relu) {
-      const float *op = bases.p[SP_OUT] + pix * bases.ld[SP_OUT] + nd.node * 8;
-      const float4 a = ld4(op), b = ld4(op + 4);
-      lo.x = a.x > 0.f ? lo.x : 0.f, lo.y = a.y > 0.f ? lo.y : 0.f, lo.z = a.z > 0.f ? lo.z : 0.f;
-      lo.w = a.w > 0.f ? lo.w : 0.f, hi.x = b.x > 0.f ? hi.x : 0.f, hi.y = b.y > 0.f ? hi.y : 0.f;
-      hi.z = b.z > 0.f ? hi.z : 0.f, hi.w = b.w > 0.f ? hi.w : 0.f;
-    }
-    st4(scratch + nd.gm_off + pix * 8, lo);
-    st4(scratch + nd.gm_off + pix * 8 + 4, hi);
-    g[0] = lo.x, g[1] = lo.y, g[2] = lo.z, g[3] = lo.w, g[4] = hi.x, g[5] = hi.y, g[6] = hi.z, g[7] = hi.w;
+    g[s] = v, s1 += v;
   }
-  float *part = scratch + nd.bpart_off + ((int64_t)n * nd.nblk + blockIdx.x) * (1 + nd.nterms) * 8;
-  block_sum_store<8>(g, part);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  if (lane < 8) s_part[warp][c] = s1;
   for (int ti = 0; ti < nd.nterms; ++ti) {
     const TermDesc &t = nd.t[ti];
-    float v[8];
+    float acc = 0.f;
+    if (t.has_y) {
+      const float *y = ref_ptr(t.y, bases) + c;
+      const int64_t ld = ref_ld(t.y, bases);
+      const float mean = saved[t.mean_off + c];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (t.has_y && ok) {
-      const float *y = ref_ptr(t.y, bases) + pix * ref_ld(t.y, bases);
-      const float4 lo = ld4(y), hi = ld4(y + 4);
-      const float yv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = g[j] * (yv[j] - saved[t.mean_off + j]) * saved[t.istd_off + j];
+      for (int s = 0; s < STEPS; ++s) {
+        const int p = p0 + s * 4 + pg;
+        const float yv = p < nd.hw ? y[(base + p) * ld] : mean;
+        acc = fmaf(g[s], yv - mean, acc);
+      }
+      acc *= saved[t.istd_off + c];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     }
-    if (t.has_y) block_sum_store<8>(v, part + (1 + ti) * 8);  // uniform branch
+    if (lane < 8) s_part[warp][(1 + ti) * 8 + c] = acc;
+  }
+  __syncthreads();
+  const int V = (1 + nd.nterms) * 8;
+  float *part = scratch + nd.bpart_off + ((int64_t)n * nd.nblk + blockIdx.x) * V;
+  for (int o = tid; o < V; o += 256) {
+    float r = 0.f;
+    for (int w = 0; w < 8; ++w) r += s_part[w][o];
+    part[o] = r;
   }
 }
 
