@@ -990,18 +990,26 @@ __global__ void node_coef_kernel(const NodeDesc *nodes, int node, Bases bases, c
 __global__ void __launch_bounds__(128) node_combine_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
   const NodeDesc &nd = nodes[node];
   const float *scratch = bases.p[SP_SCRATCH];
+  // per-(sample, term, channel) scales staged once per block: inside the term loop they were 8 dependent global loads in
+  // front of every pair of y loads (20 us per launch at 16 x 16 pixels: pure latency)
+  __shared__ float s_sc[kMaxTerms * 8 + 8];
   const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  for (int i = threadIdx.x; i < nd.nterms * 8; i += 128) {
+    const TermDesc &t = nd.t[i >> 3];
+    s_sc[8 + i] = t.has_y ? scratch[t.scale_off + n * 8 + (i & 7)] : 0.f;
+  }
+  if (threadIdx.x < 8) s_sc[threadIdx.x] = scratch[nd.bias_off + n * 8 + threadIdx.x];
+  __syncthreads();
   if (p >= nd.hw) return;
   const int64_t pix = (int64_t)n * nd.hw + p;
-  const float *bias = scratch + nd.bias_off + n * 8;
   float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias[j];
+  for (int j = 0; j < 8; ++j) acc[j] = s_sc[j];
   for (int ti = 0; ti < nd.nterms; ++ti) {
     const TermDesc &t = nd.t[ti];
     if (!t.has_y) continue;
     const float *y = ref_ptr(t.y, bases) + pix * ref_ld(t.y, bases);
-    const float *sc = scratch + t.scale_off + n * 8;
+    const float *sc = s_sc + 8 + ti * 8;
     const float4 lo = ld4(y), hi = ld4(y + 4);
     acc[0] = fmaf(sc[0], lo.x, acc[0]), acc[1] = fmaf(sc[1], lo.y, acc[1]);
     acc[2] = fmaf(sc[2], lo.z, acc[2]), acc[3] = fmaf(sc[3], lo.w, acc[3]);
@@ -1025,7 +1033,7 @@ __global__ void __launch_bounds__(128) node_combine_kernel(const NodeDesc *nodes
 // consecutive pixels, computes gm for them once (kept in registers), then streams the terms one after the other, so the
 // only reductions are 2 shuffles per term and ONE shared-memory combine per block (the first version did a block-wide
 // reduction with two barriers per term and pixel tile).   grid = (ceil(hw / 1024), B), block = 256.
-constexpr int kBstatsPx = 1024;
+constexpr int kBstatsPx = 512;
 __global__ void __launch_bounds__(256) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
   constexpr int STEPS = kBstatsPx / 8 / 4;  // 4-pixel steps per warp
   const NodeDesc &nd = nodes[node];
@@ -1057,15 +1065,15 @@ __global__ void __launch_bounds__(256) node_bstats_kernel(const NodeDesc *nodes,
     const TermDesc &t = nd.t[ti];
     float acc = 0.f;
     if (t.has_y) {
-      const float *y = ref_ptr(t.y, bases) + c;
       const int64_t ld = ref_ld(t.y, bases);
+      const float *yp = ref_ptr(t.y, bases) + c + (base + p0 + pg) * ld;
+      const int64_t step = 4 * ld;
       const float mean = saved[t.mean_off + c];
+      float yv[STEPS];
 #pragma unroll
-      for (int s = 0; s < STEPS; ++s) {
-        const int p = p0 + s * 4 + pg;
-        const float yv = p < nd.hw ? y[(base + p) * ld] : mean;
-        acc = fmaf(g[s], yv - mean, acc);
-      }
+      for (int s = 0; s < STEPS; ++s) yv[s] = (p0 + s * 4 + pg < nd.hw) ? yp[s * step] : mean;
+#pragma unroll
+      for (int s = 0; s < STEPS; ++s) acc = fmaf(g[s], yv[s] - mean, acc);
       acc *= saved[t.istd_off + c];
       acc += __shfl_xor_sync(0xffffffffu, acc, 8);
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
