@@ -141,6 +141,12 @@ static Geo make_geo(int k, int dil, int op, int dir) {
 constexpr int kLanes = 8;                         // general lanes (each owns a slice of the tmp scratch)
 constexpr int kDxLanes = 2 + SENAS_MAX_NODES;     // one per state that receives a data gradient
 constexpr int kAllLanes = kLanes + kDxLanes;
+static int env_flag(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static const int g_bstats_v = env_flag("SENAS_BSTATS", 2);      // node_bstats kernel version (A/B switch)
+static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
@@ -354,7 +360,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
       delete p;
       SENAS_FAIL("node %d has %d terms (max %d)", i, nterms, kMaxTerms);
     }
-    np.nblk = cdiv(HW, kBstatsPx);  // node_bstats_kernel grid
+    np.nblk = cdiv(HW, g_bstats_v == 1 ? 128 : kBstatsPx);  // node_bstats kernel grid
     np.bias_off = take(sc, B * 8);
     np.gm_off = take(sc, (int64_t)B * HW * 8);
     np.dnode_off = np.has_consumer ? take(sc, (int64_t)B * HW * 8) : -1;
@@ -1246,7 +1252,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   int64_t goff[kDwMaxItems];
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || e != only_edge || ed.op_type == SENAS_OP_DOWN) continue;
+    if (ed.src != src || (only_edge >= 0 && e != only_edge) || ed.op_type == SENAS_OP_DOWN) continue;
     up = ed.op_type == SENAS_OP_UP;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
@@ -1354,8 +1360,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     if (np.has_consumer && !c.touched[d.n_inputs + i])
       cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
     SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
-    SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(256), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
-                 d.node_relu);
+    if (g_bstats_v == 1)
+      SENAS_LAUNCH(node_bstats_v1_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i,
+                   c.bases, d.node_relu);
+    else
+      SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(256), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
+                   d.node_relu);
     {
       const int V = (1 + np.nterms) * 8;
       SENAS_TAG("reduce", 0, 0);
@@ -1373,7 +1383,15 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     for (int e = 0; e < d.n_edges; ++e) {
       if (d.edge[e].dst != i) continue;
       if (backward_edge(c, e)) return 1;
-      if (backward_dw_group(c, d.edge[e].src, e)) return 1;
+      if (g_dw_per_edge && backward_dw_group(c, d.edge[e].src, e)) return 1;
+    }
+    if (!g_dw_per_edge) {  // per state: once all edges that read it have produced their dz
+      if (i > 0) {
+        if (backward_dw_group(c, d.n_inputs + i - 1, -1)) return 1;
+      } else {
+        for (int src = 0; src < d.n_inputs; ++src)
+          if (backward_dw_group(c, src, -1)) return 1;
+      }
     }
   }
 #ifndef SENAS_EMU

@@ -1090,6 +1090,53 @@ __global__ void __launch_bounds__(256) node_bstats_kernel(const NodeDesc *nodes,
   }
 }
 
+// first version: thread = pixel, one block-wide reduction per term (kept selectable: SENAS_BSTATS=1)
+__global__ void __launch_bounds__(128) node_bstats_v1_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+  const NodeDesc &nd = nodes[node];
+  float *scratch = bases.p[SP_SCRATCH];
+  const float *saved = bases.p[SP_SAVED];
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  const bool ok = p < nd.hw;
+  const int64_t pix = (int64_t)n * nd.hw + (ok ? p : 0);
+  float g[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (ok) {
+    const float *gp = bases.p[SP_GOUT] + pix * bases.ld[SP_GOUT] + nd.node * 8;
+    float4 lo = ld4(gp), hi = ld4(gp + 4);
+    if (nd.dnode_off >= 0) {
+      const float4 a = ld4(scratch + nd.dnode_off + pix * 8), b = ld4(scratch + nd.dnode_off + pix * 8 + 4);
+      lo.x += a.x, lo.y += a.y, lo.z += a.z, lo.w += a.w, hi.x += b.x, hi.y += b.y, hi.z += b.z, hi.w += b.w;
+    }
+    if (relu) {
+      const float *op = bases.p[SP_OUT] + pix * bases.ld[SP_OUT] + nd.node * 8;
+      const float4 a = ld4(op), b = ld4(op + 4);
+      lo.x = a.x > 0.f ? lo.x : 0.f, lo.y = a.y > 0.f ? lo.y : 0.f, lo.z = a.z > 0.f ? lo.z : 0.f;
+      lo.w = a.w > 0.f ? lo.w : 0.f, hi.x = b.x > 0.f ? hi.x : 0.f, hi.y = b.y > 0.f ? hi.y : 0.f;
+      hi.z = b.z > 0.f ? hi.z : 0.f, hi.w = b.w > 0.f ? hi.w : 0.f;
+    }
+    st4(scratch + nd.gm_off + pix * 8, lo);
+    st4(scratch + nd.gm_off + pix * 8 + 4, hi);
+    g[0] = lo.x, g[1] = lo.y, g[2] = lo.z, g[3] = lo.w, g[4] = hi.x, g[5] = hi.y, g[6] = hi.z, g[7] = hi.w;
+  }
+  float *part = scratch + nd.bpart_off + ((int64_t)n * nd.nblk + blockIdx.x) * (1 + nd.nterms) * 8;
+  block_sum_store<8>(g, part);
+  for (int ti = 0; ti < nd.nterms; ++ti) {
+    const TermDesc &t = nd.t[ti];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (t.has_y && ok) {
+      const float *y = ref_ptr(t.y, bases) + pix * ref_ld(t.y, bases);
+      const float4 lo = ld4(y), hi = ld4(y + 4);
+      const float yv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = g[j] * (yv[j] - saved[t.mean_off + j]) * saved[t.istd_off + j];
+    }
+    if (t.has_y) block_sum_store<8>(v, part + (1 + ti) * 8);  // uniform branch
+  }
+}
+
 // backward finalize for one node: reductions, parameter / alpha / beta gradients, dy coefficient tables.
 // grid = incoming edges of the node (the terms of different edges are independent; this kernel sits on the critical path
 // of every node's backward, 3 per cell, and took ~50 us as a single block walking up to 24 terms)
