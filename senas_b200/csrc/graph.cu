@@ -145,7 +145,6 @@ static int env_flag(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static const int g_bstats_v = env_flag("SENAS_BSTATS", 2);      // node_bstats kernel version (A/B switch)
 static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -360,7 +359,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
       delete p;
       SENAS_FAIL("node %d has %d terms (max %d)", i, nterms, kMaxTerms);
     }
-    np.nblk = cdiv(HW, g_bstats_v == 1 ? 128 : kBstatsPx);  // node_bstats kernel grid
+    np.nblk = nblk_px;  // node_bstats_kernel grid
     np.bias_off = take(sc, B * 8);
     np.gm_off = take(sc, (int64_t)B * HW * 8);
     np.dnode_off = np.has_consumer ? take(sc, (int64_t)B * HW * 8) : -1;
@@ -1360,12 +1359,8 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     if (np.has_consumer && !c.touched[d.n_inputs + i])
       cudaMemsetAsync(c.scratch + np.dnode_off, 0, node_bytes, (cudaStream_t)c.stream);
     SENAS_TAG("node_bstats", 0, 4.0 * c.B * p->hw * 8 * (3 + 5 * (i + 2)));
-    if (g_bstats_v == 1)
-      SENAS_LAUNCH(node_bstats_v1_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i,
-                   c.bases, d.node_relu);
-    else
-      SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(256), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
-                   d.node_relu);
+    SENAS_LAUNCH(node_bstats_kernel, dim3(np.nblk, c.B), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases,
+                 d.node_relu);
     {
       const int V = (1 + np.nterms) * 8;
       SENAS_TAG("reduce", 0, 0);

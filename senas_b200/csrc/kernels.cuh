@@ -1029,69 +1029,10 @@ __global__ void __launch_bounds__(128) node_combine_kernel(const NodeDesc *nodes
 // backward: node statistics sweep
 //   gm = (g_out[node] + d_node) * relu'  ->  scratch;  per block: S1 = sum gm, S2_t = sum gm * yhat_t
 // ------------------------------------------------------------------------------------------------
-// lane = (pixel of a 4-pixel step, channel): every load is one coalesced 128-byte line per warp; a warp owns 128
-// consecutive pixels, computes gm for them once (kept in registers), then streams the terms one after the other, so the
-// only reductions are 2 shuffles per term and ONE shared-memory combine per block (the first version did a block-wide
-// reduction with two barriers per term and pixel tile).   grid = (ceil(hw / 1024), B), block = 256.
-constexpr int kBstatsPx = 512;
-__global__ void __launch_bounds__(256) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
-  constexpr int STEPS = kBstatsPx / 8 / 4;  // 4-pixel steps per warp
-  const NodeDesc &nd = nodes[node];
-  float *scratch = bases.p[SP_SCRATCH];
-  const float *saved = bases.p[SP_SAVED];
-  __shared__ float s_part[8][(1 + kMaxTerms) * 8];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c = lane & 7, pg = lane >> 3, n = blockIdx.y;
-  const int p0 = blockIdx.x * kBstatsPx + warp * (kBstatsPx / 8);
-  const int64_t base = (int64_t)n * nd.hw;
-  float g[STEPS];
-  float s1 = 0.f;
-#pragma unroll
-  for (int s = 0; s < STEPS; ++s) {
-    const int p = p0 + s * 4 + pg;
-    float v = 0.f;
-    if (p < nd.hw) {
-      const int64_t pix = base + p;
-      v = bases.p[SP_GOUT][pix * bases.ld[SP_GOUT] + nd.node * 8 + c];
-      if (nd.dnode_off >= 0) v += scratch[nd.dnode_off + pix * 8 + c];
-      if (relu && !(bases.p[SP_OUT][pix * bases.ld[SP_OUT] + nd.node * 8 + c] > 0.f)) v = 0.f;
-      scratch[nd.gm_off + pix * 8 + c] = v;
-    }
-    g[s] = v, s1 += v;
-  }
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-  if (lane < 8) s_part[warp][c] = s1;
-  for (int ti = 0; ti < nd.nterms; ++ti) {
-    const TermDesc &t = nd.t[ti];
-    float acc = 0.f;
-    if (t.has_y) {
-      const int64_t ld = ref_ld(t.y, bases);
-      const float *yp = ref_ptr(t.y, bases) + c + (base + p0 + pg) * ld;
-      const int64_t step = 4 * ld;
-      const float mean = saved[t.mean_off + c];
-      float yv[STEPS];
-#pragma unroll
-      for (int s = 0; s < STEPS; ++s) yv[s] = (p0 + s * 4 + pg < nd.hw) ? yp[s * step] : mean;
-#pragma unroll
-      for (int s = 0; s < STEPS; ++s) acc = fmaf(g[s], yv[s] - mean, acc);
-      acc *= saved[t.istd_off + c];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-    }
-    if (lane < 8) s_part[warp][(1 + ti) * 8 + c] = acc;
-  }
-  __syncthreads();
-  const int V = (1 + nd.nterms) * 8;
-  float *part = scratch + nd.bpart_off + ((int64_t)n * nd.nblk + blockIdx.x) * V;
-  for (int o = tid; o < V; o += 256) {
-    float r = 0.f;
-    for (int w = 0; w < 8; ++w) r += s_part[w][o];
-    part[o] = r;
-  }
-}
-
-// first version: thread = pixel, one block-wide reduction per term (kept selectable: SENAS_BSTATS=1)
-__global__ void __launch_bounds__(128) node_bstats_v1_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
+// thread = pixel, one block-wide reduction per term.  (A channel-lane rewrite -- lane = (pixel of a 4-pixel step, channel),
+// gm of 64-128 pixels in registers, terms streamed one after the other, one combine per block -- measured 6 ms per step
+// SLOWER (157 -> 148 img/s): 4x the load instructions for the same bytes and a dependent chain per term.)
+__global__ void __launch_bounds__(128) node_bstats_kernel(const NodeDesc *nodes, int node, Bases bases, int relu) {
   const NodeDesc &nd = nodes[node];
   float *scratch = bases.p[SP_SCRATCH];
   const float *saved = bases.p[SP_SAVED];
