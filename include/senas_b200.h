@@ -152,6 +152,13 @@ int senas_set_lanes(int n);
  * on different streams gives each stream its own slot (and its own scratch buffer) so that their lanes do not
  * serialise against each other; one host thread drives the library, so the selection is process-global. */
 int senas_set_slot(int slot);
+/* Deferred join of the weight-gradient lanes.  With senas_set_defer(1), senas_graph_backward returns (in stream order)
+ * as soon as the data gradients, grad_alpha and grad_beta are complete; grad_params and every buffer the call read
+ * (inputs, saved, scratch of the slot) must then stay untouched and alive until the next call in the same slot or until
+ * senas_flush(stream), which makes `stream` wait for all such pending work of the process.  Default 0: backward
+ * returns with everything ordered on the caller's stream. */
+int senas_set_defer(int on);
+int senas_flush(void *stream);
 /* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
  * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
  * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */

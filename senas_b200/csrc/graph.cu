@@ -489,7 +489,10 @@ struct LaneSet {
   cudaStream_t s[kAllLanes];
   cudaEvent_t ev[kEventPool];
   int next_ev = 0;
+  int pending = 0;  // general lanes carry weight-gradient work of an earlier backward call that nobody has joined yet
 };
+static std::vector<LaneSet *> g_lane_sets;
+static int g_defer = 0;  // senas_set_defer: leave the weight-gradient lanes of a backward call running (joined later)
 // one lane set per (device, slot): cells that the host runs concurrently on different streams (independent cells of one
 // level of the UNet++ triangle, senas_b200/supernet.py) select different slots (senas_set_slot) so that they do not
 // queue behind each other on shared lanes.  Slots, not stream handles, so that warm-up and capture share the sets.
@@ -505,6 +508,7 @@ static LaneSet *lanes_for(int slot) {
   for (int i = 0; i < kAllLanes; ++i) cudaStreamCreateWithFlags(&ls->s[i], cudaStreamNonBlocking);
   for (int i = 0; i < kEventPool; ++i) cudaEventCreateWithFlags(&ls->ev[i], cudaEventDisableTiming);
   sets[key] = ls;
+  g_lane_sets.push_back(ls);
   return ls;
 }
 #endif
@@ -524,7 +528,28 @@ struct Sched {
       g_lanes = e ? std::max(0, std::min(kLanes, atoi(e))) : kLanes;
     }
     n = g_prof_on ? 0 : g_lanes;  // per-kernel timing wants serial launches
-    if (n > 0) ls = lanes_for(g_slot);
+    if (n > 0) {
+      ls = lanes_for(g_slot);
+      if (ls->pending) {  // deferred weight-gradient work of the previous backward call in this slot: order it before us
+        for (int i = 0; i < kLanes; ++i) dep(i, -1);
+        ls->pending = 0;
+      }
+    }
+#endif
+  }
+  // end of a backward call: the caller needs the data gradients (dx lanes) now; the general lanes only finish weight
+  // gradients that nothing reads before the optimizer.  With senas_set_defer(1) they keep running beside whatever the
+  // caller enqueues next and are joined by the next call of the slot or by senas_flush(); the host keeps the buffers
+  // they read alive until then (senas_b200/fused.py).
+  void join_backward() {
+#ifndef SENAS_EMU
+    if (n == 0) return;
+    if (!g_defer) {
+      join();
+      return;
+    }
+    for (int i = kLanes; i < kAllLanes; ++i) dep(i, -1);
+    ls->pending = 1;
 #endif
   }
   void *stream(int lane) const {
@@ -1471,7 +1496,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     }
   }
 #endif
-  c.S.join();
+  c.S.join_backward();
   for (int i = 0; i < d.n_inputs; ++i)
     if (a->grad_in[i] && !c.touched[i]) {
       if (a->grad_in_ld[i] != d.edge[0].c_in) SENAS_FAIL("backward: cannot zero a strided grad_in");
@@ -1492,6 +1517,27 @@ extern "C" int senas_set_slot(int slot) {
   g_slot = slot < 0 ? 0 : slot;
 #else
   (void)slot;
+#endif
+  return 0;
+}
+extern "C" int senas_set_defer(int on) {
+  g_defer = on != 0;
+  return 0;
+}
+extern "C" int senas_flush(void *stream) {
+#ifndef SENAS_EMU
+  for (LaneSet *ls : g_lane_sets) {
+    if (!ls->pending) continue;
+    for (int i = 0; i < kLanes; ++i) {
+      cudaEvent_t e = ls->ev[ls->next_ev];
+      ls->next_ev = (ls->next_ev + 1) % kEventPool;
+      cudaEventRecord(e, ls->s[i]);
+      cudaStreamWaitEvent((cudaStream_t)stream, e, 0);
+    }
+    ls->pending = 0;
+  }
+#else
+  (void)stream;
 #endif
   return 0;
 }

@@ -77,6 +77,29 @@ def get_conv_mode():
 
 
 _slot = [0]
+_defer = [False]
+_held = {}  # slot -> buffers that deferred weight-gradient kernels of the last backward call of the slot may still read
+
+
+def set_defer(on, lib=None):
+    """Deferred join of the weight-gradient lanes (``senas_set_defer``): a fused backward then returns as soon as the
+    data / alpha / beta gradients are ordered on the stream, the weight-gradient kernels keep running beside whatever
+    comes next, and ``flush()`` must be called before anything reads the parameter gradients.  Used by
+    ``GraphedSearchStep``; off by default."""
+    lib = lib if lib is not None else _lib.get()
+    if not on:
+        flush(lib)
+    _defer[0] = bool(on)
+    lib.senas_set_defer(int(bool(on)))
+
+
+def flush(lib=None):
+    """Make the current stream wait for all deferred weight-gradient work and release the buffers held for it."""
+    lib = lib if lib is not None else _lib.get()
+    if torch.cuda.is_available():
+        lib.senas_flush(torch.cuda.current_stream().cuda_stream)
+    _held.clear()
+
 
 
 def set_slot(slot):
@@ -194,7 +217,9 @@ class GraphRunner:
         a.out, a.out_ld = out.data_ptr(), out.shape[1]
         a.saved, a.scratch, a.stream = saved.data_ptr(), scratch.data_ptr(), self._stream()
         self.lib.senas_set_slot(slot)
+        held = _held.pop(slot, None)  # the call below first orders the slot's pending lanes before itself
         _lib.check(self.lib, self.lib.senas_graph_forward(self.handle, C.byref(a)))
+        del held
         return out, saved
 
     def backward(self, ins, alpha, beta, out, grad_out, saved, training, need_in, slot=0):
@@ -222,7 +247,11 @@ class GraphRunner:
         a.grad_beta = g_beta.data_ptr() if g_beta is not None else None
         a.grad_params, a.stream = g_params.data_ptr(), self._stream()
         self.lib.senas_set_slot(slot)
+        held = _held.pop(slot, None)
         _lib.check(self.lib, self.lib.senas_graph_backward(self.handle, C.byref(a)))
+        del held
+        if _defer[0]:  # weight-gradient kernels of this call may still be reading these when we return
+            _held[slot] = (ins, out, grad_out, saved, g_params)
         return g_ins, g_alpha, g_beta, g_params
 
     # -- autograd entry ------------------------------------------------------------------------

@@ -32,10 +32,11 @@ class GraphedSearchStep:
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
-                 force_segments=False, capture_error_mode='global', concurrent_cells=True):
+                 force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=True):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
         # small latency-bound cells with the large one of the level (senas_b200/supernet.py)
+        self.defer_wgrad = bool(defer_wgrad)
         net = getattr(model, 'net', None)
         if net is not None and hasattr(net, 'concurrent_cells'):
             net.concurrent_cells = bool(concurrent_cells)
@@ -79,12 +80,25 @@ class GraphedSearchStep:
         for p in self.params:
             p.grad = None
         self.a_opt.zero_grad(set_to_none=True)
-        self.criterion(self.model(xv), yv).backward()
+        self._backward(self.criterion(self.model(xv), yv))
         if self.segmented:
             torch._foreach_copy_(self.arch_views, [p.grad for p in self.arch])
             self.bucket_arch.mul_(1.0 / self.world)
             for p in self.params:
                 p.grad = None
+
+    def _backward(self, loss):
+        """backward with the weight-gradient lanes of every fused call left running (joined by the next call of the
+        same slot, or here at the end): they are the tail of each cell's backward and nothing reads them before the
+        optimizer, so they overlap the stock blocks between the cells."""
+        from . import fused
+        if self.defer_wgrad:
+            fused.set_defer(True)
+        try:
+            loss.backward()
+        finally:
+            if self.defer_wgrad:
+                fused.set_defer(False)  # flushes: the current stream waits for everything still pending
 
     def _seg2(self):
         xt, yt, xv, yv = self.static
@@ -94,7 +108,7 @@ class GraphedSearchStep:
         self.a_opt.step()
         self.w_opt.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(xt), yt)
-        loss.backward()
+        self._backward(loss)
         if self.segmented:
             torch._foreach_copy_(self.all_views, [p.grad for p in self.params])
             self.bucket_all.mul_(1.0 / self.world)
