@@ -231,7 +231,7 @@ def run_ours(args, rank, world, local_rank):
             graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
                                                    warmup=3, group=group,
                                                    capture_error_mode='thread_local' if world > 1 else 'global',
-                                                   concurrent_cells=not args.serial_cells, defer_wgrad=not args.no_defer)
+                                                   concurrent_cells=not args.serial_cells, defer_wgrad=args.defer_wgrad)
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
             search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731
@@ -357,7 +357,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
-    ap.add_argument('--no-defer', action='store_true', help='join the weight-gradient lanes at the end of every fused backward call')
+    ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')
     ap.add_argument('--conv-mode', default='bf16', choices=['fp32', 'bf16'],
                     help='bf16: tcgen05 implicit-GEMM convs with bf16 operands / fp32 accumulation; fp32: exact FMA path')
     args = ap.parse_args()

@@ -1521,7 +1521,11 @@ extern "C" int senas_set_slot(int slot) {
   return 0;
 }
 extern "C" int senas_set_defer(int on) {
+#ifndef SENAS_EMU
   g_defer = on != 0;
+#else
+  (void)on;
+#endif
   return 0;
 }
 extern "C" int senas_flush(void *stream) {

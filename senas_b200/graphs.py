@@ -32,7 +32,7 @@ class GraphedSearchStep:
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
-                 force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=True):
+                 force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
         # small latency-bound cells with the large one of the level (senas_b200/supernet.py)
@@ -88,9 +88,9 @@ class GraphedSearchStep:
                 p.grad = None
 
     def _backward(self, loss):
-        """backward with the weight-gradient lanes of every fused call left running (joined by the next call of the
-        same slot, or here at the end): they are the tail of each cell's backward and nothing reads them before the
-        optimizer, so they overlap the stock blocks between the cells."""
+        """backward, optionally (``defer_wgrad``) with the weight-gradient lanes of every fused call left running (joined
+        by the next call of the same slot, or here at the end).  Measured: 102.6 ms vs 102.5 ms per step -- the next
+        fused call of the slot follows too closely for the tails to hide, so it is off by default."""
         from . import fused
         if self.defer_wgrad:
             fused.set_defer(True)
