@@ -138,7 +138,7 @@ static Geo make_geo(int k, int dil, int op, int dir) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-constexpr int kLanes = 8;                         // general lanes (each owns a slice of the tmp scratch)
+constexpr int kLanes = 16;                        // general lanes (each owns a slice of the tmp scratch)
 constexpr int kDxLanes = 2 + SENAS_MAX_NODES;     // one per state that receives a data gradient
 constexpr int kAllLanes = kLanes + kDxLanes;
 static int env_flag(const char *name, int dflt) {
@@ -146,6 +146,7 @@ static int env_flag(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
+static const int g_dw_fwd_per_edge = env_flag("SENAS_DW_FWD_EDGE", 0);  // same for the forward (A/B switch)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static const int kDwChunk = 1024;  // base pixels per block in dw_wgrad_kernel
@@ -525,7 +526,7 @@ struct Sched {
 #ifndef SENAS_EMU
     if (g_lanes < 0) {
       const char *e = getenv("SENAS_LANES");
-      g_lanes = e ? std::max(0, std::min(kLanes, atoi(e))) : kLanes;
+      g_lanes = e ? std::max(0, std::min(kLanes, atoi(e))) : 8;
     }
     n = g_prof_on ? 0 : g_lanes;  // per-kernel timing wants serial launches
     if (n > 0) {
@@ -687,7 +688,7 @@ static void conv_weight_strides(int op, int c_in, int T, int dir, int *ws_k, int
 // ------------------------------------------------------------------------------------------------
 // dep-sep candidates of NORM edges: the depthwise halves of every edge that reads `src` go out as ONE launch
 // (dw_multi_kernel: the input tile is read from HBM once for up to 6 convolutions).
-static int forward_dw_group(Call &c, int src) {
+static int forward_dw_group(Call &c, int src, int only_edge) {
   const senas_graph_desc_t &d = *c.d;
   const Plan &p = *c.p;
   DwMultiArgs a;
@@ -698,7 +699,7 @@ static int forward_dw_group(Call &c, int src) {
   const float *x = state_ptr(c, src, &x_ld);
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || ed.op_type == SENAS_OP_DOWN) continue;
+    if (ed.src != src || (only_edge >= 0 && e != only_edge) || ed.op_type == SENAS_OP_DOWN) continue;
     up = ed.op_type == SENAS_OP_UP;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
@@ -933,8 +934,15 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
 #endif
   for (int s = 0; s < d.n_nodes; ++s) {
     if (s > 0) c.S.fork();
-    for (int src = 0; src < d.n_inputs + d.n_nodes; ++src)
-      if (state_stage(d, src) == s && forward_dw_group(c, src)) return 1;
+    for (int src = 0; src < d.n_inputs + d.n_nodes; ++src) {
+      if (state_stage(d, src) != s) continue;
+      if (!g_dw_fwd_per_edge) {
+        if (forward_dw_group(c, src, -1)) return 1;
+        continue;
+      }
+      for (int e = 0; e < d.n_edges; ++e)
+        if (d.edge[e].src == src && forward_dw_group(c, src, e)) return 1;
+    }
     for (int e = 0; e < d.n_edges; ++e)
       if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, false)) return 1;
     c.S.join();
