@@ -146,7 +146,7 @@ int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a);
 int64_t senas_launch_count(void);
 /* number of side streams ("lanes") over which independent candidate chains of a call are spread (fork/join with
  * events on the caller's stream; a captured step becomes a DAG).  0 = strictly serial on the caller's stream,
- * negative = default (environment variable SENAS_LANES, else 8).  Results are bit-identical for every setting. */
+ * negative = default (environment variable SENAS_LANES, else 16).  Results are bit-identical for every setting. */
 int senas_set_lanes(int n);
 /* lane set used by the following calls of this process (default 0).  A host that runs independent graphs concurrently
  * on different streams gives each stream its own slot (and its own scratch buffer) so that their lanes do not
