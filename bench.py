@@ -101,7 +101,9 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': 'search_step_images_per_sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'SENAS supernet search step, 1x{args.size}x{args.size} PROMISE12-shaped, CPU'},
+        'config': {'workload': f'SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
+                               f'{args.batch} x 1x{args.size}x{args.size} per GPU, global batch {args.batch * max(1, args.gpus)}',
+                   'parallelism': 'host cpu', 'launch': f'PyTorch CPU, {cores} threads, bounded sample (see cpu_baseline.sample)'},
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
