@@ -1403,7 +1403,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     SENAS_TAG("node_bfin", 0, 0);
     int n_in = 0;
     for (int e = 0; e < d.n_edges; ++e) n_in += d.edge[e].dst == i;
-    SENAS_LAUNCH(node_bfin_kernel, dim3(n_in), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
+    SENAS_LAUNCH(node_bfin_kernel, dim3(n_in, SENAS_MAX_CAND), dim3(128), 0, c.stream, (const NodeDesc *)p->d_nodes, i, c.bases, a->alpha,
                  a->beta, a->grad_alpha, a->grad_beta, a->grad_params, c.B, a->training);
     c.S.fork();  // the candidate chains of this node's edges run on the lanes, concurrently with the next node's sweep
     // the depthwise halves (k3 + k5) of an edge go out together as soon as the edge's dz exist: waiting for all edges

@@ -1079,8 +1079,9 @@ __global__ void __launch_bounds__(128) node_bstats_kernel(const NodeDesc *nodes,
 }
 
 // backward finalize for one node: reductions, parameter / alpha / beta gradients, dy coefficient tables.
-// grid = incoming edges of the node (the terms of different edges are independent; this kernel sits on the critical path
-// of every node's backward, 3 per cell, and took ~50 us as a single block walking up to 24 terms)
+// grid = (incoming edges of the node, 6 candidates): the terms are independent except for d beta_edge; this kernel sits on
+// the critical path of every node's backward, 3 per cell (~50 us as a single block walking up to 24 terms, 13 us with one
+// block per edge)
 __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, int node, Bases bases, const float *alpha,
                                                         const float *beta, float *g_alpha, float *g_beta, float *g_params,
                                                         int batch, int training) {
@@ -1101,12 +1102,16 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
   for (int ti = 0; ti < nd.nterms; ++ti) {
     const TermDesc &t = nd.t[ti];
     if (t.edge != my_edge) continue;  // block-uniform
+    // grid.y = candidate: block (edge, k) finalizes term k of the edge; block (edge, 0) also evaluates the T of the
+    // other terms of its edge (a short loop) because d beta_edge sums them in candidate order
+    const bool full = t.cand == (int)blockIdx.y;
+    if (!full && blockIdx.y != 0) continue;
     const float w = alpha[t.edge * 6 + t.cand], be = beta ? beta[t.edge] : 1.f, kappa = w * be;
     const bool se = t.kind == 5;
     for (int i = tid; i < total; i += 128)
       s_S2[i] = t.has_y ? bsum[(int64_t)(i >> 3) * V + (1 + ti) * 8 + (i & 7)] : 0.f;
     __syncthreads();
-    if (se) {  // through the gate: u = ds * s(1-s), dh = relu'(h) * sum_c u*W2
+    if (se && full) {  // through the gate: u = ds * s(1-s), dh = relu'(h) * sum_c u*W2
       for (int n = tid; n < batch; n += 128) {
         float da = 0.f;
         for (int c = 0; c < 8; ++c) {
@@ -1127,8 +1132,8 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
       for (int n = 0; n < batch; ++n) {
         const float S1 = s_S1[n * 8 + c], S2 = s_S2[n * 8 + c];
         float s = 1.f, dq = 0.f, Yh = 0.f;
-        if (se) {
-          s = saved[t.se_off + n * 8 + c];
+        if (se) s = saved[t.se_off + n * 8 + c];
+        if (se && full) {
           dq = s_dh[n] * t.w1[c];
           Yh = (saved[t.ysum_off + n * 8 + c] - t.hw * mean) * istd;
           const float h = saved[t.se_off + batch * 16 + n];
@@ -1140,9 +1145,9 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
         T += s * (g * S2 + b * S1);
       }
       s_T[c] = T, s_dg[c] = dg, s_db[c] = db;
-      if (t.g_gamma >= 0) g_params[t.g_gamma + c] = dg;
-      if (t.g_beta >= 0) g_params[t.g_beta + c] = db;
-      if (se) {
+      if (full && t.g_gamma >= 0) g_params[t.g_gamma + c] = dg;
+      if (full && t.g_beta >= 0) g_params[t.g_beta + c] = db;
+      if (se && full) {
         if (t.g_w1 >= 0) g_params[t.g_w1 + c] = dw1;
         if (t.g_w2 >= 0) g_params[t.g_w2 + c] = dw2;
       }
@@ -1151,10 +1156,10 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
     if (tid == 0) {
       float Ts = 0.f;
       for (int c = 0; c < 8; ++c) Ts += s_T[c];
-      g_alpha[t.edge * 6 + t.cand] = be * Ts;
+      if (full) g_alpha[t.edge * 6 + t.cand] = be * Ts;
       s_gbeta += w * Ts;
     }
-    if (t.has_y) {
+    if (t.has_y && full) {
       float *cf = scratch + t.coef_off;
       for (int i = tid; i < total; i += 128) {
         const int n = i >> 3, c = i & 7;
@@ -1170,7 +1175,7 @@ __global__ void __launch_bounds__(128) node_bfin_kernel(const NodeDesc *nodes, i
     }
     __syncthreads();
   }
-  if (g_beta != nullptr && tid == 0) g_beta[my_edge] = s_gbeta;
+  if (g_beta != nullptr && tid == 0 && blockIdx.y == 0) g_beta[my_edge] = s_gbeta;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1856,7 +1861,7 @@ struct DwItem {
   float *partials;    // forward: [B][gridDim.x][2C] sums / sums of squares;  weight gradient: [B][gridDim.x][C*K*K]
   const float *in2;   // weight gradient: dz [B][H][W][C]
   int64_t in_ld, out_ld;
-  int32_t k, flip, accumulate, pad_;
+  int32_t k, flip, accumulate, in2_ld;  // in2_ld: pixel stride of in2 (0 = C)
 };
 struct DwMultiArgs {
   DwItem it[kDwMaxItems];
@@ -2388,7 +2393,7 @@ template <int C, int K, bool STATS>
 SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q,
                                 float *st) {
   const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-  float *outb = it.out + (int64_t)n * 4 * H * W * C + q * 4;  // z: [2H][2W][C]
+  float *outb = it.out + (int64_t)n * 4 * H * W * it.out_ld + q * 4;  // [2H][2W][out_ld]
   const float *wq = s_w + q * 4;
   for (int i = by0; i < by1; ++i) {
     float4 xw[3][3];
@@ -2404,8 +2409,13 @@ SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H
     for (int py = 0; py < 2; ++py)
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        const float4 v = acc[py][px];
-        st4(outb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * C, v);
+        float4 v = acc[py][px];
+        float *op = outb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * it.out_ld;
+        if (it.accumulate) {
+          const float4 old = ld4(op);
+          v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
+        }
+        st4(op, v);
         if (STATS) {
           st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
           st[4] += v.x * v.x, st[5] += v.y * v.y, st[6] += v.z * v.z, st[7] += v.w * v.w;
@@ -2414,10 +2424,11 @@ SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H
   }
 }
 
-template <int C, int K>
-SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q) {
+template <int C, int K, bool STATS>
+SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q,
+                               float *st) {
   constexpr int P = K / 2;
-  const float *dzb = it.in + (int64_t)n * 4 * H * W * C + q * 4;  // dz: [2H][2W][C]
+  const float *dzb = it.in + (int64_t)n * 4 * H * W * it.in_ld + q * 4;  // high-resolution input [2H][2W][in_ld]
   float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
   const float *wq = s_w + q * 4;
   const int OH = 2 * H, OW = 2 * W;
@@ -2432,18 +2443,25 @@ SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H,
       for (int kx = 0; kx < K; ++kx) {
         const int ox = 2 * j + kx - P;
         if (ox < 0 || ox >= OW) continue;
-        fma4(acc, ld4(dzb + ((int64_t)oy * OW + ox) * C), ld4(wq + (ky * K + kx) * C));
+        fma4(acc, ld4(dzb + ((int64_t)oy * OW + ox) * it.in_ld), ld4(wq + (ky * K + kx) * C));
       }
     }
     st4(op, acc);
+    if (STATS) {
+      st[0] += acc.x, st[1] += acc.y, st[2] += acc.z, st[3] += acc.w;
+      st[4] += acc.x * acc.x, st[5] += acc.y * acc.y, st[6] += acc.z * acc.z, st[7] += acc.w * acc.w;
+    }
   }
 }
 
-// MODE 0: forward with statistics, 1: data gradient.  grid = (tiles_x * tiles_y, B), block = 128 = Q quads x 128/Q columns
-template <int C, int MODE>
+// SCATTER: low -> high resolution (4 output pixels per low-resolution pixel), else the stride-2 gather high -> low.
+//   UP   forward <C, true, true>,  data gradient <C, false, false>
+//   DOWN forward <C, false, true> (z[o] = sum x[2o + k - P] w[k]),  data gradient <C, true, false> (+= into dx)
+// a.H, a.W = the LOW-resolution grid.  grid = (tiles_x * tiles_y, B), block = 128 = Q quads x 128/Q columns
+template <int C, bool SCATTER, bool STATS>
 __global__ void __launch_bounds__(128) dw_up_multi_kernel(DwMultiArgs a) {
   constexpr int Q = C / 4, SLOTS = 128 / Q;
-  __shared__ float s_red[MODE == 0 ? 128 : 1][8];
+  __shared__ float s_red[STATS ? 128 : 1][8];
   __shared__ float4 s_w4[25 * C / 4];
   float *s_w = reinterpret_cast<float *>(s_w4);
   const int tid = threadIdx.x, q = tid % Q, slot = tid / Q, n = blockIdx.y;
@@ -2461,15 +2479,15 @@ __global__ void __launch_bounds__(128) dw_up_multi_kernel(DwMultiArgs a) {
     __syncthreads();
     float st[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (active) {
-      if (MODE == 0) {
-        if (it.k == 5) dw_up_fwd_rows<C, 5, true>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
-        else dw_up_fwd_rows<C, 3, true>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
+      if (SCATTER) {
+        if (it.k == 5) dw_up_fwd_rows<C, 5, STATS>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
+        else dw_up_fwd_rows<C, 3, STATS>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
       } else {
-        if (it.k == 5) dw_up_dx_rows<C, 5>(it, s_w, n, a.H, a.W, by0, by1, j, q);
-        else dw_up_dx_rows<C, 3>(it, s_w, n, a.H, a.W, by0, by1, j, q);
+        if (it.k == 5) dw_up_dx_rows<C, 5, STATS>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
+        else dw_up_dx_rows<C, 3, STATS>(it, s_w, n, a.H, a.W, by0, by1, j, q, st);
       }
     }
-    if (MODE == 0) {
+    if (STATS) {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) s_red[tid][jj] = st[jj];
       __syncthreads();
@@ -2483,7 +2501,8 @@ __global__ void __launch_bounds__(128) dw_up_multi_kernel(DwMultiArgs a) {
   }
 }
 
-// weight gradient of the same group; partial layout [C][K*K] per block like dw_wgrad_multi_kernel
+// weight gradient of the same group (in = low-resolution operand, in2 = high-resolution operand: UP x / dz, DOWN dz / x);
+// partial layout [C][K*K] per block like dw_wgrad_multi_kernel
 template <int C, int K>
 SENAS_DEVFN void dw_up_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, int by1, int j, int q, bool active,
                                   float *s_part, int nblk_idx) {
@@ -2492,15 +2511,16 @@ SENAS_DEVFN void dw_up_wgrad_rows(const DwItem &it, int n, int H, int W, int by0
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = f4zero();
   if (active) {
+    const int64_t ld2 = it.in2_ld ? it.in2_ld : C;
     const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-    const float *dzb = it.in2 + (int64_t)n * 4 * H * W * C + q * 4;
+    const float *dzb = it.in2 + (int64_t)n * 4 * H * W * ld2 + q * 4;
     for (int i = by0; i < by1; ++i) {
       float4 xw[3][3], dz[2][2];
       up_load_window(inb, it.in_ld, H, W, i, j, xw);
 #pragma unroll
       for (int py = 0; py < 2; ++py)
 #pragma unroll
-        for (int px = 0; px < 2; ++px) dz[py][px] = ld4(dzb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * C);
+        for (int px = 0; px < 2; ++px) dz[py][px] = ld4(dzb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * ld2);
 #pragma unroll
       for (int ky = 0; ky < K; ++ky)
 #pragma unroll
