@@ -172,6 +172,7 @@ struct TermPlan {
   int nblk = 0, nblk1 = 0;
   int64_t scale_off = -1, coef_off = -1;
   bool tc = false;  // forward runs in a tcgen05 group (bf16 operands)
+  bool dwg = false; // dep-sep: depthwise half runs in the grouped row-walk kernels (all but DOWN on odd-sized maps)
 };
 struct TcGroup {
   int src, op, kind, k, dil, nterms;
@@ -326,8 +327,10 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
+          t.dwg = ed.op_type != SENAS_OP_DOWN || (ep.in_h == 2 * p->out_h && ep.in_w == 2 * p->out_w && C == 32);
           if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false);  // dw_multi_kernel grid
           if (ed.op_type == SENAS_OP_UP) t.nblk1 = dw_nblk(C, B, bh, bw, true);     // dw_up_multi_kernel grid (input grid)
+          if (ed.op_type == SENAS_OP_DOWN && t.dwg) t.nblk1 = dw_nblk(C, B, p->out_h, p->out_w, true);  // (output grid)
           t.nblk = cdiv(HW, kPwPx);  // pw_fwd_kernel grid
           t.z_off = take(sv, (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -335,8 +338,9 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int64_t pw_tmp = (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
           const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
-          if (ed.op_type != SENAS_OP_DOWN)  // grouped weight gradient: one partial per block and convolution
-            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * dw_nblk(C, B, bh, bw, true) * kDwMaxItems * C * 25);
+          if (t.dwg)  // grouped weight gradient: one partial per block and convolution
+            tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * dw_nblk(C, B, ed.op_type == SENAS_OP_DOWN ? p->out_h : bh,
+                                                                        ed.op_type == SENAS_OP_DOWN ? p->out_w : bw, true) * kDwMaxItems * C * 25);
           break;
         }
         default:
@@ -694,25 +698,26 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
   DwMultiArgs a;
   memset(&a, 0, sizeof(a));
   int C = 0, h = 0, w = 0, nblk = 0;
-  bool up = false;  // every edge that reads a state has the same op type (cell.py:76-90)
+  bool up = false, down = false;  // every edge that reads a state has the same op type (cell.py:76-90)
   int64_t x_ld = 0;
   const float *x = state_ptr(c, src, &x_ld);
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || (only_edge >= 0 && e != only_edge) || ed.op_type == SENAS_OP_DOWN) continue;
-    up = ed.op_type == SENAS_OP_UP;
+    if (ed.src != src || (only_edge >= 0 && e != only_edge)) continue;
+    up = ed.op_type == SENAS_OP_UP, down = ed.op_type == SENAS_OP_DOWN;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
-      if (t.kind != SENAS_KIND_DEPSEP) continue;
+      if (t.kind != SENAS_KIND_DEPSEP || !t.dwg) continue;
       if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
       DwItem &it = a.it[a.n++];
       it.in = x, it.in_ld = x_ld, it.out = c.saved + t.z_off, it.out_ld = ed.c_in;
       it.w = (const float *)ed.param[k][0], it.partials = c.scratch + t.part1_off, it.k = t.k;
-      C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk1;
+      C = ed.c_in, h = down ? p.out_h : p.edges[e].in_h, w = down ? p.out_w : p.edges[e].in_w, nblk = t.nblk1;
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, up), a.tile_rows = dw_rows(C, c.B, h, w, up);
+  const bool col1 = up || down;  // one column per thread, tiles on the low-resolution grid
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1), a.tile_rows = dw_rows(C, c.B, h, w, col1);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   void *st = c.S.stream(c.S.pick());
@@ -720,7 +725,10 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
   dim3 grid(nblk, c.B);
   if (up) {
     if (C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
-    auto kern = dw_up_multi_kernel<32, 0>;
+    auto kern = dw_up_multi_kernel<32, true, true>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  } else if (down) {  // z[o] = sum x[2o + k - P] w[k]: the stride-2 gather, with statistics
+    auto kern = dw_up_multi_kernel<32, false, true>;
     SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
   } else if (C == 32) {
     auto kern = dw_multi_kernel<32, true>;
@@ -828,7 +836,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         break;
       }
       case SENAS_KIND_DEPSEP: {
-        if (ed.op_type != SENAS_OP_DOWN) break;  // forward_dw_group
+        if (t.dwg) break;  // forward_dw_group
         Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
         DwArgs a;
         a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.z = c.saved + t.z_off;
@@ -1180,7 +1188,7 @@ static int backward_edge(BwdCall &c, int e) {
           auto kern = pw_bwd_q_kernel<8, 2>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
-        if (ed.op_type != SENAS_OP_DOWN) {  // data / weight gradient of the depthwise half: backward_dw_group
+        if (t.dwg) {  // data / weight gradient of the depthwise half: backward_dw_group
           c.dw_wait[ed.src].push_back(ln);
           break;
         }
@@ -1278,27 +1286,28 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   DwMultiArgs a;
   memset(&a, 0, sizeof(a));
   int C = 0, h = 0, w = 0, nblk = 0;
-  bool up = false;
+  bool up = false, down = false;
   int64_t x_ld = 0;
   const float *x = state_ptr(c, src, &x_ld);
   int64_t goff[kDwMaxItems];
   for (int e = 0; e < d.n_edges; ++e) {
     const senas_edge_desc_t &ed = d.edge[e];
-    if (ed.src != src || (only_edge >= 0 && e != only_edge) || ed.op_type == SENAS_OP_DOWN) continue;
-    up = ed.op_type == SENAS_OP_UP;
+    if (ed.src != src || (only_edge >= 0 && e != only_edge)) continue;
+    up = ed.op_type == SENAS_OP_UP, down = ed.op_type == SENAS_OP_DOWN;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
-      if (t.kind != SENAS_KIND_DEPSEP) continue;
+      if (t.kind != SENAS_KIND_DEPSEP || !t.dwg) continue;
       if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
       goff[a.n] = ed.grad_off[k][0];
       DwItem &it = a.it[a.n++];
       it.in = c.saved + t.z_off, it.in_ld = ed.c_in;  // dz (in place over z)
-      it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = up ? 0 : 1;
-      C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk1;
+      it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = (up || down) ? 0 : 1;
+      C = ed.c_in, h = down ? p.out_h : p.edges[e].in_h, w = down ? p.out_w : p.edges[e].in_w, nblk = t.nblk1;
     }
   }
   if (a.n == 0) return 0;
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, up), a.tile_rows = dw_rows(C, c.B, h, w, up);
+  const bool col1 = up || down;  // tiles on the low-resolution grid, one column per thread
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1), a.tile_rows = dw_rows(C, c.B, h, w, col1);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   dim3 grid(nblk, c.B);
@@ -1313,7 +1322,10 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
       g.it[m].out = dx, g.it[m].out_ld = c.dstate_ld[src], g.it[m].accumulate = (m > 0 || c.touched[src]) ? 1 : 0;
     SENAS_TAG("dw_dx", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
     if (up) {
-      auto kern = dw_up_multi_kernel<32, 1>;
+      auto kern = dw_up_multi_kernel<32, false, false>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    } else if (down) {  // dx[2i + p] += sum dz[i + d] w: the scatter onto the high-resolution grid
+      auto kern = dw_up_multi_kernel<32, true, false>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
     } else if (C == 32) {
       auto kern = dw_multi_kernel<32, false>;
@@ -1332,10 +1344,15 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     nblk = dw_nblk(C, c.B, h, w, true);
     grid = dim3(nblk, c.B);
     const int64_t per = (int64_t)c.B * nblk * C * 25;
-    for (int m = 0; m < g.n; ++m)
-      g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld, g.it[m].flip = 0, g.it[m].partials = tmp + m * per;
+    for (int m = 0; m < g.n; ++m) {
+      g.it[m].flip = 0, g.it[m].partials = tmp + m * per;
+      if (down)  // low-resolution operand = dz (already in .in), high-resolution operand = x
+        g.it[m].in2 = x, g.it[m].in2_ld = (int32_t)x_ld;
+      else
+        g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld;
+    }
     SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
-    if (up) {
+    if (up || down) {
       auto kern = dw_up_wgrad_multi_kernel<32>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
     } else if (C == 32) {
