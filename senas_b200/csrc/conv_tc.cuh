@@ -44,6 +44,7 @@ struct TcConvArgs {
   int32_t P, S;                  // staged pixels per row (even), ring slots
   int32_t img_mul, img_add;      // image index of the TMA source = n * img_mul + img_add (phase-major packed dy of UP)
   int32_t M;                     // pixels per MMA = strip width: 128, or 64 for maps that are a multiple of 64 wide only
+  int32_t acc_y, no_stats;       // mode 0 in several launches (DOWN: one per input phase): y += , statistics on the last
   TapTable taps;
 };
 
@@ -276,6 +277,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
           for (int g = 0; g < kTcMaxTerms; ++g) {
             if (g < a.nterms) {
               float *o = a.y[g] + pix * 8;
+              if (a.acc_y) {
+                const float4 lo = ld4(o), hi = ld4(o + 4);
+                v[g * 8] += lo.x, v[g * 8 + 1] += lo.y, v[g * 8 + 2] += lo.z, v[g * 8 + 3] += lo.w;
+                v[g * 8 + 4] += hi.x, v[g * 8 + 5] += hi.y, v[g * 8 + 6] += hi.z, v[g * 8 + 7] += hi.w;
+              }
               st4(o, make_float4(v[g * 8], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]));
               st4(o + 4, make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]));
             }
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
     }
   }
   __syncthreads();
-  if (tid < 64 && a.mode == 0) {
+  if (tid < 64 && a.mode == 0 && !a.no_stats) {
     const float r = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
     const int which = tid >> 5, col = tid & 31, g = col >> 3, c = col & 7;
     if (g < a.nterms) a.partials[g][((int64_t)n * gridDim.x + blockIdx.x) * 16 + which * 8 + c] = r;
@@ -312,16 +318,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
   }
 }
 
-// fp32 NHWC (any pixel stride) -> dense bf16 NHWC, 32 channels; thread = (pixel, 8-channel plane)
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float *src, int64_t ld, __nv_bfloat16 *dst, int64_t npix) {
+// fp32 NHWC (any pixel stride) -> dense bf16 NHWC, 32 channels; thread = (pixel, 8-channel plane).
+// ph_h > 0 (inputs of DOWN groups, H = 2 ph_h, W = 2 ph_w): the copy is PHASE-MAJOR, [B][4][ph_h][ph_w][32] with
+// dst[n][2 py + px][i][j] = src[n][2i + py][2j + px], so that a stride-2 tap is a stride-1 tap inside one phase image.
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float *src, int64_t ld, __nv_bfloat16 *dst, int64_t npix,
+                                                        int ph_h, int ph_w) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= npix * 4) return;
-  const int64_t pix = i >> 2;
+  const int64_t dpix = i >> 2;
   const int pl = (int)(i & 3);
+  int64_t pix = dpix;
+  if (ph_h > 0) {
+    const int64_t hw = (int64_t)ph_h * ph_w, n = dpix / (4 * hw), r = dpix - n * 4 * hw;
+    const int ph = (int)(r / hw), ij = (int)(r - ph * hw), ii = ij / ph_w, jj = ij - ii * ph_w;
+    pix = (n * 2 * ph_h + 2 * ii + (ph >> 1)) * (2 * ph_w) + 2 * jj + (ph & 1);
+  }
   const float4 lo = ld4(src + pix * ld + pl * 8), hi = ld4(src + pix * ld + pl * 8 + 4);
   __align__(16) __nv_bfloat16 v[8] = {__float2bfloat16(lo.x), __float2bfloat16(lo.y), __float2bfloat16(lo.z), __float2bfloat16(lo.w),
                                       __float2bfloat16(hi.x), __float2bfloat16(hi.y), __float2bfloat16(hi.z), __float2bfloat16(hi.w)};
-  *reinterpret_cast<uint4 *>(dst + pix * 32 + pl * 8) = *reinterpret_cast<const uint4 *>(v);
+  *reinterpret_cast<uint4 *>(dst + dpix * 32 + pl * 8) = *reinterpret_cast<const uint4 *>(v);
 }
 
 // dy of up to 4 grouped terms -> one dense bf16 NHWC tensor [B][hw][32] (channels g*8.. = dy of term g, rest 0),
@@ -376,6 +391,7 @@ struct TcWgradArgs {
   int32_t Wt;                // strip width in pixels (= GEMM-K per row): 128 or 64
   int32_t t_begin, t_count;  // taps [t_begin, t_begin + t_count) of the table
   int32_t dy_img_mul, dy_img_add;  // image index of the dy rows = n * dy_img_mul + dy_img_add
+  int32_t x_img_mul, x_img_add;    // same for the x rows (phase-major x of DOWN groups)
   float *partials;           // [B * gridDim.x][t_count][32 ci][32 m]
   TapTable taps;
 };
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
           const int slot = idx & (a.S - 1), use = idx / a.S;
           if (use > 0) mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
           mbar_expect_tx(&full[slot], row_bytes);
-          tma_load_5d(rows + (size_t)slot * row_bytes, &tmap_x, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n);
+          tma_load_5d(rows + (size_t)slot * row_bytes, &tmap_x, &full[slot], 0, x0 + a.taps.min_dx, y, 0, n * a.x_img_mul + a.x_img_add);
         }
         const int ds = it & (kTcDySlots - 1), duse = it / kTcDySlots;
         if (duse > 0) mbar_wait(&dempty[ds], (uint32_t)((duse - 1) & 1));
@@ -577,18 +593,18 @@ static int tc_encode(CUtensorMap *tmap, const __nv_bfloat16 *p, int B, int H, in
 // floats.  dy rows come from image n * dy_mul + dy_add of dyb (NORM: 1, 0; UP: 4, phase).
 static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dyb, int B, int H, int W, const TapTable &taps,
                                 int t0, int t1, int dy_mul, int dy_add, float *partials, float *const *dst, int nterms,
-                                int ws_ci, int ws_co, void *stream) {
+                                int ws_ci, int ws_co, void *stream, int x_mul = 1, int x_add = 0) {
   TcWgradArgs a;
   memset(&a, 0, sizeof(a));
   a.H = H, a.W = W, a.rows_per_cta = tc_rows(H, W, B, taps.max_dy - taps.min_dy);
   a.row_chunks = (H + a.rows_per_cta - 1) / a.rows_per_cta, a.taps = taps, a.partials = partials;
-  a.dy_img_mul = dy_mul, a.dy_img_add = dy_add;
+  a.dy_img_mul = dy_mul, a.dy_img_add = dy_add, a.x_img_mul = x_mul, a.x_img_add = x_add;
   a.Wt = tc_strip(W);
   if (a.Wt == 0) return 1;
   a.P = (a.Wt + taps.max_dx - taps.min_dx + 1) & ~1, a.S = 16;
   const size_t smem = (size_t)a.S * a.P * 64 + (size_t)(kTcDySlots + 1) * 8192 + (size_t)(2 * a.S + 2 * kTcDySlots + 2) * 8 + 64;
   CUtensorMap mx, md;
-  if (tc_encode(&mx, xb, B, H, W, a.P) || tc_encode(&md, dyb, B * dy_mul, H, W, a.Wt)) return 2;
+  if (tc_encode(&mx, xb, B * x_mul, H, W, a.P) || tc_encode(&md, dyb, B * dy_mul, H, W, a.Wt)) return 2;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 2;

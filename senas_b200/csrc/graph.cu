@@ -135,6 +135,36 @@ static Geo make_geo(int k, int dil, int op, int dir) {
   return g;
 }
 
+// A stride-2 (DOWN) convolution on a PHASE-MAJOR copy of its input: tap offset `off` (input pixels) reads phase
+// (off_y & 1, off_x & 1) at offset (floor(off_y / 2), floor(off_x / 2)) of that phase image, so the conv is the sum over
+// the 4 input phases of ordinary stride-1 convs on the output grid.  out[ph] = single-phase table of phase ph.
+static void down_phase_tables(const TapTable &fwd, TapTable out[4]) {
+  for (int ph = 0; ph < 4; ++ph) {
+    TapTable &t = out[ph];
+    memset(&t, 0, sizeof(t));
+    t.nphase = 1;
+    t.min_dy = t.min_dx = 1000, t.max_dy = t.max_dx = -1000;
+    for (int q = 0; q < fwd.n; ++q) {
+      const int oy = fwd.dy[q], ox = fwd.dx[q];
+      if ((((oy & 1) << 1) | (ox & 1)) != ph) continue;
+      const int dy = (oy - (oy & 1)) / 2, dx = (ox - (ox & 1)) / 2;  // floor division
+      t.dy[t.n] = (int8_t)dy, t.dx[t.n] = (int8_t)dx, t.widx[t.n] = fwd.widx[q], t.phase[t.n] = 0;
+      t.min_dy = std::min(t.min_dy, dy), t.max_dy = std::max(t.max_dy, dy);
+      t.min_dx = std::min(t.min_dx, dx), t.max_dx = std::max(t.max_dx, dx);
+      ++t.n;
+    }
+    if (t.n == 0) t.min_dy = t.max_dy = t.min_dx = t.max_dx = 0;
+    t.pstart[0] = 0;
+    for (int q = 1; q <= 4; ++q) t.pstart[q] = t.n;
+  }
+}
+static int down_last_phase(const TapTable t[4]) {
+  int last = 0;
+  for (int ph = 0; ph < 4; ++ph)
+    if (t[ph].n) last = ph;
+  return last;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
@@ -254,8 +284,10 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
   if (d.reserved & 1) {  // SENAS_FLAG_TC_BF16: group equal candidates of edges that share an input
     for (int e = 0; e < d.n_edges; ++e) {
       const senas_edge_desc_t &ed = d.edge[e];
-      if (ed.src >= d.n_inputs || ed.c_in != 32 || ed.op_type == SENAS_OP_DOWN) continue;
-      const int strip = tc_strip(p->edges[e].in_w);
+      if (ed.src >= d.n_inputs || ed.c_in != 32) continue;
+      const bool down = ed.op_type == SENAS_OP_DOWN;  // DOWN: strips on the output grid, even-sized inputs only
+      if (down && (p->edges[e].in_h != 2 * p->out_h || p->edges[e].in_w != 2 * p->out_w)) continue;
+      const int strip = tc_strip(down ? p->out_w : p->edges[e].in_w);
       if (strip == 0) continue;
       for (int k = 0; k < SENAS_MAX_CAND; ++k) {
         if (ed.kind[k] != SENAS_KIND_CONV && ed.kind[k] != SENAS_KIND_SE_CONV) continue;
@@ -280,7 +312,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
     }
     for (auto &g2 : p->tc_groups) {
       if (p->xb_off[g2.src] < 0) p->xb_off[g2.src] = take(sv, (int64_t)B * ih[g2.src] * iw[g2.src] * 16);
-      tmp_need = std::max<int64_t>(tmp_need, (int64_t)std::max(592, B * (iw[g2.src] / tc_strip(iw[g2.src]))) * kTcWTaps * 1024);
+      tmp_need = std::max<int64_t>(tmp_need, (int64_t)std::max(592, B * 4) * kTcWTaps * 1024);
     }
   }
 #endif
@@ -317,7 +349,14 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk = cdiv(bh, kTileH) * cdiv(bw, kTileW * gather_pix(8, geo.si, bw));
-          if (t.tc) t.nblk = (ep.in_w / tc_strip(ep.in_w)) * cdiv(ep.in_h, tc_rows(ep.in_h, ep.in_w, B, geo.taps.max_dy - geo.taps.min_dy));
+          if (t.tc && ed.op_type == SENAS_OP_DOWN) {  // statistics come from the launch of the last non-empty phase
+            TapTable pt[4];
+            down_phase_tables(geo.taps, pt);
+            const TapTable &lt = pt[down_last_phase(pt)];
+            t.nblk = (p->out_w / tc_strip(p->out_w)) * cdiv(p->out_h, tc_rows(p->out_h, p->out_w, B, lt.max_dy - lt.min_dy));
+          } else if (t.tc) {
+            t.nblk = (ep.in_w / tc_strip(ep.in_w)) * cdiv(ep.in_h, tc_rows(ep.in_h, ep.in_w, B, geo.taps.max_dy - geo.taps.min_dy));
+          }
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)148 * 6 * T * C * 8);
           if (t.kind == SENAS_KIND_SE_CONV) t.ysum_off = take(sv, B * 8), t.se_off = take(sv, B * 17);
           break;
@@ -911,8 +950,11 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     if (p->xb_off[i] < 0) continue;
     const int64_t npix = (int64_t)c.B * p->in_h[i] * p->in_w[i];
     SENAS_TAG("cast_bf16", 0, 6.0 * npix * 32);
+    bool down = false;  // inputs of DOWN groups get the phase-major copy
+    for (const TcGroup &g2 : p->tc_groups) down |= g2.src == i && g2.op == SENAS_OP_DOWN;
     SENAS_LAUNCH(cast_bf16_kernel, dim3((unsigned)((npix * 4 + 255) / 256)), dim3(256), 0, c.stream, a->in[i], a->in_ld[i],
-                 reinterpret_cast<__nv_bfloat16 *>(c.saved + p->xb_off[i]), npix);
+                 reinterpret_cast<__nv_bfloat16 *>(c.saved + p->xb_off[i]), npix, down ? p->in_h[i] / 2 : 0,
+                 down ? p->in_w[i] / 2 : 0);
   }
 #endif
   c.S.fork();
@@ -930,13 +972,33 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     }
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ta.ws_k, &ta.ws_n);
+    const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]);
+    void *gst = c.S.stream(c.S.pick());
+    if (g2.op == SENAS_OP_DOWN) {  // one launch per non-empty input phase, accumulating into y; statistics on the last
+      TapTable pt[4];
+      down_phase_tables(geo.taps, pt);
+      const int last = down_last_phase(pt);
+      bool first = true;
+      ta.H = p->out_h, ta.W = p->out_w, ta.Ho = p->out_h, ta.Wo = p->out_w, ta.so = 1, ta.img_mul = 4;
+      for (int ph = 0; ph < 4; ++ph) {
+        if (pt[ph].n == 0) continue;
+        ta.taps = pt[ph], ta.img_add = ph, ta.acc_y = first ? 0 : 1, ta.no_stats = ph == last ? 0 : 1;
+        ta.rows_per_cta = tc_rows(p->out_h, p->out_w, c.B, pt[ph].max_dy - pt[ph].min_dy);
+        ta.row_chunks = cdiv(p->out_h, ta.rows_per_cta);
+        SENAS_TAG("conv_tc_fwd", 2.0 * c.B * p->hw * pt[ph].n * 32 * 8 * g2.nterms,
+                  2.0 * c.B * p->hw * 32 + 4.0 * c.B * p->hw * 8 * g2.nterms);
+        const int rc = launch_conv_tc(xb, c.B, ta, gst);
+        if (rc) SENAS_FAIL("tcgen05 conv launch failed (code %d)", rc);
+        first = false;
+      }
+      continue;
+    }
     ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = p->out_h, ta.Wo = p->out_w, ta.so = geo.so;
     ta.rows_per_cta = tc_rows(ep0.in_h, ep0.in_w, c.B, geo.taps.max_dy - geo.taps.min_dy);
     ta.row_chunks = cdiv(ep0.in_h, ta.rows_per_cta), ta.taps = geo.taps;
     SENAS_TAG("conv_tc_fwd", 2.0 * c.B * ep0.in_h * ep0.in_w * geo.taps.n * 32 * 8 * g2.nterms,
               2.0 * c.B * ep0.in_h * ep0.in_w * 32 + 4.0 * c.B * p->hw * 8 * g2.nterms);
-    const int rc = launch_conv_tc(reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]), c.B, ta,
-                                  c.S.stream(c.S.pick()));
+    const int rc = launch_conv_tc(xb, c.B, ta, gst);
     if (rc) SENAS_FAIL("tcgen05 conv launch failed (code %d)", rc);
   }
 #endif
@@ -1447,15 +1509,18 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
   for (size_t gi = 0; gi < p->tc_groups.size(); ++gi) {
     const TcGroup &g2 = p->tc_groups[gi];
     if (!a->grad_in[g2.src]) continue;
-    const bool up = g2.op == SENAS_OP_UP;
+    const bool up = g2.op == SENAS_OP_UP, down = g2.op == SENAS_OP_DOWN;
     const EdgePlan &ep0 = p->edges[g2.edge[0]];
-    const int64_t npix = (int64_t)c.B * ep0.in_h * ep0.in_w;
+    // grid of the GEMM-M pixels: the input grid (NORM: = output grid; UP: the 4 output phases live on it), or, for DOWN,
+    // the output grid (the 4 INPUT phases live on it)
+    const int gh = down ? p->out_h : ep0.in_h, gw = down ? p->out_w : ep0.in_w;
+    const int64_t npix = (int64_t)c.B * gh * gw;
     __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off[gi]);
     const int ln = c.S.pick(), dxl = c.S.dx_lane(g2.src);
     void *st = c.S.stream(ln);
     PackDyArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.nterms = g2.nterms, pa.hw = ep0.in_h * ep0.in_w, pa.batch = c.B, pa.dst = dyb;
+    pa.nterms = g2.nterms, pa.hw = gh * gw, pa.batch = c.B, pa.dst = dyb;
     if (up) pa.up_h = ep0.in_h, pa.up_w = ep0.in_w;
     TcConvArgs ta;
     memset(&ta, 0, sizeof(ta));
@@ -1474,10 +1539,12 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     const Geo gf = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);
-    ta.H = ep0.in_h, ta.W = ep0.in_w, ta.Ho = ep0.in_h, ta.Wo = ep0.in_w, ta.so = 1;
+    ta.H = gh, ta.W = gw, ta.Ho = ep0.in_h, ta.Wo = ep0.in_w, ta.so = down ? 2 : 1;
     ta.out32 = a->grad_in[g2.src], ta.out_ld = a->grad_in_ld[g2.src];
     for (int ph = 0; ph < nph; ++ph) {
-      if (up) {  // mirrored taps of this output phase, as a single-phase table on the input grid
+      if (down) {  // dx[2i + p] = sum_{t in p} dy[i + d_t] W_t^T: the 4-phase table in ONE launch (as the UP forward)
+        ta.taps = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD).taps, ta.img_mul = 1, ta.img_add = 0;
+      } else if (up) {  // mirrored taps of this output phase, as a single-phase table on the input grid
         const int t0 = gf.taps.pstart[ph], t1 = gf.taps.pstart[ph + 1];
         if (t1 == t0) continue;
         TapTable tt;
@@ -1496,8 +1563,8 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       } else {
         ta.taps = make_geo(g2.k, g2.dil, g2.op, DIR_DGRAD).taps, ta.img_mul = 1, ta.img_add = 0;
       }
-      ta.rows_per_cta = tc_rows(ep0.in_h, ep0.in_w, c.B, ta.taps.max_dy - ta.taps.min_dy);
-      ta.row_chunks = cdiv(ep0.in_h, ta.rows_per_cta);
+      ta.rows_per_cta = tc_rows(gh, gw, c.B, ta.taps.max_dy - ta.taps.min_dy);
+      ta.row_chunks = cdiv(gh, ta.rows_per_cta);
       ta.accumulate = c.touched[g2.src];
       SENAS_TAG("conv_tc_dgrad", 2.0 * npix * ta.taps.n * 32 * 8 * g2.nterms, 2.0 * npix * 32 + 8.0 * npix * 32);
       const int rc = launch_conv_tc(dyb, c.B, ta, c.S.stream(dxl));
@@ -1511,7 +1578,16 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       int ws_ci, ws_co;
       conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_FWD, &ws_ci, &ws_co);
       const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(c.saved + p->xb_off[g2.src]);
-      for (int ph = 0; ph < nph; ++ph) {
+      TapTable pt[4];
+      if (down) down_phase_tables(gf.taps, pt);
+      for (int ph = 0; ph < (down ? 4 : nph); ++ph) {
+        if (down) {  // dW_t = sum_o x_ph(t)[o + d_t]^T dy[o]: x rows from phase image 4n + ph
+          if (pt[ph].n == 0) continue;
+          const int rcw = launch_conv_tc_wgrad(xb, dyb, c.B, gh, gw, pt[ph], 0, pt[ph].n, 1, 0, c.tmp(ln), dst, g2.nterms,
+                                               ws_ci, ws_co, st, 4, ph);
+          if (rcw) SENAS_FAIL("tcgen05 wgrad launch failed (code %d)", rcw);
+          continue;
+        }
         const int t0 = up ? gf.taps.pstart[ph] : 0, t1 = up ? gf.taps.pstart[ph + 1] : gf.taps.n;
         if (t1 == t0) continue;
         const int rcw = launch_conv_tc_wgrad(xb, dyb, c.B, ep0.in_h, ep0.in_w, gf.taps, t0, t1, up ? 4 : 1, up ? ph : 0,

@@ -296,7 +296,7 @@ def bf16_mode():
 
 
 @pytest.mark.parametrize('op_id,B,H,W', [(3, 2, 24, 128), (1, 2, 10, 128), (3, 1, 40, 256), (3, 2, 24, 64), (1, 2, 10, 64),
-                                          (3, 1, 9, 192)])
+                                          (3, 1, 9, 192), (2, 2, 20, 128), (2, 1, 12, 256)])
 def test_mixed_op_bf16_tensor_core(bf16_mode, op_id, B, H, W):
     torch.manual_seed(200 + op_id + H)
     m = senas_b200.MixedOp(32, 8, OP_BY_ID[op_id])
@@ -479,3 +479,43 @@ def test_deferred_weight_gradient_lanes_same_result():
     got, want = run(True, True)
     for n in got:
         assert max_err(got[n], want[n]) <= 1e-4, n
+
+
+def test_down_cell_bf16_tensor_core(bf16_mode):
+    """Down cell with 128-wide inputs: the DOWN edges 0/2/5 (in0) and 1/3/6 (in1) run as 3-edge tcgen05 groups on the
+    PHASE-MAJOR bf16 copy of their input (forward: one launch per input phase accumulating into y, statistics on the
+    last; data gradient: the 4-phase table in one launch; weight gradient per phase).  bf16-representable operands, so
+    the forward is exact up to accumulation order and every gradient meets the 2e-2 gate (see the up-cell test)."""
+    torch.manual_seed(13)
+    c = senas_b200.Cell(3, 1, 32, 32, 32, 'down')
+    c.apply(senas_b200.weights_init)
+    in0, in1 = torch.randn(2, 32, 16, 128).bfloat16().float(), torch.randn(2, 32, 16, 128).bfloat16().float()
+    with torch.no_grad():
+        for e in (0, 1, 2, 3, 5, 6):
+            for k in (1, 2, 3):
+                w = c._ops[e]._ops[k][0].weight
+                w.copy_(w.bfloat16().float())
+    store = oracle.clone_store(c.state_dict())
+    wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
+    b = torch.softmax(torch.randn(9), -1)
+    t = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    ref = oracle.cell_nodes(oracle.Params(store), 'down', *t)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    c = c.to(DEV)
+    g = [v.to(DEV).requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    lib = senas_b200._lib.get()
+    lib.senas_profile(1)
+    out = c.nodes(*g)
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    lib.senas_profile(0)
+    prof = senas_b200._lib.profile_dump(lib)
+    assert {'conv_tc_fwd', 'conv_tc_dgrad', 'conv_tc_wgrad'} <= set(prof), sorted(prof)
+    assert not any(k.endswith('.down') for k in prof), sorted(prof)  # no CUDA-core DOWN conv left
+    check('cat', out, ref.detach(), 1e-4)
+    check('gin0', g[0].grad, t[0].grad, 2e-2)
+    check('gin1', g[1].grad, t[1].grad, 2e-2)
+    check('gbetas', g[4].grad, t[4].grad, 2e-2)
+    for n, p in c._ops.named_parameters():
+        check('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 6e-2 if 'excitation' in n else 3e-2)
