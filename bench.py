@@ -158,6 +158,10 @@ class ClockSampler:
 # our arm
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
+    # libraries print banners on stdout at fd level ("NCCL version ..."): keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import senas_b200
@@ -341,7 +345,10 @@ def run_ours(args, rank, world, local_rank):
         out['cpu_baseline'] = {'value': args.ref_batch / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                'sample': f'2 search steps of the full supernet at batch {args.ref_batch}, '
                                          f'1x{size}x{size}, fp32, all host threads, oracle port of the reference'}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
