@@ -176,6 +176,7 @@ static int env_flag(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
+static const int g_split_lanes = env_flag("SENAS_SPLIT_LANES", 1);  // backward: chain lanes / weight-gradient lanes (A/B)
 static const int g_dw_fwd_per_edge = env_flag("SENAS_DW_FWD_EDGE", 1);  // same for the forward (measured: 102.4 -> 101.4 ms)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -549,7 +550,14 @@ static LaneSet *lanes_for(int slot) {
   auto it = sets.find(key);
   if (it != sets.end()) return it->second;
   LaneSet *ls = new LaneSet();
-  for (int i = 0; i < kAllLanes; ++i) cudaStreamCreateWithFlags(&ls->s[i], cudaStreamNonBlocking);
+  // backward: lanes [0, n/2) carry the chains that feed a data gradient (statistics -> dz, packed dy) and the dx lanes
+  // carry the data gradients themselves: both are on the critical path of the next node / the caller and get the high
+  // stream priority; lanes [n/2, n) carry weight gradients that nothing waits for (low priority).  Priorities are
+  // captured into the graph's kernel nodes.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  for (int i = 0; i < kAllLanes; ++i)
+    cudaStreamCreateWithPriority(&ls->s[i], cudaStreamNonBlocking, (i >= kLanes / 2 && i < kLanes) ? prio_lo : prio_hi);
   for (int i = 0; i < kEventPool; ++i) cudaEventCreateWithFlags(&ls->ev[i], cudaEventDisableTiming);
   sets[key] = ls;
   g_lane_sets.push_back(ls);
@@ -608,6 +616,22 @@ struct Sched {
     if (n == 0) return -1;
     const int l = rr;
     rr = (rr + 1) % n;
+    return l;
+  }
+  // backward: chain lanes (first half) / background lanes for weight gradients (second half)
+  int rr_chain = 0, rr_bg = 0;
+  int pick_chain() {
+    if (n == 0) return -1;
+    if (n < 2 || !g_split_lanes) return pick();
+    const int l = rr_chain;
+    rr_chain = (rr_chain + 1) % (n / 2);
+    return l;
+  }
+  int pick_bg() {
+    if (n == 0) return -1;
+    if (n < 2 || !g_split_lanes) return pick();
+    const int l = n / 2 + rr_bg;
+    rr_bg = (rr_bg + 1) % (n - n / 2);
     return l;
   }
   int dx_lane(int state) const { return n == 0 ? -1 : kLanes + state; }
@@ -1072,7 +1096,10 @@ static int backward_edge(BwdCall &c, int e) {
   for (int k = 0; k < SENAS_MAX_CAND; ++k) {
     const TermPlan &t = ep.t[k];
     if (!t.has_y) continue;
-    const int ln = c.S.pick();            // the candidate's own chain (statistics, weight gradients, reductions)
+    // dep-sep / quad adapters start with a chain that feeds the data gradient; conv / old adapters only have a weight
+    // gradient left on their lane
+    const bool chain = t.kind == SENAS_KIND_DEPSEP || ((t.kind == SENAS_KIND_IDENTITY || t.kind == SENAS_KIND_UP_SAMPLE) && C == 32);
+    const int ln = chain ? c.S.pick_chain() : c.S.pick_bg();
     void *st = c.S.stream(ln);
     float *tmp = c.tmp(ln);
     int64_t y_ld = 8;
@@ -1375,7 +1402,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   dim3 grid(nblk, c.B);
   if (up && C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
   float *dx = c.dstate[src];
-  const int dxl = c.S.dx_lane(src), ln = c.S.pick();
+  const int dxl = c.S.dx_lane(src), ln = c.S.pick_bg();
   for (int l : c.dw_wait[src]) c.S.dep(l, dxl), c.S.dep(l, ln);
   c.dw_wait[src].clear();
   if (dx) {
@@ -1516,7 +1543,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     const int gh = down ? p->out_h : ep0.in_h, gw = down ? p->out_w : ep0.in_w;
     const int64_t npix = (int64_t)c.B * gh * gw;
     __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(c.scratch + p->dyb_off[gi]);
-    const int ln = c.S.pick(), dxl = c.S.dx_lane(g2.src);
+    const int lp = c.S.pick_chain(), ln = c.S.pick_bg(), dxl = c.S.dx_lane(g2.src);
     void *st = c.S.stream(ln);
     PackDyArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -1534,8 +1561,8 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     }
     const int nph = up ? 4 : 1;
     SENAS_TAG("pack_dy", 0, npix * nph * (64.0 * g2.nterms + 64.0));
-    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * nph * 4 + 255) / 256)), dim3(256), 0, st, pa);
-    c.S.dep(ln, dxl);
+    SENAS_LAUNCH(pack_dy_kernel, dim3((unsigned)((npix * nph * 4 + 255) / 256)), dim3(256), 0, c.S.stream(lp), pa);
+    c.S.dep(lp, dxl), c.S.dep(lp, ln);
     const Geo gf = make_geo(g2.k, g2.dil, g2.op, DIR_FWD);
     ta.ws_t = 1;
     conv_weight_strides(g2.op, 32, g2.k * g2.k, DIR_DGRAD, &ta.ws_k, &ta.ws_n);

@@ -19,6 +19,8 @@ all-reduce of a flat bucket that the graphs pack / unpack themselves:
 BatchNorm statistics and the soft-dice sums stay local to each rank (replica semantics of the reference's DataParallel
 path for BN; per-shard dice is the stated choice of SURVEY.md H8 for the graphed path), gradients are averaged.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -87,6 +89,16 @@ class GraphedSearchStep:
             for p in self.params:
                 p.grad = None
 
+    def _capture_stream(self):
+        """High-priority capture stream: the kernels the step enqueues on the caller's stream (node statistics, the stock
+        blocks between the cells) are its serial spine and must not queue behind the low-priority weight-gradient lanes
+        of the library; stream priorities are recorded in the graph's kernel nodes."""
+        if os.environ.get('SENAS_CAPTURE_PRIORITY', '1') == '0':
+            return torch.cuda.Stream()
+        if getattr(self, '_cap_stream', None) is None:
+            self._cap_stream = torch.cuda.Stream(priority=-1)
+        return self._cap_stream
+
     def _backward(self, loss):
         """backward, optionally (``defer_wgrad``) with the weight-gradient lanes of every fused call left running (joined
         by the next call of the same slot, or here at the end).  Measured: 102.6 ms vs 102.5 ms per step -- the next
@@ -128,7 +140,7 @@ class GraphedSearchStep:
         if not self.segmented:  # nothing to exchange: one graph
             if capture:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
+                with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode=self.capture_error_mode):
                     for s in segs:
                         s()
                 self.graphs = [g]
@@ -140,7 +152,7 @@ class GraphedSearchStep:
             if capture:  # each graph keeps its own memory pool; nothing executes while capturing
                 g = torch.cuda.CUDAGraph()
                 # thread_local: the NCCL watchdog thread keeps polling CUDA events while we capture
-                with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
+                with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode=self.capture_error_mode):
                     s()
                 self.graphs.append(g)
             else:

@@ -72,7 +72,7 @@ class SenasSearch(nn.Module):
         pool = self.__dict__.setdefault('_cell_streams', {})
         key = (str(device), j)
         if key not in pool:
-            pool[key] = torch.cuda.Stream(device=device)
+            pool[key] = torch.cuda.Stream(device=device, priority=-1)
         return pool[key]
 
     def forward(self, x, alpha_dn_nm, alpha_up_nm, alpha_dn, alpha_up, beta_dn, beta_up, gamma):
