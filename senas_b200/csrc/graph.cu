@@ -176,6 +176,7 @@ static int env_flag(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
+static const int g_pw_un = env_flag("SENAS_PW_UN", 2);  // pixel steps in flight in the pointwise statistics sweep (A/B)
 static const int g_split_lanes = env_flag("SENAS_SPLIT_LANES", 1);  // backward: chain lanes / weight-gradient lanes (A/B)
 static const int g_dw_fwd_per_edge = env_flag("SENAS_DW_FWD_EDGE", 1);  // same for the forward (measured: 102.4 -> 101.4 ms)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
@@ -1256,7 +1257,13 @@ static int backward_edge(BwdCall &c, int e) {
         sums1 = tmp + (int64_t)B * nblk_cc * 10 * C, coef1 = sums1 + 12 * C;
         a.bn1_coef = coef1;
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
-        if (C == 32) {
+        if (C == 32 && g_pw_un == 3) {
+          auto kern = pw_bwd_q_kernel<32, 1, 3>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
+        } else if (C == 32 && g_pw_un == 4) {
+          auto kern = pw_bwd_q_kernel<32, 1, 4>;
+          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
+        } else if (C == 32) {
           auto kern = pw_bwd_q_kernel<32, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         } else {
@@ -1637,7 +1644,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
 // ------------------------------------------------------------------------------------------------
 // C ABI: lifecycle
 // ------------------------------------------------------------------------------------------------
-extern "C" const char *senas_version(void) { return "senas_b200 0.1 (sm_100a, fp32 exact path)"; }
+extern "C" const char *senas_version(void) { return "senas_b200 0.2 (sm_100a)"; }
 extern "C" const char *senas_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t senas_launch_count(void) { return g_launch_count; }
 extern "C" int senas_set_slot(int slot) {

@@ -2085,9 +2085,9 @@ __global__ void __launch_bounds__(128) dw_wgrad_multi_kernel(DwMultiArgs a) {
 // broadcast with shuffles, W_pw[:, 4l..4l+3] lives in registers.
 //   PASS 1: per-channel sums of du and du*zhat and dW_pw partials ([10C] per block);   PASS 2: dz in place over z.
 // ------------------------------------------------------------------------------------------------
-template <int C, int PASS>
+template <int C, int PASS, int UN = (PASS == 1 ? 2 : 4)>  // UN pixel steps in flight; pass 1 carries 40 accumulators
 __global__ void __launch_bounds__(256, 2) pw_bwd_q_kernel(PwBwdArgs a, int px_per_block, int training) {
-  constexpr int LP = C / 4, PPW = 32 / LP, NDY = 8 / LP, UN = PASS == 1 ? 2 : 4;  // pass 1 carries 40 accumulators
+  constexpr int LP = C / 4, PPW = 32 / LP, NDY = 8 / LP;
   __shared__ float s_part[PASS == 1 ? 8 : 1][PASS == 1 ? 10 * C : 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
   const int l = lane % LP, sub = lane / LP;
