@@ -142,6 +142,12 @@ int senas_graph_plan(senas_graph_t *g, int32_t batch, const int32_t in_h[2], con
                      senas_plan_info_t *info);
 int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a);
 int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a);
+
+/* Row f1 of the scope table ("next"): AvgPool2d(3, stride 2, padding 1, count_include_pad=False) of the down cells'
+ * preprocess0 (utils/operations.py:141-152, search/cell.py:57-60) on NHWC fp32.  x: [B][H][W][x_ld >= C], y and gy:
+ * [B][ceil(H/2)][ceil(W/2)][C] dense, gx: [B][H][W][C] dense (written, not accumulated). */
+int senas_avgpool_forward(const float *x, int64_t x_ld, float *y, int32_t B, int32_t H, int32_t W, int32_t C, void *stream);
+int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int32_t H, int32_t W, int32_t C, void *stream);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t senas_launch_count(void);
 /* number of side streams ("lanes") over which independent candidate chains of a call are spread (fork/join with

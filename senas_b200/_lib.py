@@ -47,7 +47,8 @@ class BwdArgs(C.Structure):
 
 
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
-           'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_profile',
+           'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_avgpool_forward',
+           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_profile',
            'senas_profile_dump']
 
 
@@ -65,6 +66,9 @@ def bind(path):
     lib.senas_graph_forward.argtypes = [C.c_void_p, C.POINTER(FwdArgs)]
     lib.senas_graph_backward.argtypes = [C.c_void_p, C.POINTER(BwdArgs)]
     lib.senas_launch_count.restype = C.c_int64
+    lib.senas_avgpool_forward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p]
+    lib.senas_avgpool_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.senas_set_lanes.argtypes = [C.c_int]
     lib.senas_set_slot.argtypes = [C.c_int]
     lib.senas_set_defer.argtypes = [C.c_int]

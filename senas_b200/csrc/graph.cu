@@ -1655,6 +1655,22 @@ extern "C" int senas_set_slot(int slot) {
 #endif
   return 0;
 }
+// NHWC AvgPool2d(3, 2, 1, count_include_pad=False) of the down cells' preprocess0 (row f1): y [B][ceil(H/2)][ceil(W/2)][C]
+extern "C" int senas_avgpool_forward(const float *x, int64_t x_ld, float *y, int32_t B, int32_t H, int32_t W, int32_t C,
+                                     void *stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 4 || (C & 3) || (x_ld & 3)) SENAS_FAIL("avgpool forward: bad arguments");
+  const int64_t total = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+  SENAS_TAG("stock_avgpool", 0, 4.0 * B * H * W * C * 1.25);
+  SENAS_LAUNCH(avgpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, x_ld, y, B, H, W, C);
+  return check_cuda("avgpool forward");
+}
+extern "C" int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int32_t H, int32_t W, int32_t C, void *stream) {
+  if (!gy || !gx || B < 1 || H < 1 || W < 1 || C < 4 || (C & 3)) SENAS_FAIL("avgpool backward: bad arguments");
+  const int64_t total = (int64_t)B * H * W * (C / 4);
+  SENAS_TAG("stock_avgpool", 0, 4.0 * B * H * W * C * 1.25);
+  SENAS_LAUNCH(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, gx, B, H, W, C);
+  return check_cuda("avgpool backward");
+}
 extern "C" int senas_set_defer(int on) {
 #ifndef SENAS_EMU
   g_defer = on != 0;

@@ -2566,3 +2566,52 @@ __global__ void __launch_bounds__(128) dw_up_wgrad_multi_kernel(DwMultiArgs a) {
     else dw_up_wgrad_rows<C, 3>(it, n, a.H, a.W, by0, by1, j, q, active, s_part, nblk_idx);
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// AvgPool2d(3, stride 2, padding 1, count_include_pad=False) on NHWC fp32, forward and backward: the pooling of the
+// down cells' `preprocess0` (build_rectify, utils/operations.py:141-152).  PyTorch 2.11's CUDA backward of
+// this op is wrong for channels_last tensors and its NCHW fallback cost 1.7 ms per step (8 launches) plus two layout
+// conversions each.  thread = (pixel, channel quad).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float *x, int64_t x_ld, float *y, int B, int H, int W, int C) {
+  const int Q = C / 4, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x, total = (int64_t)B * Ho * Wo * Q;
+  if (i >= total) return;
+  const int q = (int)(i % Q);
+  const int64_t pix = i / Q;
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+  const float *xn = x + (int64_t)n * H * W * x_ld + q * 4;
+  float4 acc = f4zero();
+  int cnt = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      ++cnt;
+      const float4 v = ld4(xn + ((int64_t)iy * W + ix) * x_ld);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  const float inv = 1.f / (float)cnt;
+  st4(y + pix * C + q * 4, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float *gy, float *gx, int B, int H, int W, int C) {
+  const int Q = C / 4, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x, total = (int64_t)B * H * W * Q;
+  if (i >= total) return;
+  const int q = (int)(i % Q);
+  const int64_t pix = i / Q;
+  const int ix = (int)(pix % W), iy = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+  const float *gn = gy + (int64_t)n * Ho * Wo * C + q * 4;
+  float4 acc = f4zero();
+  for (int oy = iy >> 1; oy <= (iy + 1) >> 1; ++oy) {  // output windows that contain input row iy
+    if (oy >= Ho) continue;
+    for (int ox = ix >> 1; ox <= (ix + 1) >> 1; ++ox) {
+      if (ox >= Wo) continue;
+      const float inv = 1.f / (float)(pool_cnt(oy, H) * pool_cnt(ox, W));
+      const float4 v = ld4(gn + ((int64_t)oy * Wo + ox) * C);
+      acc.x = fmaf(v.x, inv, acc.x), acc.y = fmaf(v.y, inv, acc.y), acc.z = fmaf(v.z, inv, acc.z), acc.w = fmaf(v.w, inv, acc.w);
+    }
+  }
+  st4(gx + pix * C + q * 4, acc);
+}

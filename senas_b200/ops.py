@@ -204,7 +204,38 @@ class _AvgPool2dNCHW(nn.AvgPool2d):
     scripts/diag_pool.py), and the rest of the network runs channels_last."""
 
     def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0:
+            return _AvgPoolNHWCFn.apply(x)  # libsenas_b200 kernels on the channels_last tensor, no layout round trip
         return super().forward(x.contiguous()).contiguous(memory_format=torch.channels_last)
+
+
+class _AvgPoolNHWCFn(torch.autograd.Function):
+    """AvgPool2d(3, stride 2, padding 1, count_include_pad=False) on channels_last fp32 CUDA tensors through
+    ``senas_avgpool_forward / backward`` (row f1 of the scope table)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import _lib
+        lib = _lib.get()
+        x = x.contiguous(memory_format=torch.channels_last)
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, (H + 1) // 2, (W + 1) // 2), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        _lib.check(lib, lib.senas_avgpool_forward(x.data_ptr(), C, y.data_ptr(), B, H, W, C,
+                                                  torch.cuda.current_stream(x.device).cuda_stream))
+        ctx.shape = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import _lib
+        lib = _lib.get()
+        B, C, H, W = ctx.shape
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device, memory_format=torch.channels_last)
+        _lib.check(lib, lib.senas_avgpool_backward(gy.data_ptr(), gx.data_ptr(), B, H, W, C,
+                                                   torch.cuda.current_stream(gy.device).cuda_stream))
+        return gx
 
 
 def build_rectify(c_in, c_ot, cell_type):

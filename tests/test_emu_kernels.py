@@ -161,3 +161,23 @@ def test_mixed_op_wide_maps_emulated(emu, op_id, c_in, B, H, W):
     names = {id(p): n for n, p in m.named_parameters()}
     for p, gp in zip(runner.params, r['g_params']):
         check('grad.' + names[id(p)], gp, store[names[id(p)]].grad)
+
+
+@pytest.mark.parametrize('B,C,H,W', [(2, 32, 8, 8), (1, 8, 7, 5), (2, 32, 1, 3)])
+def test_avgpool_nhwc_emulated(emu, B, C, H, W):
+    """senas_avgpool_forward / backward (row f1: the down cells' preprocess0 pooling) against torch on the CPU,
+    including odd sizes (count_include_pad=False divisors 4 / 6 / 9)."""
+    import ctypes as C_
+    torch.manual_seed(B + C + H + W)
+    x = torch.randn(B, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ref = torch.nn.functional.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False)
+    gy = torch.randn(ref.shape).contiguous(memory_format=torch.channels_last)
+    ref.backward(gy)
+    xn = x.detach().permute(0, 2, 3, 1).contiguous()       # NHWC buffers
+    y = torch.empty(ref.shape).permute(0, 2, 3, 1).contiguous()
+    assert emu.senas_avgpool_forward(xn.data_ptr(), C, y.data_ptr(), B, H, W, C, None) == 0
+    check('y', y.permute(0, 3, 1, 2), ref.detach(), 1e-6)
+    gyn = gy.permute(0, 2, 3, 1).contiguous()
+    gx = torch.empty(B, H, W, C)
+    assert emu.senas_avgpool_backward(gyn.data_ptr(), gx.data_ptr(), B, H, W, C, None) == 0
+    check('gx', gx.permute(0, 3, 1, 2), x.grad, 1e-6)

@@ -519,3 +519,24 @@ def test_down_cell_bf16_tensor_core(bf16_mode):
     check('gbetas', g[4].grad, t[4].grad, 2e-2)
     for n, p in c._ops.named_parameters():
         check('grad._ops.' + n, p.grad, store['_ops.' + n].grad, 6e-2 if 'excitation' in n else 3e-2)
+
+
+@pytest.mark.parametrize('B,C,H,W', [(2, 32, 64, 64), (1, 32, 7, 9)])
+def test_avgpool_nhwc(B, C, H, W):
+    """The down cells' preprocess0 pooling through libsenas_b200 (channels_last, no NCHW round trip) against torch on
+    the CPU, forward and backward."""
+    from senas_b200.ops import build_rectify
+    torch.manual_seed(5)
+    pool = build_rectify(C, C, 'down')[1]
+    x = torch.randn(B, C, H, W)
+    xc = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.avg_pool2d(xc, 3, stride=2, padding=1, count_include_pad=False)
+    gy = torch.randn(ref.shape)
+    ref.backward(gy)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    n0 = senas_b200._lib.get().senas_launch_count()
+    out = pool(xg)
+    out.backward(gy.to(DEV))
+    assert senas_b200._lib.get().senas_launch_count() == n0 + 2
+    check('y', out, ref.detach(), 1e-6)
+    check('gx', xg.grad, xc.grad, 1e-6)
