@@ -67,6 +67,7 @@ class SenasSearch(nn.Module):
     # the small latency-bound cells hide under the large one in the captured graph.  Same operations on the same data:
     # results do not depend on the setting.
     concurrent_cells = False
+    gamma_rows_sum_to_one = False  # set by NAS (which softmaxes gamma); a direct caller may pass any gamma
 
     def _cell_stream(self, j, device):
         pool = self.__dict__.setdefault('_cell_streams', {})
@@ -104,7 +105,12 @@ class SenasSearch(nn.Module):
                     with (torch.cuda.stream(st) if st is not None else _nullctx()):
                         parts = [out[0][j]]
                         for k, g in enumerate(gidx):
-                            parts.append(out[k][j] * gamma[g][0] + out[k + 1][j] * gamma[g][1])
+                            if self.gamma_rows_sum_to_one:
+                                # softmax pairs (NAS.forward, senas_search.py:260): a*g0 + b*g1 == lerp(a, b, g1), one
+                                # kernel instead of three; the logits receive the same gradient g0*g1*(dL/dg1 - dL/dg0)
+                                parts.append(torch.lerp(out[k][j], out[k + 1][j], gamma[g][1]))
+                            else:
+                                parts.append(out[k][j] * gamma[g][0] + out[k + 1][j] * gamma[g][1])
                         in0 = torch.cat(parts, dim=1)
                         row.append(self.blocks[i][j](in0, out[i - 1][j + 1], alpha_up_nm, alpha_up, beta_up))
                 finally:
@@ -143,6 +149,7 @@ class NAS(nn.Module):
         self._use_sharing, self._meta_node_num, self._depth = use_sharing, meta_node_num, depth
         self.net = SenasSearch(input_c, c, num_classes, depth, meta_node_num, double_down_channel, supervision)
         self.net.apply(weights_init)
+        self.net.gamma_rows_sum_to_one = True  # forward() below always passes softmax(gamma)
         self.device_ids = [0]
         self._init_alphas()
 
