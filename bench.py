@@ -188,10 +188,7 @@ def run_ours(args, rank, world, local_rank):
     model.train()
     group = dist.group.WORLD if world > 1 else None
     crit = SegmentationLosses('dice_ce', group=group)
-    try:     # same SGD (search_arc.py:135), horizontally fused: one multi-tensor pass per step instead of four
-        w_opt = torch.optim.SGD(model.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4, fused=not args.no_fused_sgd)
-    except (TypeError, RuntimeError):
-        w_opt = torch.optim.SGD(model.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4)
+    w_opt = torch.optim.SGD(model.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4)
     a_opt = torch.optim.Adam(model.arch_parameters(), lr=1e-4, betas=(0.5, 0.999), weight_decay=1e-3)
     buckets = None
     if world > 1:
@@ -368,7 +365,6 @@ def main():
     ap.add_argument('--ref-max-steps', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--no-fused-sgd', action='store_true', help='torch.optim.SGD(foreach) instead of fused=True')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
     ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')
     ap.add_argument('--conv-mode', default='bf16', choices=['fp32', 'bf16'],
