@@ -176,7 +176,6 @@ static int env_flag(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static const int g_dw_per_edge = env_flag("SENAS_DW_EDGE", 1);  // depthwise backward groups per edge (1) or per state (0)
-static const int g_pw_un = env_flag("SENAS_PW_UN", 2);  // pixel steps in flight in the pointwise statistics sweep (A/B)
 static const int g_split_lanes = env_flag("SENAS_SPLIT_LANES", 1);  // backward: chain lanes / weight-gradient lanes (A/B)
 static const int g_dw_fwd_per_edge = env_flag("SENAS_DW_FWD_EDGE", 1);  // same for the forward (measured: 102.4 -> 101.4 ms)
 static inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
@@ -1257,13 +1256,7 @@ static int backward_edge(BwdCall &c, int e) {
         sums1 = tmp + (int64_t)B * nblk_cc * 10 * C, coef1 = sums1 + 12 * C;
         a.bn1_coef = coef1;
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
-        if (C == 32 && g_pw_un == 3) {
-          auto kern = pw_bwd_q_kernel<32, 1, 3>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
-        } else if (C == 32 && g_pw_un == 4) {
-          auto kern = pw_bwd_q_kernel<32, 1, 4>;
-          SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
-        } else if (C == 32) {
+        if (C == 32) {  // (2 / 3 / 4 pixel steps in flight measured the same under the 128-register cap: 2)
           auto kern = pw_bwd_q_kernel<32, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         } else {
