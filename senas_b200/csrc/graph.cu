@@ -339,7 +339,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
         case SENAS_KIND_AVG_POOL:
         case SENAS_KIND_UP_SAMPLE:
           t.has_y = t.owns_y = true, t.nblk = nblk_px;
-          if (t.kind == SENAS_KIND_UP_SAMPLE && C == 32)  // low-resolution u / du (8 channels) + dW partials
+          if (C == 32)  // u / du on the input grid (8 channels) + dW partials (up_sample: low, avg_pool: high resolution)
             tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * ep.in_h * ep.in_w * 8 +
                                                        (int64_t)B * cdiv(ep.in_h * ep.in_w, kPwPx) * 8 * C);
           tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * cdiv(std::max(HW, ep.in_h * ep.in_w), 128 * kPxTilesPerBlock) * 8 * C);
@@ -846,13 +846,13 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         a.x = x, a.x_ld = x_ld, a.x_h = ep.in_h, a.x_w = ep.in_w, a.y = y, a.o_h = p.out_h, a.o_w = p.out_w;
         a.w = (const float *)ed.param[k][0], a.partials = part;
         if ((C != 8) != (a.w != nullptr)) SENAS_FAIL("edge %d candidate %d: 1x1 weight does not match c_in", e, k);
-        if (C == 32 && t.kind != SENAS_KIND_AVG_POOL) {  // quad-layout 1x1 on the input grid (+ 8-channel upsample)
-          const bool up = t.kind == SENAS_KIND_UP_SAMPLE;
+        if (C == 32) {  // quad-layout 1x1 on the input grid (+ 8-channel upsample / pooling)
+          const bool up = t.kind == SENAS_KIND_UP_SAMPLE, pool = t.kind == SENAS_KIND_AVG_POOL;
           const int in_px = ep.in_h * ep.in_w;
           PwArgs pa;
           memset(&pa, 0, sizeof(pa));
           pa.z = x, pa.z_ld = x_ld, pa.hw = in_px, pa.wpw = a.w;
-          pa.y = up ? c.tmp(ln) : y, pa.partials = up ? nullptr : part;
+          pa.y = (up || pool) ? c.tmp(ln) : y, pa.partials = (up || pool) ? nullptr : part;
           SENAS_TAG("adapter_fwd", 2.0 * B * in_px * C * 8, 4.0 * B * (in_px * C + p.hw * 8));
           auto kern = pw_fwd_kernel<32, true>;
           SENAS_LAUNCH(kern, dim3(cdiv(in_px, kPwPx), B), dim3(256), 0, st, pa);
@@ -861,6 +861,12 @@ static int forward_edge(Call &c, int e, bool second_pass) {
             ua.u = c.tmp(ln), ua.y = y, ua.h = ep.in_h, ua.w = ep.in_w, ua.partials = part;
             SENAS_TAG("adapter_fwd", 0, 0);
             SENAS_LAUNCH(up8_fwd_kernel, dim3(cdiv(p.hw, 128), B), dim3(128), 0, st, ua);
+          }
+          if (pool) {
+            Pool8Args qa;
+            qa.u = c.tmp(ln), qa.y = y, qa.h = ep.in_h, qa.w = ep.in_w, qa.oh = p.out_h, qa.ow = p.out_w, qa.partials = part;
+            SENAS_TAG("adapter_fwd", 0, 0);
+            SENAS_LAUNCH(pool8_fwd_kernel, dim3(cdiv(p.hw, 128), B), dim3(128), 0, st, qa);
           }
           break;
         }
@@ -1098,7 +1104,7 @@ static int backward_edge(BwdCall &c, int e) {
     if (!t.has_y) continue;
     // dep-sep / quad adapters start with a chain that feeds the data gradient; conv / old adapters only have a weight
     // gradient left on their lane
-    const bool chain = t.kind == SENAS_KIND_DEPSEP || ((t.kind == SENAS_KIND_IDENTITY || t.kind == SENAS_KIND_UP_SAMPLE) && C == 32);
+    const bool chain = t.kind == SENAS_KIND_DEPSEP || ((t.kind == SENAS_KIND_IDENTITY || t.kind == SENAS_KIND_UP_SAMPLE || t.kind == SENAS_KIND_AVG_POOL) && C == 32);
     const int ln = chain ? c.S.pick_chain() : c.S.pick_bg();
     void *st = c.S.stream(ln);
     float *tmp = c.tmp(ln);
@@ -1119,12 +1125,15 @@ static int backward_edge(BwdCall &c, int e) {
         a.partials = tmp;
         const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
         const int in_px = ep.in_h * ep.in_w;
-        if (C == 32 && kk != AD_POOL) {  // one quad-layout sweep over the input grid: dx += W^T.dy and dW partials
-          const bool up = kk == AD_UP, want_dw = ed.grad_off[k][0] >= 0;
+        if (C == 32) {  // one quad-layout sweep over the input grid: dx += W^T.dy and dW partials
+          const bool up = kk != AD_IDENTITY, want_dw = ed.grad_off[k][0] >= 0;  // up: dy first goes through U^T / P^T
           float *du = tmp, *dwp = tmp + (up ? (int64_t)B * in_px * 8 : 0);
-          if (up) {
+          if (kk == AD_UP) {
             SENAS_TAG("adapter_dx", 0, 4.0 * B * HW * 16);
             SENAS_LAUNCH(up8_bwd_kernel, dim3(cdiv(in_px, 128), B), dim3(128), 0, st, a, du);
+          } else if (kk == AD_POOL) {
+            SENAS_TAG("adapter_dx", 0, 4.0 * B * HW * 16);
+            SENAS_LAUNCH(pool8_bwd_kernel, dim3(cdiv(in_px, 128), B), dim3(128), 0, st, a, du);
           }
           LinBwdArgs la;
           memset(&la, 0, sizeof(la));

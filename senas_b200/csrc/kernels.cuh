@@ -2615,3 +2615,56 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float *gy, float
   }
   st4(gx + pix * C + q * 4, acc);
 }
+
+// avg_pool AdapterBlock on 32 channels (DOWN edges): the 1x1 conv commutes with the pooling as it does with the bilinear
+// interpolation, so u = W.x runs on the input grid in quad layout (pw_fwd_kernel<32, true>) and only 8 channels are
+// pooled; backward: du = pool^T(dy) once (8 channels on the input grid), then lin_bwd_q_kernel.
+struct Pool8Args {
+  const float *u;  // [B][h][w][8] input resolution
+  float *y;        // [B][oh][ow][8], oh = ceil(h/2)
+  int32_t h, w, oh, ow;
+  float *partials;  // [B][gridDim.x][16]
+};
+__global__ void __launch_bounds__(128) pool8_fwd_kernel(Pool8Args a) {
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  if (p < a.oh * a.ow) {
+    const int oy = p / a.ow, ox = p - oy * a.ow;
+    const float *un = a.u + (int64_t)n * a.h * a.w * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+        if (iy < 0 || iy >= a.h || ix < 0 || ix >= a.w) continue;
+        ++cnt;
+        const float *q = un + ((int64_t)iy * a.w + ix) * 8;
+        const float4 lo = ld4(q), hi = ld4(q + 4);
+        acc[0] += lo.x, acc[1] += lo.y, acc[2] += lo.z, acc[3] += lo.w;
+        acc[4] += hi.x, acc[5] += hi.y, acc[6] += hi.z, acc[7] += hi.w;
+      }
+    const float inv = 1.f / (float)cnt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    float *yp = a.y + ((int64_t)n * a.oh * a.ow + p) * 8;
+    st4(yp, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(yp + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[j], v[8 + j] = acc[j] * acc[j];
+  }
+  block_sum_store<16>(v, a.partials + ((int64_t)n * gridDim.x + blockIdx.x) * 16);
+}
+
+// du[B][x_h][x_w][8] = pool^T(dy), dy = A*gm + B*y + C on the output grid.  thread = input pixel.
+__global__ void __launch_bounds__(128) pool8_bwd_kernel(AdapterBwdArgs a, float *du) {
+  const int n = blockIdx.y, p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= a.x_h * a.x_w) return;
+  const int iy = p / a.x_w, ix = p - iy * a.x_w;
+  float s[8];
+  adapter_gather_dy<AD_POOL>(a, n, iy, ix, s);
+  float *o = du + ((int64_t)n * a.x_h * a.x_w + p) * 8;
+  st4(o, make_float4(s[0], s[1], s[2], s[3]));
+  st4(o + 4, make_float4(s[4], s[5], s[6], s[7]));
+}
