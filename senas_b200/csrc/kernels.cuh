@@ -1671,7 +1671,7 @@ struct WgradTile {
 };
 
 template <int KC, int K, int SI, int SO>
-__global__ void __launch_bounds__(32 * K, K == 5 ? 4 : 1) conv_wgrad2_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(32 * K) conv_wgrad2_kernel(WgradArgs a) {
   using TL = WgradTile<KC, K, SI, SO>;
   constexpr int TH = TL::TH, TW = TL::TW, PS = TL::PS, NT = TL::THREADS;
   SENAS_DYN_SMEM(float4, smem);
