@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- SENAS supernet search step on B200: images/sec, roofline of the dominant kernel, CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_eager]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Arms: ``ours`` (default) = senas_b200 on the GPU(s); ``reference`` = the UNMODIFIED reference (oracle/_ref, staged by
+oracle/make_ref.py) on the box's host cores -- the reported CPU baseline; ``torch_eager`` = the same unmodified
+reference module tree on ONE B200 through stock PyTorch (fp32, cudnn.benchmark=True as experiments/search_arc.py:72),
+eagerly launched and as a replayed CUDA graph -- "the kernel to beat" of SURVEY.md section 2.3 / BASELINE.md 4.2.  The default
+run also embeds a short torch_eager measurement (``reference_b200``) and an fp32-mode line (``fp32_mode``).
 
 One "step" = one search step of experiments/search_arc.py:252-293 (epoch >= alpha_begin) on synthetic
 PROMISE12-shaped 1x256x256 slices: Architecture.step on a validation batch (fwd, dice_ce, bwd, Adam on
@@ -27,6 +33,7 @@ os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 # algorithmic work per image (SURVEY.md section 8d / BASELINE.md section 3), search step = 2 x (fwd + bwd)
 STEP_GFLOP_PER_IMG = 176.0          # whole supernet
 STEP_GFLOP_PER_IMG_MIXED = 129.7    # MixedOp path only
+STEP_MB_PER_IMG = 390.4             # MixedOp-boundary bytes, bf16 activations
 
 
 def peaks():
@@ -47,65 +54,182 @@ def synth(B, size, seed, pin):
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU implementation
+# reference arms: the UNMODIFIED reference (oracle/ref_env.py finds it: /root/reference here, oracle/_ref on the GPU box)
 # ------------------------------------------------------------------------------------------------------
-def cpu_search_step_factory(size, batch, seed=0):
-    import torch
+WORKLOAD = ('SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
+            '{B} x 1x{S}x{S} per GPU, global batch {G}')
+
+
+def ref_env():
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import senas_oracle as oracle
-    import senas_b200
-    torch.manual_seed(seed)
-    m = senas_b200.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
-                       supervision=False)  # parameter container only: the arithmetic below is the oracle's
-    store = dict(m.state_dict())
-    names = [n for n, _ in m.named_parameters()]
-    params = [store[n].requires_grad_(True) for n in names]
-    arch = [store[n] for n in ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma')]
-    w_opt = torch.optim.SGD(params, lr=5e-3, momentum=0.9, weight_decay=3e-4)
-    a_opt = torch.optim.Adam(arch, lr=1e-4, betas=(0.5, 0.999), weight_decay=1e-3)
+    import ref_env as re_
+    return re_
+
+
+def reference_step_factory(size, batch, device='cpu', seed=0):
+    """search step of experiments/search_arc.py:252-293 on the reference's own NAS / Architecture / SegmentationLosses
+    classes with the optimizers of configs/senas/senas_promise12.yml; synthetic batches as for our arm."""
+    import contextlib
+    import io
+    re_ = ref_env()
+    with contextlib.redirect_stdout(io.StringIO()):   # the reference prints "Using loss: ..." on stdout
+        model = re_.make_nas(seed=seed).to(device)
+        model.train()
+        step, w_opt, a_opt = re_.make_search_step(model)
     xt, yt = synth(batch, size, 1234, False)
     xv, yv = synth(batch, size, 4321, False)
+    data = [t.to(device) for t in (xt, yt, xv, yv)]
+    return step, data, model, (w_opt, a_opt)
 
-    def step():
-        a_opt.zero_grad()
-        oracle.dice_ce_loss(oracle.nas_forward(store, xv)[-1], yv).backward()
-        a_opt.step()
-        w_opt.zero_grad()
-        loss = oracle.dice_ce_loss(oracle.nas_forward(store, xt)[-1], yt)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 5)
-        w_opt.step()
-        return loss.item()
 
-    return step
+def cpu_reference_sample(size, batch, steps, warmup):
+    """(seconds per step, what ran) of the reference on all host threads."""
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    step, data, _, _ = reference_step_factory(size, batch)
+    for _ in range(warmup):
+        step(*data)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(*data)
+    return (time.perf_counter() - t0) / steps, cores
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation (PyTorch CPU kernels) of the same workload, all host
+    threads.  A step is a whole search step at the full batch unless K + W such steps would exceed --ref-budget-s, in
+    which case the per-step sample shrinks to the batch that fits -- and config.workload says which batch ran."""
     if rank != 0:
         return
     import torch
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    batch = args.ref_batch
-    step = cpu_search_step_factory(args.size, batch)
-    for _ in range(min(args.warmup, 1)):
-        step()
-    steps = max(1, min(args.steps, args.ref_max_steps))
+    batch = args.ref_batch if args.ref_batch > 0 else args.batch
+    step, data, _, _ = reference_step_factory(args.size, batch)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
+    step(*data)                                   # warm-up step 1 (also the probe that sizes the sample)
+    t_probe = time.perf_counter() - t0
+    total = args.steps + args.warmup
+    if args.ref_batch <= 0 and t_probe * total > args.ref_budget_s:
+        batch = max(1, int(batch * args.ref_budget_s / (t_probe * total)))
+        step, data, _, _ = reference_step_factory(args.size, batch)
+        step(*data)
+    for _ in range(max(0, args.warmup - 1)):
+        step(*data)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(*data)
+    dt = (time.perf_counter() - t0) / args.steps
     v = batch / dt
-    sample = f'{steps} search step(s) of the full supernet at batch {batch}, 1x{args.size}x{args.size}, fp32, oracle port'
+    re_ = ref_env()
+    sample = (f'{args.steps} search steps (+{args.warmup} warm-up) of the full supernet at batch {batch}, '
+              f'1x{args.size}x{args.size}, fp32, {cores} threads; unmodified reference from {re_.kind()}')
     print(json.dumps({
         'impl': 'reference', 'metric': 'search_step_images_per_sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
-                               f'{args.batch} x 1x{args.size}x{args.size} per GPU, global batch {args.batch * max(1, args.gpus)}',
-                   'parallelism': 'host cpu', 'launch': f'PyTorch CPU, {cores} threads, bounded sample (see cpu_baseline.sample)'},
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': WORKLOAD.format(B=batch, S=args.size, G=batch),
+                   'parallelism': 'host cpu', 'launch': f'PyTorch CPU (oneDNN), {cores} threads',
+                   'sample_batch': batch, 'full_batch': args.batch},
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def torch_eager_measure(args, steps, warmup, graph=True):
+    """The unmodified reference on ONE B200 through stock PyTorch: fp32 parameters and activations, cuDNN/ATen kernels,
+    cudnn.benchmark=True and PyTorch's default TF32 policy for cuDNN convolutions -- exactly what
+    experiments/search_arc.py:61-76 sets up.  Times the eagerly launched search step and the same step captured into a
+    CUDA graph (the same capture our arm uses), CUDA events around the timed steps."""
+    import torch
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.enabled = True
+    torch.backends.cudnn.benchmark = True
+    B, size = args.batch, args.size
+    step, data, model, (w_opt, a_opt) = reference_step_factory(size, B, device=dev)
+    out = {'batch': B, 'dtype': 'f32', 'cudnn_benchmark': True,
+           'cudnn_allow_tf32': bool(torch.backends.cudnn.allow_tf32), 'source': ref_env().kind()}
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    eager = lambda: step(*data)  # noqa: E731
+    for _ in range(warmup):
+        eager()
+    ms = timed(eager, steps)
+    out['eager'] = {'ms_per_step': ms, 'images_per_sec': B / (ms * 1e-3), 'steps': steps, 'warmup': warmup}
+    out['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 2 ** 30
+    if graph:
+        try:
+            del step, model, w_opt, a_opt
+            torch.cuda.empty_cache()
+            # fresh model / optimizers: Adam must be capturable from its first step (its `step` counters live on the
+            # device then); nothing else differs from the eager run
+            step, data, model, (w_opt, a_opt) = reference_step_factory(size, B, device=dev)
+            for g in a_opt.param_groups:
+                g['capturable'] = True
+            eager = lambda: step(*data)  # noqa: E731
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    eager()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                eager()
+            for _ in range(max(3, warmup)):
+                cg.replay()
+            ms = timed(cg.replay, steps)
+            out['cuda_graph'] = {'ms_per_step': ms, 'images_per_sec': B / (ms * 1e-3), 'steps': steps}
+        except Exception as e:
+            out['cuda_graph'] = {'failed': f'{type(e).__name__}: {str(e)[:200]}'}
+    return out
+
+
+def run_torch_eager(args, rank):
+    if rank != 0:
+        return
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    r = torch_eager_measure(args, args.steps, max(3, args.warmup))
+    best = r['eager']
+    if 'images_per_sec' in r.get('cuda_graph', {}) and r['cuda_graph']['images_per_sec'] > best['images_per_sec']:
+        best = r['cuda_graph']
+    line = {'impl': 'torch_eager', 'metric': 'search_step_images_per_sec', 'value': best['images_per_sec'],
+            'unit': 'images/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': best['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD.format(B=args.batch, S=args.size, G=args.batch), 'parallelism': 'dp1',
+                       'launch': 'unmodified reference, stock PyTorch (cuDNN/ATen) on one B200; value = the faster of '
+                                 'eager and CUDA-graph replay'},
+            'detail': r}
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
+def subprocess_json(argv, timeout):
+    """Run bench.py with other arguments in a fresh process (own CUDA context / allocator / cuDNN settings) and return
+    the JSON line it prints, or {'failed': why}."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True, timeout=timeout)
+        for line in reversed(res.stdout.strip().splitlines()):
+            if line.startswith('{'):
+                return json.loads(line)
+        return {'failed': f'rc={res.returncode}: {res.stderr.strip()[-300:]}'}
+    except Exception as e:
+        return {'failed': f'{type(e).__name__}: {str(e)[:200]}'}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -300,23 +424,35 @@ def run_ours(args, rank, world, local_rank):
     gB = B * world
     ms_step, ms_step_e2e = ms / args.steps, ms_e2e / args.steps
     value, value_e2e = gB / (ms_step * 1e-3), gB / (ms_step_e2e * 1e-3)
-    # dominant kernel = the family with the largest device time among those that carry algorithmic work (the 'reduce' /
-    # finalize families are fixed-order partial-sum folds: overhead of the bit-reproducible reductions, no flops/bytes
-    # of the reference graph; their share is reported under kernel_families like everything else)
-    work = {k: v for k, v in prof.items() if v['flops'] > 0 or v['bytes'] > 0} or prof
-    name, t = max(work.items(), key=lambda kv: kv[1]['ms'])
-    tensor_bound = name.startswith('conv_')  # conv_fwd / conv_dgrad / conv_wgrad / conv_tc_*
-    if tensor_bound:
-        ach = t['flops'] / (t['ms'] * 1e-3) / 1e12
-        roof = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s',
-                'frac': ach / pk['tf'], 'traffic': None}
-    else:
-        ach = t['bytes'] / (t['ms'] * 1e-3) / 1e9
-        roof = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm'], 'unit': 'GB/s',
-                'frac': ach / pk['hbm'], 'traffic': None}
-    roof.update(peak_source=pk['src'], launches=t['launches'], avg_launch_ms=t['ms'] / max(1, t['launches']),
-                share_of_senas_kernels=t['ms'] / total_ms,
-                step_tensor_frac=STEP_GFLOP_PER_IMG * 1e9 * value / world / (pk['tf'] * 1e12))
+    # roofline.  `frac` is the SURVEY 8(d) quantity for the path: algorithmic FLOPs of the reference graph per image
+    # (176 GFLOP, no credit for recompute / padding) x images/s per GPU / the measured sustained bf16 peak; the HBM
+    # counterpart (390.4 MB/img MixedOp-boundary bytes) sits beside it.  `dominant_family` is the kernel family with the
+    # largest device time of the step (reduction folds included), with its own achieved rate; `traffic` = DRAM bytes of
+    # one step from the committed ncu pass (profiles/r2_traffic.json), null when that file is absent.
+    per_gpu = value / world
+    ach_tf = STEP_GFLOP_PER_IMG * 1e9 * per_gpu / 1e12
+    ach_gb = STEP_MB_PER_IMG * 1e6 * per_gpu / 1e9
+    name, t = max(prof.items(), key=lambda kv: kv[1]['ms'])
+    dom = {'kernel': name, 'ms_per_step': t['ms'], 'launches': t['launches'],
+           'avg_launch_ms': t['ms'] / max(1, t['launches']), 'share_of_senas_kernels': t['ms'] / total_ms,
+           'tflops': t['flops'] / (t['ms'] * 1e-3) / 1e12, 'gbs': t['bytes'] / (t['ms'] * 1e-3) / 1e9}
+    dom['frac_tensor'], dom['frac_hbm'] = dom['tflops'] / pk['tf'], dom['gbs'] / pk['hbm']
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    roof = {'kernel': 'search step, all kernels (algorithmic 176 GFLOP/img, SURVEY 8d)', 'bound': 'tensor',
+            'achieved': ach_tf, 'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ach_tf / pk['tf'],
+            'traffic': traffic.get('dram_bytes_per_step') if traffic else None,
+            'traffic_over_algorithmic': (traffic['dram_bytes_per_step'] / (STEP_MB_PER_IMG * 1e6 * B)
+                                         if traffic and traffic.get('dram_bytes_per_step') else None),
+            'traffic_source': traffic.get('source') if traffic else None,
+            'peak_source': pk['src'] + ' (bf16_tflops_sustained: the kernels are timed inside a long step)',
+            'hbm': {'achieved': ach_gb, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': ach_gb / pk['hbm'],
+                    'algorithmic_mb_per_img': STEP_MB_PER_IMG},
+            'dominant_family': dom}
     families = {k: {'ms': round(v['ms'], 3), 'launches': v['launches'],
                     'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 3) if v['ms'] > 0 else 0,
                     'gbs': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 1) if v['ms'] > 0 else 0}
@@ -325,26 +461,31 @@ def run_ours(args, rank, world, local_rank):
         'metric': 'search_step_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.conv_mode == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': f'SENAS supernet search step (arch step + weight step), NAS(1,32,2,depth=5,nodes=3), '
-                               f'{B} x 1x{size}x{size} per GPU, global batch {gB}',
-                   'parallelism': f'dp{world}', 'launch': graph_note, 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate/storage)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
+        'config': {'workload': WORKLOAD.format(B=B, S=size, G=gB),
+                   'parallelism': f'dp{world}', 'launch': graph_note, 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
         'e2e': {'value': value_e2e, 'unit': 'images/s', 'ms_per_step': ms_step_e2e,
                 'h2d_bytes_per_step': 2 * B * size * size * (4 + 8), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'roofline': roof, 'kernel_families': families, 'clocks': clk,
     }
     if world == 1 and not args.no_cpu:
-        import torch as _t
-        cores = os.cpu_count()
-        _t.set_num_threads(cores)
-        cpu_search_step_factory(64, 1)()                      # thread-pool / allocator warm-up on a tiny input
-        step = cpu_search_step_factory(size, args.ref_batch)
-        t0 = time.perf_counter()
-        step()
-        step()
-        dt = (time.perf_counter() - t0) / 2
-        out['cpu_baseline'] = {'value': args.ref_batch / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                               'sample': f'2 search steps of the full supernet at batch {args.ref_batch}, '
-                                         f'1x{size}x{size}, fp32, all host threads, oracle port of the reference'}
+        # the unmodified reference on the host cores: ONE search step at the full batch after a tiny warm-up
+        cpu_reference_sample(64, 1, 1, 0)                      # thread pool / allocator warm-up on a tiny input
+        dt, cores = cpu_reference_sample(size, B, 1, 0)
+        out['cpu_baseline'] = {'value': B / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'reference',
+                               'sample': f'1 search step of the full supernet at batch {B}, 1x{size}x{size}, fp32, '
+                                         f'{cores} host threads, unmodified reference from {ref_env().kind()}'}
+    if world == 1 and not args.no_ref_gpu:
+        # "the kernel to beat": the unmodified reference through stock PyTorch on this same B200 (own process)
+        r = subprocess_json(['--impl', 'torch_eager', '--steps', str(min(args.steps, 10)), '--warmup', '3',
+                             '--batch', str(B), '--size', str(size)], 900)
+        out['reference_b200'] = r.get('detail', r)
+    if world == 1 and args.conv_mode == 'bf16' and not args.no_fp32_line:
+        r = subprocess_json(['--conv-mode', 'fp32', '--steps', str(min(args.steps, 10)), '--warmup', '3', '--no-cpu',
+                             '--no-ref-gpu', '--batch', str(B), '--size', str(size)], 900)
+        out['fp32_mode'] = ({k: r[k] for k in ('value', 'ms_per_step', 'dtype') if k in r} if 'value' in r else r)
+        if 'value' in r:
+            out['fp32_mode']['e2e'] = r['e2e']['value']
+            out['fp32_mode']['roofline_frac'] = r['roofline']['frac']
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
@@ -358,12 +499,16 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'torch_eager'])
     ap.add_argument('--batch', type=int, default=16, help='images per GPU')
     ap.add_argument('--size', type=int, default=256)
-    ap.add_argument('--ref-batch', type=int, default=4, help='CPU sample: images per (bounded) reference step')
-    ap.add_argument('--ref-max-steps', type=int, default=4)
-    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--ref-batch', type=int, default=0,
+                    help='--impl reference: images per step of the CPU sample (0 = the full batch, shrunk only if K + W steps '
+                         'would exceed --ref-budget-s)')
+    ap.add_argument('--ref-budget-s', type=float, default=540.0)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-ref-gpu', action='store_true', help='skip the reference-on-B200 (stock PyTorch) leg')
+    ap.add_argument('--no-fp32-line', action='store_true', help='skip the fp32-mode measurement beside the bf16 one')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
     ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')
@@ -374,6 +519,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         run_reference(args, rank)
+        return
+    if args.impl == 'torch_eager':
+        run_torch_eager(args, rank)
         return
     if args.warmup < 3:
         args.warmup = 3

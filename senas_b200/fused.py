@@ -112,13 +112,44 @@ def get_slot():
     return _slot[0]
 
 
+_retired = []   # superseded scratch buffers: never freed (a captured CUDA graph may have their address baked in)
+_pinned = {}    # (device, slot) -> data_ptr recorded by a live capture (GraphedSearchStep)
+
+
 def scratch_for(device, nbytes, slot=0):
-    """One grow-only scratch buffer per (device, slot), shared by every graph that runs in that slot."""
-    buf = _scratch.get((device, slot))
+    """One grow-only scratch buffer per (device, slot), shared by every graph that runs in that slot.  A buffer that has
+    been handed out is never returned to the allocator: when a later call needs more bytes the old block is retired
+    (kept alive), because captured CUDA graphs keep using its address.  Growing a slot that a live capture has pinned is
+    allowed for eager calls (they get the new block; replays keep the old one), see ``check_scratch``."""
+    key = (torch.device(device), slot)
+    buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired.append(buf)
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-        _scratch[(device, slot)] = buf
+        _scratch[key] = buf
     return buf
+
+
+def pin_scratch(device):
+    """Called by a CUDA-graph capture after its warm-up: the scratch blocks of ``device`` as {slot: data_ptr}.  The
+    blocks stay allocated for the life of the process (``scratch_for`` retires, never frees)."""
+    device = torch.device(device)
+    ptrs = {slot: buf.data_ptr() for (dev, slot), buf in _scratch.items() if dev == device}
+    for slot, ptr in ptrs.items():
+        _pinned[(device, slot)] = ptr
+    return {'device': device, 'ptrs': ptrs, 'keep': [buf for (dev, _), buf in _scratch.items() if dev == device]}
+
+
+def check_scratch(pinned):
+    """Raise if a scratch block that a capture baked in is no longer alive (cannot happen through ``scratch_for``;
+    guards against someone clearing the cache)."""
+    if pinned is None:
+        return
+    alive = {b.data_ptr() for b in pinned['keep']}
+    for slot, ptr in pinned['ptrs'].items():
+        if ptr not in alive:
+            raise RuntimeError(f'senas_b200: scratch block of slot {slot} captured by a CUDA graph was released')
 
 
 def _nhwc(t):
@@ -202,6 +233,9 @@ class GraphRunner:
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == 'cuda' else 0
 
     def forward(self, ins, alpha, beta, training, slot=0):
+        if self.device.type == 'cuda' and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):  # the library launches on, and allocates tables on, the current device
+                return self.forward(ins, alpha, beta, training, slot)
         B = ins[0].shape[0]
         hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
         info = self.plan(B, hs, ws)
@@ -223,6 +257,9 @@ class GraphRunner:
         return out, saved
 
     def backward(self, ins, alpha, beta, out, grad_out, saved, training, need_in, slot=0):
+        if self.device.type == 'cuda' and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.backward(ins, alpha, beta, out, grad_out, saved, training, need_in, slot)
         B = ins[0].shape[0]
         hs, ws = [t.shape[2] for t in ins], [t.shape[3] for t in ins]
         info = self.plan(B, hs, ws)

@@ -34,14 +34,15 @@ class GraphedSearchStep:
     ``loss = step(x_train, y_train, x_valid, y_valid)`` (device or pinned-host tensors of the captured shapes)."""
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
-                 force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False):
+                 force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False,
+                 restore_state=True):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
-        # small latency-bound cells with the large one of the level (senas_b200/supernet.py)
+        # small latency-bound cells with the large one of the level (senas_b200/supernet.py).  Only while warming up
+        # and capturing: eager forwards outside the graphs (validation) keep the serial single-stream walk.
         self.defer_wgrad = bool(defer_wgrad)
-        net = getattr(model, 'net', None)
-        if net is not None and hasattr(net, 'concurrent_cells'):
-            net.concurrent_cells = bool(concurrent_cells)
+        self._net = getattr(model, 'net', None)
+        self._concurrent = bool(concurrent_cells) and self._net is not None and hasattr(self._net, 'concurrent_cells')
         self.model, self.criterion, self.w_opt, self.a_opt = model, criterion, w_opt, a_opt
         self.grad_clip, self.group = grad_clip, group
         self.world = dist.get_world_size(group) if group is not None else 1
@@ -61,21 +62,83 @@ class GraphedSearchStep:
             self.bucket_all = torch.zeros(sum(p.numel() for p in self.params), device=dev)
             self.arch_views = _flat_views(self.bucket_arch, self.arch)
             self.all_views = _flat_views(self.bucket_all, self.params)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._run(capture=False)
-        torch.cuda.current_stream().wait_stream(side)
+        # The warm-up iterations are real optimizer steps (they create the optimizer state tensors whose addresses the
+        # graphs bake in, let cudnn.benchmark pick algorithms and size the library's scratch).  With ``restore_state``
+        # the model (weights, BatchNorm buffers, arch parameters) and both optimizers are put back afterwards, in
+        # place, so that the first replay is the first step of the search.
+        snap = self._snapshot() if restore_state else None
+        self._set_concurrent(True)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._run(capture=False, arch=True)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            # the library's scratch buffers are baked into the graphs: pin them (fused.scratch_for never frees a buffer
+            # it handed out, and refuses to regrow a pinned slot silently)
+            from . import fused
+            self._scratch_ptrs = fused.pin_scratch(self.params[0].device)
+            self._variants = {}          # arch flag -> (graphs, lr the SGD update was captured with)
+            self._capture(arch=True)
+        finally:
+            self._set_concurrent(False)
+        if snap is not None:
+            self._restore(snap)
+
+    # -- state ------------------------------------------------------------------------------------------------
+    def _set_concurrent(self, on):
+        if self._concurrent:
+            self._net.concurrent_cells = bool(on)
+
+    def _snapshot(self):
+        model = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        return model, [o.state_dict() for o in (self.w_opt, self.a_opt)]
+
+    def _restore(self, snap):
+        """In place (the graphs hold the addresses): model tensors back to their values, optimizer state tensors that did
+        not exist before the warm-up back to zero (SGD's first step sets buf = grad, i.e. 0.9 * 0 + grad; Adam starts from
+        exp_avg = exp_avg_sq = step = 0), those that did exist back to their values."""
+        model, opts = snap
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model[k])
+            for opt, old in zip((self.w_opt, self.a_opt), opts):
+                old_state = old['state']
+                index = {id(p): i for i, p in enumerate(p for g in opt.param_groups for p in g['params'])}
+                for p, st in opt.state.items():
+                    prev = old_state.get(index[id(p)], {})
+                    for name, t in st.items():
+                        if not torch.is_tensor(t):
+                            continue
+                        if name in prev and torch.is_tensor(prev[name]):
+                            t.copy_(prev[name])
+                        else:
+                            t.zero_()
         torch.cuda.synchronize()
+
+    def _lr(self):
+        return tuple(float(g['lr']) for g in self.w_opt.param_groups) + tuple(float(g['lr']) for g in self.a_opt.param_groups)
+
+    def _capture(self, arch):
         self.graphs = []
-        self._run(capture=True)
+        self._set_concurrent(True)
+        try:
+            self._run(capture=True, arch=arch)
+        finally:
+            self._set_concurrent(False)
+        self._variants[arch] = (self.graphs, self._lr())
 
     # -- the three segments -----------------------------------------------------------------------------------
     # Segments exchange gradients only through the two flat buckets (ordinary allocations): a segment packs its
     # gradients and drops them before it ends, the next one adopts persistent *views* of the bucket as p.grad, so no
     # tensor that lives in one graph's private memory pool is touched by another graph.
     def _seg1(self):
+        if not self._arch:  # epochs before alpha_begin (experiments/search_arc.py:268): no architecture step
+            for p in self.params:
+                p.grad = None
+            return
         xt, yt, xv, yv = self.static
         # the arch pass also produces (unused) weight gradients; dropping the stale ones first makes autograd adopt
         # the new buffers instead of launching ~3 400 in-place adds (same values reach both optimizers either way)
@@ -114,10 +177,11 @@ class GraphedSearchStep:
 
     def _seg2(self):
         xt, yt, xv, yv = self.static
-        if self.segmented:
-            for p, v in zip(self.arch, self.arch_views):
-                p.grad = v
-        self.a_opt.step()
+        if self._arch:
+            if self.segmented:
+                for p, v in zip(self.arch, self.arch_views):
+                    p.grad = v
+            self.a_opt.step()
         self.w_opt.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(xt), yt)
         self._backward(loss)
@@ -135,7 +199,8 @@ class GraphedSearchStep:
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip)
         self.w_opt.step()
 
-    def _run(self, capture):
+    def _run(self, capture, arch=True):
+        self._arch = bool(arch)
         segs = (self._seg1, self._seg2, self._seg3)
         if not self.segmented:  # nothing to exchange: one graph
             if capture:
@@ -157,21 +222,33 @@ class GraphedSearchStep:
                 self.graphs.append(g)
             else:
                 s()
-                if i < 2 and self.world > 1:
+                if i < 2 and self.world > 1 and (i == 1 or self._arch):
                     dist.all_reduce(self.bucket_arch if i == 0 else self.bucket_all, group=self.group)
 
-    def __call__(self, xt, yt, xv, yv):
+    def __call__(self, xt, yt, xv, yv, arch=True):
+        """One search step.  ``arch=False`` skips the architecture step (the driver does for ``epoch < alpha_begin``,
+        experiments/search_arc.py:268).  The optimizers' learning rates are kernel arguments of the captured updates:
+        when a scheduler has changed them since the capture (CosineAnnealingLR, once per epoch, search_arc.py:296) the
+        step is captured again -- no warm-up is needed, nothing executes during a capture."""
+        from . import fused
+        fused.check_scratch(self._scratch_ptrs)
+        arch = bool(arch)
+        var = self._variants.get(arch)
+        if var is None or var[1] != self._lr():
+            self._capture(arch)
+            var = self._variants[arch]
+        graphs = var[0]
         for dst, src in zip(self.static, (xt, yt, xv, yv)):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
         if not self.segmented:
-            self.graphs[0].replay()
+            graphs[0].replay()
         else:
-            self.graphs[0].replay()
-            if self.world > 1:
+            graphs[0].replay()
+            if self.world > 1 and arch:
                 dist.all_reduce(self.bucket_arch, group=self.group)
-            self.graphs[1].replay()
+            graphs[1].replay()
             if self.world > 1:
                 dist.all_reduce(self.bucket_all, group=self.group)
-            self.graphs[2].replay()
+            graphs[2].replay()
         return self.loss

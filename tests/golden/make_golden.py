@@ -68,13 +68,13 @@ def mixed_case(tag, op_type, c_in, B, H, W, seed, training=True):
     save(tag, **arrays)
 
 
-def cell_case(tag, cell_type, B, H, seed):
+def cell_case(tag, cell_type, B, H, seed, training=True):
     gen = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     c = cell_mod.Cell(3, 1, 32, 32, 32, cell_type)
     c.apply(weights_init)
     randomise_bn(c, gen)
-    c.train()
+    c.train(training)
     # in0 enters at twice in1's size for both cell types (down: rectified by preprocess0; up: skip input)
     in0 = torch.randn(B, 32, 2 * H, 2 * H, generator=gen, requires_grad=True)
     in1 = torch.randn(B, 32, H, H, generator=gen, requires_grad=True)
@@ -83,6 +83,12 @@ def cell_case(tag, cell_type, B, H, seed):
     betas = F.softmax(torch.randn(9, generator=gen), -1).requires_grad_(True)
     state = {k: v.clone() for k, v in c.state_dict().items()}
     out = c(in0, in1, wn, wc, betas)
+    if not training:  # infer() path (experiments/search_arc.py:301-330): running statistics, forward only
+        arrays = {'in0': in0.detach().numpy(), 'in1': in1.detach().numpy(), 'wn': wn.detach().numpy(),
+                  'wc': wc.detach().numpy(), 'betas': betas.detach().numpy(), 'out': out.detach().numpy()}
+        arrays.update({'state.' + k: v.numpy() for k, v in state.items()})
+        save(tag, **arrays)
+        return
     gout = torch.randn(out.shape, generator=gen)
     out.backward(gout)
     arrays = {'in0': in0.detach().numpy(), 'in1': in1.detach().numpy(), 'wn': wn.detach().numpy(),
@@ -132,8 +138,35 @@ def nas_case(tag, B, H, seed, steps):
     save(tag, **arrays)
 
 
+def nas_eval_case(tag, B, H, seed):
+    """``NAS.eval()`` forward (the infer() pass of experiments/search_arc.py:301-330) of the fixed-seed supernet with
+    non-trivial BatchNorm parameters / running statistics drawn from a seeded generator in ``modules()`` order (the
+    mirror model applies the same function: identical module order, tested through the identical state-dict keys), so
+    only the input and the logits need to be stored."""
+    torch.manual_seed(seed)
+    m = ss_mod.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
+                   supervision=False, device=torch.device('cpu'))
+    gen = torch.Generator().manual_seed(seed + 1)
+    randomise_bn(m, gen)
+    with torch.no_grad():
+        for n in ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma'):
+            getattr(m, n).copy_(0.5 * torch.randn(getattr(m, n).shape, generator=gen))
+    m.eval()
+    x = torch.randn(B, 1, H, H, generator=gen)
+    with torch.no_grad():
+        out = m(x)[-1]
+    save(tag, x=x.numpy(), out=out.numpy(), meta=np.array([B, H, seed]))
+
+
 if __name__ == '__main__':
     OT = ops_mod.OpType
+    if len(sys.argv) > 1 and sys.argv[1] == 'r2':  # round-2 additions only (eval-mode cases)
+        mixed_case('mixed_down32_eval', OT.DOWN, 32, 2, 10, 12, seed=31, training=False)
+        mixed_case('mixed_norm8_eval', OT.NORM, 8, 2, 7, 9, seed=32, training=False)
+        cell_case('cell_up_eval', 'up', 2, 6, seed=33, training=False)
+        cell_case('cell_down_eval', 'down', 2, 6, seed=34, training=False)
+        nas_eval_case('nas_eval', 2, 64, seed=0)
+        sys.exit(0)
     mixed_case('mixed_norm32', OT.NORM, 32, 2, 12, 20, seed=11)
     mixed_case('mixed_norm8', OT.NORM, 8, 3, 9, 18, seed=12)
     mixed_case('mixed_down32', OT.DOWN, 32, 2, 14, 18, seed=13)
@@ -144,3 +177,8 @@ if __name__ == '__main__':
     cell_case('cell_down', 'down', 2, 8, seed=21)
     cell_case('cell_up', 'up', 2, 8, seed=22)
     nas_case('nas_search_2steps', 2, 64, seed=0, steps=2)
+    mixed_case('mixed_down32_eval', OT.DOWN, 32, 2, 10, 12, seed=31, training=False)
+    mixed_case('mixed_norm8_eval', OT.NORM, 8, 2, 7, 9, seed=32, training=False)
+    cell_case('cell_up_eval', 'up', 2, 6, seed=33, training=False)
+    cell_case('cell_down_eval', 'down', 2, 6, seed=34, training=False)
+    nas_eval_case('nas_eval', 2, 64, seed=0)

@@ -96,7 +96,32 @@ def test_cell_nodes_emulated(emu, name, cell_type):
             check('after.' + k, sd[k], v, 1e-5)
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/search'), reason='reference tree only in the build container')
+@pytest.mark.parametrize('name,cell_type', [('cell_down_eval', 'down'), ('cell_up_eval', 'up')])
+def test_cell_eval_emulated(emu, name, cell_type):
+    """infer() path: the node loop in eval mode (running statistics, single pass, BatchNorm buffers untouched)."""
+    g = golden(name)
+    c = cell_module(g, cell_type).eval()
+    before = {k: v.clone() for k, v in c.state_dict().items()}
+    in0, in1 = torch.from_numpy(g['in0']), torch.from_numpy(g['in1'])
+    wn, wc, betas = (torch.from_numpy(g[k]) for k in ('wn', 'wc', 'betas'))
+    with torch.no_grad():
+        p0, p1 = c.preprocess0(in0), c.preprocess1(in1)
+        edges = [op._edge(s, d) for op, s, d in zip(c._ops, c._srcs, c._dsts)]
+        runner = GraphRunner(edges, n_inputs=2, n_nodes=3, node_relu=True, lib=emu)
+        alpha = torch.where(c._norm_rows, wn, wc)
+        r = run_graph_raw(runner, [p0, p1], alpha, betas, None, training=False)
+        out = c.post_process(r['out'])
+    check('out', out, g['out'])
+    for k, v in c.state_dict().items():
+        assert torch.equal(v, before[k]), k
+
+
+def _ref_available():
+    import ref_shim
+    return ref_shim.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason='reference tree not present (oracle/make_ref.py stages it)')
 def test_patch_reference_classes_emulated(emu):
     """senas_b200.patch_reference() on the UNMODIFIED reference classes (emulated kernels, CPU tensors): the
     reference's own Cell / MixedOp objects, parameters and autograd graph, only forward() rerouted."""

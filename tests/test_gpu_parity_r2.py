@@ -1,0 +1,391 @@
+"""Round-2 parity gates on the paths the benchmark actually times ("next round" item 1).  `-m gpu` only.
+
+* eval-mode (infer(), experiments/search_arc.py:301-330) goldens: Cell down / up, whole NAS;
+* CUDA vs oracle at the BASELINE config-2 sizes (batch 16, 32 channels, 256^2 / 128^2 / 64^2) for every MixedOp
+  flavour, in fp32 mode (gate 1e-4) and bf16 mode (gate 2e-2), and the head cell at 256^2;
+* the captured search step (GraphedSearchStep, one graph and three segments) against the eagerly launched step;
+* senas_b200.patch_reference() on the UNMODIFIED reference classes on the GPU, and experiments/search_arc.py run
+  untouched: CPU reference vs patched GPU run => same genotype.
+"""
+import copy
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import senas_b200
+import senas_oracle as oracle
+from helpers import OP_BY_ID, OP_NAME, cell_module, golden, max_err, sub
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+ARCH = ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma')
+
+
+def check(name, got, want, tol):
+    e = max_err(got, want)
+    assert e <= tol, f'{name}: rel err {e:.3e} > {tol}'
+
+
+def l2_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_default():
+    senas_b200.exact_fp32()
+    senas_b200.set_conv_mode('fp32')
+    yield
+    senas_b200.set_conv_mode('fp32')
+    senas_b200.exact_fp32()
+
+
+def _new_nas():
+    torch.manual_seed(0)
+    return senas_b200.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
+                          supervision=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# eval mode
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,cell_type', [('cell_down_eval', 'down'), ('cell_up_eval', 'up')])
+def test_cell_eval_golden(name, cell_type):
+    g = golden(name)
+    c = cell_module(g, cell_type).to(DEV).eval()
+    before = {k: v.clone() for k, v in c.state_dict().items()}
+    t = {k: torch.from_numpy(g[k]).to(DEV) for k in ('in0', 'in1', 'wn', 'wc', 'betas')}
+    with torch.no_grad():
+        out = c(t['in0'], t['in1'], t['wn'], t['wc'], t['betas'])
+    check('out', out, g['out'], 1e-4)
+    for k, v in c.state_dict().items():  # eval mode must not touch the BatchNorm buffers
+        assert torch.equal(v, before[k]), k
+
+
+def test_nas_eval_golden():
+    from test_oracle_golden import randomise_like_golden
+    g = golden('nas_eval')
+    B, H, seed = [int(v) for v in g['meta']]
+    torch.manual_seed(seed)
+    m = senas_b200.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
+                       supervision=False)
+    gen = randomise_like_golden(m, seed)
+    x = torch.randn(B, 1, H, H, generator=gen)
+    assert torch.equal(x, torch.from_numpy(g['x']))
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m(x.to(DEV))[-1]
+    check('logits', out, g['out'], 2e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config-2 sizes against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _randomised_mixed(c_in, op_id, seed):
+    torch.manual_seed(seed)
+    m = senas_b200.MixedOp(c_in, 8, OP_BY_ID[op_id])
+    m.apply(senas_b200.weights_init)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    return m
+
+
+# (op, c_in, input H=W): every (type, level) of SURVEY section 8a's census that is at least 64 wide at batch 16
+FULL = [(3, 32, 256), (3, 32, 128), (3, 32, 64), (3, 8, 256), (3, 8, 128), (3, 8, 64),
+        (1, 32, 128), (1, 32, 64), (1, 32, 32), (2, 32, 128), (2, 32, 64)]
+
+
+@pytest.mark.parametrize('op_id,c_in,H', FULL)
+def test_mixed_op_config2_size_vs_oracle(op_id, c_in, H):
+    """One MixedOp of the config-2 supernet at its real size (batch 16), forward + every gradient, against the CPU oracle;
+    both conv modes against the same oracle run.  fp32 mode: 1e-4.  bf16 mode (arbitrary fp32 operands): 2e-2, the SE
+    excitation weights (behind a 1-unit ReLU + sigmoid gate) included."""
+    B = 16
+    m = _randomised_mixed(c_in, op_id, 300 + op_id + c_in + H)
+    store = oracle.clone_store(m.state_dict())
+    gen = torch.Generator().manual_seed(H + op_id)
+    x = torch.randn(B, c_in, H, H, generator=gen)
+    if c_in == 8:
+        x = x.relu()  # node states are post-ReLU
+    alpha = torch.softmax(torch.randn(6, generator=gen), -1)
+    xo, ao = x.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], xo, ao, True)
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout)
+    want = {n: store[n].grad for n, _ in m.named_parameters()}
+    ref, gx, ga = ref.detach(), xo.grad, ao.grad
+    del xo
+    lib = senas_b200._lib.get()
+    for mode, tol in (('fp32', 1e-4), ('bf16', 2e-2)):
+        if mode == 'bf16' and c_in == 8:
+            continue  # the 8->8 edges run the same fp32 kernels in both modes
+        senas_b200.set_conv_mode(mode)
+        mg = copy.deepcopy(m).to(DEV)
+        xg, ag = x.to(DEV).requires_grad_(True), alpha.to(DEV).requires_grad_(True)
+        lib.senas_profile(1)
+        out = mg(xg, ag, ag)
+        out.backward(gout.to(DEV))
+        torch.cuda.synchronize()
+        lib.senas_profile(0)
+        prof = senas_b200._lib.profile_dump(lib)
+        if mode == 'bf16' and (H if op_id != 2 else H // 2) % 64 == 0:
+            assert 'conv_tc_fwd' in prof, sorted(prof)
+        check(f'{mode}.out', out, ref, tol)
+        check(f'{mode}.gx', xg.grad, gx, tol)
+        check(f'{mode}.galpha', ag.grad, ga, tol)
+        for n, p in mg.named_parameters():
+            check(f'{mode}.grad.' + n, p.grad, want[n], tol)
+        del mg, xg, out
+
+
+def test_head_cell_config2_size_vs_oracle():
+    """The head up-cell of the config-2 supernet (in0 16x32x256x256, in1 16x32x128x128): node loop + concat against the
+    oracle in fp32 mode.  Every node ends in a ReLU: among 2.5e7 pre-activations a handful lie within fp32 rounding of 0
+    and take the other branch, which moves the gradient at those pixels by a whole summand; so the output is gated in the
+    max norm (1e-4) and the gradients in the L2 norm (1e-4) plus a bound on how many elements exceed the max-norm gate."""
+    B = 16
+    torch.manual_seed(41)
+    c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
+    c.apply(senas_b200.weights_init)
+    for mod in c.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    store = oracle.clone_store(c.state_dict())
+    gen = torch.Generator().manual_seed(42)
+    in0, in1 = torch.randn(B, 32, 256, 256, generator=gen), torch.randn(B, 32, 128, 128, generator=gen).relu()
+    wn = torch.softmax(torch.randn(9, 6, generator=gen), -1)
+    wc = torch.softmax(torch.randn(9, 6, generator=gen), -1)
+    b = torch.softmax(torch.randn(9, generator=gen), -1)
+    t = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    ref = oracle.cell_nodes(oracle.Params(store), 'up', *t)
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout)
+    ref = ref.detach()
+    cg = c.to(DEV)
+    g = [v.to(DEV).requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    out = cg.nodes(*g)
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    check('cat', out, ref, 1e-4)
+
+    def gcheck(name, got, want):
+        got, want = got.detach().double().cpu(), want.double()
+        e2 = l2_err(got, want)
+        bad = ((got - want).abs() > 1e-4 * want.abs().max()).sum().item()
+        assert e2 <= 1e-4 and bad <= max(4, want.numel() // 10000), f'{name}: L2 {e2:.2e}, {bad} of {want.numel()} beyond 1e-4'
+
+    gcheck('gin0', g[0].grad, t[0].grad)
+    gcheck('gin1', g[1].grad, t[1].grad)
+    gcheck('gbetas', g[4].grad, t[4].grad)
+    norm = cg._norm_rows.view(-1).cpu()
+    gcheck('gwn', g[2].grad.cpu()[norm], t[2].grad[norm])
+    gcheck('gwc', g[3].grad.cpu()[~norm], t[3].grad[~norm])
+    for n, p in cg._ops.named_parameters():
+        gcheck('grad._ops.' + n, p.grad, store['_ops.' + n].grad)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the captured search step == the eager search step
+# ---------------------------------------------------------------------------------------------------------------
+def _optimizers(m):
+    return (torch.optim.SGD(m.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4),
+            torch.optim.Adam(m.arch_parameters(), lr=1e-4, betas=(0.5, 0.999), weight_decay=1e-3))
+
+
+def _batches(n, B, H, seed=1234):
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        xt = torch.randn(B, 1, H, H, generator=gen)
+        yt = (torch.rand(B, H, H, generator=gen) > 0.8).long()
+        xv = torch.randn(B, 1, H, H, generator=gen)
+        yv = (torch.rand(B, H, H, generator=gen) > 0.8).long()
+        out.append(tuple(t.to(DEV) for t in (xt, yt, xv, yv)))
+    return out
+
+
+@pytest.mark.parametrize('mode,segments', [('fp32', False), ('fp32', True), ('bf16', False)])
+def test_graphed_search_step_matches_eager(mode, segments):
+    """GraphedSearchStep (what bench.py times): replayed loss and the whole model state after each of three steps
+    (weights, BatchNorm buffers, arch parameters -- i.e. every gradient as seen through clip + SGD / Adam) against the
+    eagerly launched reference sequence of experiments/search_arc.py:252-293, including a weight-only step (epoch <
+    alpha_begin) and a changed learning rate (CosineAnnealingLR) between replays."""
+    from senas_b200.loss import SegmentationLosses
+    B, H = 2, 64
+    batches = _batches(3, B, H)
+    arch_flags = (True, False, True)
+    lrs = (5e-3, 5e-3, 2.5e-3)
+
+    senas_b200.set_conv_mode(mode)
+    ref = _new_nas().to(DEV).train()
+    w_opt, a_opt = _optimizers(ref)
+    crit = SegmentationLosses('dice_ce')
+    arch = senas_b200.Architecture(ref, a_opt, crit)
+    want_losses, want_states = [], []
+    for (xt, yt, xv, yv), do_arch, lr in zip(batches, arch_flags, lrs):
+        for gp in w_opt.param_groups:
+            gp['lr'] = lr
+        if do_arch:
+            arch.step(xv, yv)
+        w_opt.zero_grad()
+        loss = crit(ref(xt), yt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 5)
+        w_opt.step()
+        want_losses.append(loss.item())
+        want_states.append({k: v.detach().clone() for k, v in ref.state_dict().items()})
+
+    m = _new_nas().to(DEV).train()
+    init = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    w2, a2 = _optimizers(m)
+    step = senas_b200.GraphedSearchStep(m, SegmentationLosses('dice_ce'), w2, a2, batches[0], grad_clip=5.0, warmup=3,
+                                        force_segments=segments)
+    for k, v in m.state_dict().items():  # the warm-up steps left no trace
+        assert torch.equal(v, init[k]), k
+    prev = init
+    for i, ((xt, yt, xv, yv), do_arch, lr) in enumerate(zip(batches, arch_flags, lrs)):
+        for gp in w2.param_groups:
+            gp['lr'] = lr
+        loss = step(xt, yt, xv, yv, arch=do_arch)
+        torch.cuda.synchronize()
+        tol = 2e-5 if mode == 'fp32' else 2e-3
+        assert abs(loss.item() - want_losses[i]) <= tol * (1 + i) * abs(want_losses[i]), (i, loss.item(), want_losses[i])
+        got = m.state_dict()
+        for k, v in want_states[i].items():
+            if not v.is_floating_point():
+                assert torch.equal(got[k], v), k
+                continue
+            if k in ARCH:  # Adam: +-lr per entry whatever the gradient magnitude (sign flips of noise-level gradients)
+                assert (got[k] - v).abs().max().item() <= 2.5e-4 * (i + 1), k
+                continue
+            # compare the UPDATE of this step (what the gradients did), relative to its own size
+            upd_w, upd_g = (v - prev_state(want_states, init, i)[k]).double(), (got[k] - prev[k]).double()
+            scale = upd_w.abs().max().item()
+            if scale < 1e-12:
+                assert (upd_g - upd_w).abs().max().item() < 1e-9, k
+                continue
+            e = (upd_g - upd_w).abs().max().item() / scale
+            assert e <= (5e-3 if mode == 'fp32' else 5e-2) * (1 + i), f'step {i} {k}: update differs by {e:.2e}'
+        prev = {k: v.detach().clone() for k, v in got.items()}
+
+
+def prev_state(states, init, i):
+    return init if i == 0 else states[i - 1]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fixed-seed search in the benchmarked mode
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_fixed_seed_search_genotype_in_bench_mode(mode):
+    """The fixed-seed 2-step search of tests/golden/nas_search_2steps.npz (the unmodified reference on the CPU) with
+    senas_b200 configured exactly as bench.py configures it: fp32 mode = exact FMA convs + no TF32 in the stock blocks;
+    bf16 mode = tcgen05 bf16 operands + cudnn.allow_tf32 for the stock convs.  Same genotype in both; loss trajectory
+    1e-4-level in fp32 and within 2e-2 in bf16."""
+    g = golden('nas_search_2steps')
+    B, H, seed, steps = [int(v) for v in g['meta']]
+    senas_b200.set_conv_mode(mode)
+    if mode == 'bf16':
+        torch.backends.cudnn.allow_tf32 = True
+    try:
+        m = _new_nas().to(DEV).train()
+        w_opt, a_opt = _optimizers(m)
+        crit = lambda outs, y: oracle.dice_ce_loss(outs[-1], y)  # noqa: E731
+        arch = senas_b200.Architecture(m, a_opt, crit)
+        losses = []
+        for xt, yt, xv, yv in _batches(steps, B, H):
+            arch.step(xv, yv)
+            w_opt.zero_grad()
+            loss = crit(m(xt), yt)
+            losses.append(loss.item())
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+            w_opt.step()
+        assert np.allclose(losses, g['losses'], rtol=5e-4 if mode == 'fp32' else 2e-2), (losses, g['losses'])
+        for n in ARCH:
+            d = (getattr(m, n).detach().cpu() - torch.from_numpy(g['arch.' + n])).abs()
+            assert d.max() < 4.5e-4, (n, d.max().item())
+        assert repr(m.genotype()) == str(g['genotype'])
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# drop-in boundary on the reference's own classes (row b)
+# ---------------------------------------------------------------------------------------------------------------
+def _ref():
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference tree not staged (oracle/make_ref.py)')
+    return ref_shim.load()
+
+
+def test_patch_reference_classes_on_gpu():
+    """senas_b200.patch_reference() on the UNMODIFIED reference Cell (its own constructors, parameters, autograd
+    graph) on the B200: identical to the mirror module bit for bit, and to the reference's own forward within 1e-4."""
+    cell_mod, _, _ = _ref()
+    orig_m, orig_c = cell_mod.MixedOp.forward, cell_mod.Cell.forward
+    torch.manual_seed(5)
+    ref_cell = cell_mod.Cell(3, 1, 32, 32, 32, 'up')
+    mirror = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
+    mirror.load_state_dict(ref_cell.state_dict())
+    new_cell = copy.deepcopy(ref_cell).to(DEV)
+    in0, in1 = torch.randn(2, 32, 16, 16), torch.randn(2, 32, 8, 8)
+    wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
+    b = torch.softmax(torch.randn(9), -1)
+    t_ref = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    out_ref = ref_cell(*t_ref)  # the reference itself, CPU
+    gout = torch.randn(out_ref.shape)
+    out_ref.backward(gout)
+    try:
+        senas_b200.patch_reference(cell_mod)
+        t_new = [v.to(DEV).requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+        n0 = senas_b200._lib.get().senas_launch_count()
+        out_new = new_cell(*t_new)
+        out_new.backward(gout.to(DEV))
+        assert senas_b200._lib.get().senas_launch_count() > n0
+    finally:
+        cell_mod.MixedOp.forward, cell_mod.Cell.forward = orig_m, orig_c
+    mirror = mirror.to(DEV)
+    t_mir = [v.to(DEV).requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    out_mir = mirror(*t_mir)
+    out_mir.backward(gout.to(DEV))
+    assert list(new_cell.state_dict().keys()) == list(ref_cell.state_dict().keys())
+    # fused part is bit-reproducible; the stock pre/post blocks (cuDNN) are the same calls on the same data
+    check('mirror.out', out_new, out_mir.detach(), 1e-6)
+    check('out', out_new, out_ref.detach(), 1e-4)
+    for i, n in enumerate(('gin0', 'gin1', 'gwn', 'gwc', 'gbetas')):
+        check(n, t_new[i].grad, t_ref[i].grad, 1e-4)
+    for (n, p), (_, q) in zip(new_cell.named_parameters(), ref_cell.named_parameters()):
+        check('grad.' + n, p.grad, q.grad, 1e-4)
+
+
+def test_search_arc_untouched_same_genotype():
+    """experiments/search_arc.py run UNTOUCHED (runpy, stub set of SURVEY 8c, synthetic promise12 dataset, 1 epoch =
+    2 search steps + infer()): the reference on the CPU vs the same driver with senas_b200.patch_reference() on the GPU
+    => same printed genotype, same arch tables within the Adam two-step bound."""
+    import ref_env
+    cell_mod, _, _ = _ref()
+    orig_m, orig_c = cell_mod.MixedOp.forward, cell_mod.Cell.forward
+    kw = dict(epochs=1, n_samples=8, size=64, batch_size=2, alpha_begin=0)
+    g_cpu = ref_env.run_search_arc(tempfile.mkdtemp(), gpu=False, **kw)
+    cpu = g_cpu['search_network']
+    geno_cpu = repr(cpu.model.genotype())
+    arch_cpu = {n: getattr(cpu.model, n).detach().cpu().clone() for n in ARCH}
+    try:
+        g_gpu = ref_env.run_search_arc(tempfile.mkdtemp(), gpu=True,
+                                       before_run=lambda: senas_b200.patch_reference(cell_mod), **kw)
+    finally:
+        cell_mod.MixedOp.forward, cell_mod.Cell.forward = orig_m, orig_c
+    gpu = g_gpu['search_network']
+    assert next(gpu.model.parameters()).is_cuda
+    for n in ARCH:
+        d = (getattr(gpu.model, n).detach().cpu() - arch_cpu[n]).abs().max().item()
+        assert d < 4.5e-4, (n, d)
+    assert repr(gpu.model.genotype()) == geno_cpu

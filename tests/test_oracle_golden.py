@@ -49,6 +49,49 @@ def test_cell_matches_reference(name, cell_type):
         assert close(store[k], v), k
 
 
+@pytest.mark.parametrize('name,cell_type', [('cell_down_eval', 'down'), ('cell_up_eval', 'up')])
+def test_cell_eval_matches_reference(name, cell_type):
+    """infer() path (experiments/search_arc.py:301-330): running statistics, forward only."""
+    g = golden(name)
+    store = oracle.clone_store(sub(g, 'state.'), requires_grad=False)
+    t = {k: torch.from_numpy(g[k]) for k in ('in0', 'in1', 'wn', 'wc', 'betas')}
+    with torch.no_grad():
+        out = oracle.cell(oracle.Params(store), cell_type, t['in0'], t['in1'], t['wn'], t['wc'], t['betas'],
+                          training=False)
+    assert close(out, g['out'])
+
+
+def randomise_like_golden(m, seed):
+    """Same draws, in the same ``modules()`` order, as tests/golden/make_golden.py:nas_eval_case."""
+    gen = torch.Generator().manual_seed(seed + 1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data = 0.5 + torch.rand(mod.weight.shape, generator=gen)
+            mod.bias.data = 0.3 * torch.randn(mod.bias.shape, generator=gen)
+            mod.running_mean.data = 0.2 * torch.randn(mod.running_mean.shape, generator=gen)
+            mod.running_var.data = 0.5 + torch.rand(mod.running_var.shape, generator=gen)
+    with torch.no_grad():
+        for n in ('alphas_dn', 'alphas_up', 'alphas_dn_nm', 'alphas_up_nm', 'betas_dn', 'betas_up', 'gamma'):
+            getattr(m, n).copy_(0.5 * torch.randn(getattr(m, n).shape, generator=gen))
+    return gen
+
+
+def test_nas_eval_matches_reference():
+    """``NAS.eval()`` forward of the fixed-seed supernet with non-trivial running statistics (nas_eval.npz)."""
+    import senas_b200
+    g = golden('nas_eval')
+    B, H, seed = [int(v) for v in g['meta']]
+    torch.manual_seed(seed)
+    m = senas_b200.NAS(1, 32, 2, depth=5, meta_node_num=3, use_sharing=False, double_down_channel=False,
+                       supervision=False)
+    gen = randomise_like_golden(m, seed)
+    x = torch.randn(B, 1, H, H, generator=gen)
+    assert torch.equal(x, torch.from_numpy(g['x']))  # same generator stream as the reference run => same parameters
+    with torch.no_grad():
+        out = oracle.nas_forward({k: v for k, v in m.state_dict().items()}, x, training=False)[-1]
+    assert close(out, g['out'], 1e-5)
+
+
 def test_fixed_seed_search_matches_reference():
     """Two search steps (arch step + weight step) of the whole supernet from seed 0: same losses, same
     arch gradients, same alpha tables, same genotype as the reference (nas_search_2steps.npz)."""
