@@ -169,14 +169,30 @@ def torch_eager_measure(args, steps, warmup, graph=True):
     out['peak_mem_gb'] = torch.cuda.max_memory_allocated() / 2 ** 30
     if graph:
         try:
-            del step, model, w_opt, a_opt
+            del step, model, w_opt, a_opt, eager
             torch.cuda.empty_cache()
             # fresh model / optimizers: Adam must be capturable from its first step (its `step` counters live on the
             # device then); nothing else differs from the eager run
-            step, data, model, (w_opt, a_opt) = reference_step_factory(size, B, device=dev)
+            # and a device-resident dice_ce: the reference's own loss builds its one-hot target on the host every step
+            # (utils/loss/loss.py:203-206), a host->device copy that cannot be captured; senas_b200.loss is the same
+            # arithmetic in plain torch ops.  The model, Architecture and optimizers are the reference's.
+            _step, data, model, (w_opt, a_opt) = reference_step_factory(size, B, device=dev)
             for g in a_opt.param_groups:
                 g['capturable'] = True
-            eager = lambda: step(*data)  # noqa: E731
+            from senas_b200.loss import SegmentationLosses as _DevLoss
+            crit = _DevLoss('dice_ce')
+
+            def eager():
+                xt, yt, xv, yv = data
+                a_opt.zero_grad()
+                crit(model(xv), yv).backward()
+                a_opt.step()
+                w_opt.zero_grad()
+                loss = crit(model(xt), yt)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+                w_opt.step()
+                return loss
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):

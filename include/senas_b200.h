@@ -165,6 +165,10 @@ int senas_set_slot(int slot);
  * returns with everything ordered on the caller's stream. */
 int senas_set_defer(int on);
 int senas_flush(void *stream);
+/* Experimental: dep-sep candidates of NORM edges through the recompute kernels (ds_norm_kernel: the depthwise output is
+ * recomputed from the input in every sweep and never stored).  Off by default (measured slower than the spill path on
+ * B200); applies to graphs planned after the call.  Environment variable SENAS_DS_FUSED sets the default. */
+int senas_set_ds_fused(int on);
 /* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
  * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
  * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */

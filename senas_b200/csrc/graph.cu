@@ -194,6 +194,23 @@ static int dw_rows(int C, int B, int h, int w, bool wgrad) {
 }
 static int dw_nblk(int C, int B, int h, int w, bool wgrad) { return dw_tiles_x(C, w, wgrad) * cdiv(h, dw_rows(C, B, h, w, wgrad)); }
 
+// fused dep-sep kernels (ds_norm_kernel): tile = DsGeo<C>::TILE_W columns x rows, the largest of 32/16/8 rows that still
+// gives the 148 SMs a few blocks each
+// NORM dep-sep candidates through the recompute kernels (z never stored).  Measured on B200 and OFF by default: the four
+// sweeps cost 185 warp-instructions per pixel and candidate against ~85 for the spill path (recompute x3, the 1x1 as a
+// cross-lane reduction, dy evaluated by every channel lane): head cell 8.1 ms vs 3.0 ms, search step 117.7 vs 92.9 ms
+// (profiles/README.md, round 2).  Kept behind the switch with its emulator tests as the starting point for a version with
+// the pointwise halves on tensor cores.
+static int g_ds_fused = env_flag("SENAS_DS_FUSED", 0);
+static int ds_tile_w(int C) { return C == 32 ? DsGeo<32>::TILE_W : DsGeo<8>::TILE_W; }
+static int ds_rows(int C, int B, int h, int w) {
+  const int tx = cdiv(w, ds_tile_w(C));
+  for (int r = 32; r > 8; r /= 2)
+    if (tx * cdiv(h, r) * B >= 3 * 148) return r;
+  return 8;
+}
+static int ds_nblk(int C, int B, int h, int w) { return cdiv(w, ds_tile_w(C)) * cdiv(h, ds_rows(C, B, h, w)); }
+
 struct TermPlan {
   int kind = 0, k = 0, dil = 1;
   bool has_y = false, owns_y = false;
@@ -203,6 +220,8 @@ struct TermPlan {
   int nblk = 0, nblk1 = 0;
   int64_t scale_off = -1, coef_off = -1;
   bool tc = false;  // forward runs in a tcgen05 group (bf16 operands)
+  bool zb = false;  // fused dep-sep (recompute path) in bf16 mode: the gradient dz is stored as bf16
+  bool fused = false;  // dep-sep on a NORM edge: z is recomputed from x in every sweep and never stored (ds_norm_kernel)
   bool dwg = false; // dep-sep: depthwise half runs in the grouped row-walk kernels (all but DOWN on odd-sized maps)
 };
 struct TcGroup {
@@ -372,10 +391,16 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           if (ed.op_type == SENAS_OP_UP) t.nblk1 = dw_nblk(C, B, bh, bw, true);     // dw_up_multi_kernel grid (input grid)
           if (ed.op_type == SENAS_OP_DOWN && t.dwg) t.nblk1 = dw_nblk(C, B, p->out_h, p->out_w, true);  // (output grid)
           t.nblk = cdiv(HW, kPwPx);  // pw_fwd_kernel grid
-          t.z_off = take(sv, (int64_t)B * HW * C);
+          t.fused = g_ds_fused && ed.op_type == SENAS_OP_NORM;
+          if (t.fused) {  // only dz lives in the buffer (backward); bf16 in bf16 mode: a gradient value, no mask depends on it
+            t.nblk1 = t.nblk = ds_nblk(C, B, bh, bw);
+            t.zb = (d.reserved & 1) != 0;
+          }
+          t.z_off = take(sv, t.zb ? ((int64_t)B * HW * C + 1) / 2 : (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
           t.part1_off = take(sc, (int64_t)B * t.nblk1 * 2 * C), t.psum1_off = take(sc, (int64_t)B * 2 * C);
-          const int64_t pw_tmp = (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
+          const int64_t pw_tmp = t.fused ? 2 * ((int64_t)B * t.nblk * 10 * C + 16 * C)  // both candidates of an edge share a lane
+                                         : (int64_t)B * cdiv(HW, 512) * 10 * C + 16 * C;
           const int64_t dw_tmp = (int64_t)B * std::max(cdiv(bh * bw, kDwChunk), cdiv(bh, 4)) * C * T;
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           if (t.dwg)  // grouped weight gradient: one partial per block and convolution
@@ -770,10 +795,10 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
     up = ed.op_type == SENAS_OP_UP, down = ed.op_type == SENAS_OP_DOWN;
     for (int k = 0; k < SENAS_MAX_CAND; ++k) {
       const TermPlan &t = p.edges[e].t[k];
-      if (t.kind != SENAS_KIND_DEPSEP || !t.dwg) continue;
+      if (t.kind != SENAS_KIND_DEPSEP || !t.dwg || t.fused) continue;
       if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
       DwItem &it = a.it[a.n++];
-      it.in = x, it.in_ld = x_ld, it.out = c.saved + t.z_off, it.out_ld = ed.c_in;
+      it.in = x, it.in_ld = x_ld, it.out = c.saved + t.z_off, it.out_ld = ed.c_in, it.out_bf = t.zb;
       it.w = (const float *)ed.param[k][0], it.partials = c.scratch + t.part1_off, it.k = t.k;
       C = ed.c_in, h = down ? p.out_h : p.edges[e].in_h, w = down ? p.out_w : p.edges[e].in_w, nblk = t.nblk1;
     }
@@ -803,6 +828,62 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
   return 0;
 }
 
+// fused dep-sep candidates of the NORM edges that read `src`: ONE launch per sweep for all of them (the input tile is
+// read once for up to 6 convolutions).  mode = DS_FWD_STATS (stage A) or DS_FWD_Y (stage B).
+static int forward_ds_group(Call &c, int src, int mode) {
+  const senas_graph_desc_t &d = *c.d;
+  const Plan &p = *c.p;
+  DsArgs a;
+  memset(&a, 0, sizeof(a));
+  int C = 0, h = 0, w = 0, nblk = 0;
+  a.x = state_ptr(c, src, &a.x_ld);
+  double taps = 0;
+  for (int e = 0; e < d.n_edges; ++e) {
+    const senas_edge_desc_t &ed = d.edge[e];
+    if (ed.src != src) continue;
+    for (int k = 0; k < SENAS_MAX_CAND; ++k) {
+      const TermPlan &t = p.edges[e].t[k];
+      if (t.kind != SENAS_KIND_DEPSEP || !t.fused) continue;
+      if (a.n == kDsMaxItems) SENAS_FAIL("more than %d fused dep-sep candidates read state %d", kDsMaxItems, src);
+      DsItem &it = a.it[a.n++];
+      it.w = (const float *)ed.param[k][0], it.k = t.k;
+      it.mean1 = c.saved + t.mean1_off, it.istd1 = c.saved + t.istd1_off;
+      it.g1 = (const float *)ed.param[k][1], it.b1 = (const float *)ed.param[k][2], it.wpw = (const float *)ed.param[k][6];
+      it.y = c.saved + t.y_off;
+      it.partials = c.scratch + (mode == DS_FWD_STATS ? t.part1_off : t.part_off);
+      C = ed.c_in, h = p.edges[e].in_h, w = p.edges[e].in_w, nblk = t.nblk;
+      taps += t.k * t.k;
+    }
+  }
+  if (a.n == 0) return 0;
+  a.H = h, a.W = w, a.tiles_x = cdiv(w, ds_tile_w(C)), a.tile_rows = ds_rows(C, c.B, h, w), a.batch = c.B;
+  void *st = c.S.stream(c.S.pick());
+  dim3 grid(nblk, c.B);
+  const double px = (double)c.B * h * w;
+  if (mode == DS_FWD_STATS) {
+    SENAS_TAG("ds_fwd_stats", 2.0 * px * taps * C, 4.0 * px * C);
+    if (C == 32) {
+      auto kern = ds_norm_kernel<32, DS_FWD_STATS>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+    }
+    else {
+      auto kern = ds_norm_kernel<8, DS_FWD_STATS>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+    }
+  } else {
+    SENAS_TAG("ds_fwd_y", 2.0 * px * (taps * C + 8.0 * C * a.n), 4.0 * px * (C + 8.0 * a.n));
+    if (C == 32) {
+      auto kern = ds_norm_kernel<32, DS_FWD_Y>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+    }
+    else {
+      auto kern = ds_norm_kernel<8, DS_FWD_Y>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+    }
+  }
+  return 0;
+}
+
 static int forward_edge(Call &c, int e, bool second_pass) {
   const senas_edge_desc_t &ed = c.d->edge[e];
   const EdgePlan &ep = c.p->edges[e];
@@ -817,6 +898,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
     if (t.kind == SENAS_KIND_NONE || (second_pass && t.kind != SENAS_KIND_DEPSEP) ||
         (!second_pass && t.tc && (t.kind == SENAS_KIND_CONV || t.kind == SENAS_KIND_SE_CONV)))
       continue;
+    if (t.kind == SENAS_KIND_DEPSEP && t.fused) continue;  // forward_ds_group
     const int ln = c.S.pick();  // candidates of a stage are independent: one lane each (with its tmp slice)
     void *st = c.S.stream(ln);
     if (second_pass) {
@@ -824,7 +906,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
       a.z = c.saved + t.z_off, a.z_ld = C, a.hw = p.hw, a.y = y;
       a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
       a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
-      a.wpw = (const float *)ed.param[k][6], a.partials = part;
+      a.wpw = (const float *)ed.param[k][6], a.partials = part, a.z_bf = t.zb;
       dim3 grid(cdiv(p.hw, kPwPx), B);
       SENAS_TAG("pw_fwd", 2.0 * B * p.hw * C * 8, 4.0 * B * p.hw * (C + 8));
       if (C == 32) {
@@ -1036,6 +1118,7 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     if (s > 0) c.S.fork();
     for (int src = 0; src < d.n_inputs + d.n_nodes; ++src) {
       if (state_stage(d, src) != s) continue;
+      if (forward_ds_group(c, src, DS_FWD_STATS)) return 1;
       if (!g_dw_fwd_per_edge) {
         if (forward_dw_group(c, src, -1)) return 1;
         continue;
@@ -1055,6 +1138,8 @@ extern "C" int senas_graph_forward(senas_graph_t *g, const senas_fwd_args_t *a) 
     }
     if (p->n_bnB[s]) {
       c.S.fork();
+      for (int src = 0; src < d.n_inputs + d.n_nodes; ++src)
+        if (state_stage(d, src) == s && forward_ds_group(c, src, DS_FWD_Y)) return 1;
       for (int e = 0; e < d.n_edges; ++e)
         if (state_stage(d, d.edge[e].src) == s && forward_edge(c, e, true)) return 1;
       c.S.join();
@@ -1251,13 +1336,76 @@ static int backward_edge(BwdCall &c, int e) {
         break;
       }
       case SENAS_KIND_DEPSEP: {
+        if (t.fused) {  // the dep-sep candidates of the edge as ONE chain: stats sweep -> fold -> dz sweep (z recomputed)
+          bool first = true;
+          for (int k2 = 0; k2 < k; ++k2) first &= !(ep.t[k2].kind == SENAS_KIND_DEPSEP && ep.t[k2].fused);
+          if (!first) break;
+          DsArgs da;
+          memset(&da, 0, sizeof(da));
+          da.x = x, da.x_ld = x_ld, da.H = ep.in_h, da.W = ep.in_w, da.batch = B;
+          da.tiles_x = cdiv(ep.in_w, ds_tile_w(C)), da.tile_rows = ds_rows(C, B, ep.in_h, ep.in_w);
+          const int nb = t.nblk;
+          const int64_t per = (int64_t)B * nb * 10 * C + 16 * C;  // [partials | sums1 (12C) | coef1 (3C)] per candidate
+          int ks[SENAS_MAX_CAND], nk = 0;
+          double taps = 0;
+          for (int k2 = k; k2 < SENAS_MAX_CAND; ++k2) {
+            const TermPlan &t2 = ep.t[k2];
+            if (t2.kind != SENAS_KIND_DEPSEP || !t2.fused) continue;
+            if (ed.grad_off[k2][1] < 0 || ed.grad_off[k2][2] < 0 || ed.grad_off[k2][6] < 0 || ed.grad_off[k2][0] < 0)
+              SENAS_FAIL("dep-sep candidate needs gradient slots 0,1,2,6");
+            if ((nk + 1) * per > p.tmp_floats) break;  // (cannot happen: tmp is sized for 2 candidates, see build_plan)
+            DsItem &it = da.it[da.n++];
+            float *base = tmp + nk * per;
+            it.w = (const float *)ed.param[k2][0], it.k = t2.k, it.training = c.a->training, it.dz_bf = t2.zb;
+            it.mean1 = c.saved + t2.mean1_off, it.istd1 = c.saved + t2.istd1_off;
+            it.g1 = (const float *)ed.param[k2][1], it.b1 = (const float *)ed.param[k2][2];
+            it.wpw = (const float *)ed.param[k2][6], it.y = c.saved + t2.y_off, it.gm = gm;
+            it.coef = c.scratch + t2.coef_off, it.dz = c.saved + t2.z_off;
+            it.partials = base, it.bn1_coef = base + (int64_t)B * nb * 10 * C + 12 * C;
+            ks[nk++] = k2;
+            taps += t2.k * t2.k;
+          }
+          dim3 grid(nb, B);
+          const double px = (double)B * HW;
+          SENAS_TAG("ds_bwd_stats", 2.0 * px * (taps * C + 24.0 * C * nk), 4.0 * px * (C + 16.0 * nk));
+          if (C == 32) {
+            auto kern = ds_norm_kernel<32, DS_BWD_STATS>;
+            SENAS_LAUNCH(kern, grid, dim3(128), 0, st, da);
+          }
+          else {
+            auto kern = ds_norm_kernel<8, DS_BWD_STATS>;
+            SENAS_LAUNCH(kern, grid, dim3(128), 0, st, da);
+          }
+          for (int q = 0; q < nk; ++q) {
+            const int k2 = ks[q];
+            float *base = tmp + q * per, *sums = base + (int64_t)B * nb * 10 * C;
+            SENAS_TAG("reduce", 0, 0);
+            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)base, sums,
+                         nb * B, 10 * C);
+            SENAS_TAG("pw_bfin", 0, 0);
+            SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums, C, (float)B * (float)HW,
+                         da.it[q].g1, da.it[q].istd1, sums + 12 * C, gp + ed.grad_off[k2][1], gp + ed.grad_off[k2][2],
+                         gp + ed.grad_off[k2][6]);
+          }
+          SENAS_TAG("ds_bwd_dz", 2.0 * px * (taps * C + 16.0 * C * nk), 4.0 * px * (C + 16.0 * nk + (double)C * nk));
+          if (C == 32) {
+            auto kern = ds_norm_kernel<32, DS_BWD_DZ>;
+            SENAS_LAUNCH(kern, grid, dim3(128), 0, st, da);
+          }
+          else {
+            auto kern = ds_norm_kernel<8, DS_BWD_DZ>;
+            SENAS_LAUNCH(kern, grid, dim3(128), 0, st, da);
+          }
+          c.dw_wait[ed.src].push_back(ln);  // data / weight gradient of the depthwise halves: backward_dw_group
+          break;
+        }
         PwBwdArgs a;
         memset(&a, 0, sizeof(a));
         float *sums1 = nullptr, *coef1 = nullptr;
         a.gm = gm, a.y = y, a.z = c.saved + t.z_off, a.hw = HW, a.batch = B, a.coefA = cA, a.coefB = cB, a.coefC = cC;
         a.mean1 = c.saved + t.mean1_off, a.istd1 = c.saved + t.istd1_off;
         a.g1 = (const float *)ed.param[k][1], a.b1 = (const float *)ed.param[k][2];
-        a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1;
+        a.wpw = (const float *)ed.param[k][6], a.partials = tmp, a.bn1_coef = coef1, a.z_bf = t.zb;
         const int px_pb = 512, nblk_cc = cdiv(HW, px_pb);
         dim3 grid_cc(nblk_cc, B);
         if (ed.grad_off[k][1] < 0 || ed.grad_off[k][2] < 0 || ed.grad_off[k][6] < 0 || ed.grad_off[k][0] < 0)
@@ -1398,7 +1546,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
       if (a.n == kDwMaxItems) SENAS_FAIL("more than %d dep-sep candidates read state %d", kDwMaxItems, src);
       goff[a.n] = ed.grad_off[k][0];
       DwItem &it = a.it[a.n++];
-      it.in = c.saved + t.z_off, it.in_ld = ed.c_in;  // dz (in place over z)
+      it.in = c.saved + t.z_off, it.in_ld = ed.c_in, it.in_bf = t.zb;  // dz (in place over z)
       it.w = (const float *)ed.param[k][0], it.k = t.k, it.flip = (up || down) ? 0 : 1;
       C = ed.c_in, h = down ? p.out_h : p.edges[e].in_h, w = down ? p.out_w : p.edges[e].in_w, nblk = t.nblk1;
     }
@@ -1408,6 +1556,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1), a.tile_rows = dw_rows(C, c.B, h, w, col1);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
+  nblk = dw_nblk(C, c.B, h, w, col1);  // (t.nblk1 is the statistics grid: the fused dep-sep kernels tile differently)
   dim3 grid(nblk, c.B);
   if (up && C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
   float *dx = c.dstate[src];
@@ -1445,9 +1594,9 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     for (int m = 0; m < g.n; ++m) {
       g.it[m].flip = 0, g.it[m].partials = tmp + m * per;
       if (down)  // low-resolution operand = dz (already in .in), high-resolution operand = x
-        g.it[m].in2 = x, g.it[m].in2_ld = (int32_t)x_ld;
+        g.it[m].in2 = x, g.it[m].in2_ld = (int32_t)x_ld, g.it[m].in2_bf = 0;
       else
-        g.it[m].in2 = g.it[m].in, g.it[m].in = x, g.it[m].in_ld = x_ld;
+        g.it[m].in2 = g.it[m].in, g.it[m].in2_bf = g.it[m].in_bf, g.it[m].in = x, g.it[m].in_ld = x_ld, g.it[m].in_bf = 0;
     }
     SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
     if (up || down) {
@@ -1672,6 +1821,10 @@ extern "C" int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int
   SENAS_TAG("stock_avgpool", 0, 4.0 * B * H * W * C * 1.25);
   SENAS_LAUNCH(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, gx, B, H, W, C);
   return check_cuda("avgpool backward");
+}
+extern "C" int senas_set_ds_fused(int on) {  // affects graphs planned afterwards
+  g_ds_fused = on != 0;
+  return 0;
 }
 extern "C" int senas_set_defer(int on) {
 #ifndef SENAS_EMU

@@ -22,6 +22,50 @@ SENAS_DEVFN float4 ld4(const float *p) { return *reinterpret_cast<const float4 *
 SENAS_DEVFN void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 SENAS_DEVFN float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// bf16 storage of the dep-sep intermediate (z, then dz in place) in bf16 mode: 64 instead of 128 bytes per pixel for the
+// tensor that dominates the traffic of the depthwise-separable candidates.  Round to nearest even, written with integer
+// arithmetic so that the emulator build (tests/emu) and the device agree bit for bit.  `bf` is uniform per launch.
+#ifdef SENAS_EMU
+static inline uint32_t senas_f_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float senas_bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#else
+SENAS_DEVFN uint32_t senas_f_bits(float f) { return __float_as_uint(f); }
+SENAS_DEVFN float senas_bits_f(uint32_t u) { return __uint_as_float(u); }
+#endif
+struct alignas(8) senas_bf16x4 {
+  uint32_t lo, hi;
+};
+SENAS_DEVFN uint32_t senas_f2bf(float f) {
+  uint32_t u = senas_f_bits(f);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+SENAS_DEVFN uint32_t senas_pack_bf2(float a, float b) { return senas_f2bf(a) | (senas_f2bf(b) << 16); }
+// element e of a tensor stored as fp32 (bf == 0) or bf16 (bf != 0); e is a multiple of 4 elements
+SENAS_DEVFN float4 ldx4(const float *base, int64_t e, int bf) {
+  if (bf) {
+    const senas_bf16x4 r = *reinterpret_cast<const senas_bf16x4 *>(reinterpret_cast<const uint16_t *>(base) + e);
+    return make_float4(senas_bits_f(r.lo << 16), senas_bits_f(r.lo & 0xffff0000u), senas_bits_f(r.hi << 16),
+                       senas_bits_f(r.hi & 0xffff0000u));
+  }
+  return ld4(base + e);
+}
+SENAS_DEVFN void stx4(float *base, int64_t e, float4 v, int bf) {
+  if (bf) {
+    senas_bf16x4 r;
+    r.lo = senas_pack_bf2(v.x, v.y), r.hi = senas_pack_bf2(v.z, v.w);
+    *reinterpret_cast<senas_bf16x4 *>(reinterpret_cast<uint16_t *>(base) + e) = r;
+  } else {
+    st4(base + e, v);
+  }
+}
+// the value a bf16 store keeps (statistics must describe what the consumers will read)
+SENAS_DEVFN float4 roundx4(float4 v, int bf) {
+  if (!bf) return v;
+  return make_float4(senas_bits_f(senas_f2bf(v.x) << 16), senas_bits_f(senas_f2bf(v.y) << 16),
+                     senas_bits_f(senas_f2bf(v.z) << 16), senas_bits_f(senas_f2bf(v.w) << 16));
+}
+
 SENAS_DEVFN float warp_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -462,6 +506,7 @@ struct PwArgs {
   const float *mean1, *istd1, *g1, *b1;
   const float *wpw;  // [8][C]
   float *partials;   // [B][gridDim.x][16]
+  int32_t z_bf, pad_;  // z is the bf16-stored dep-sep intermediate
 };
 
 // LP = C/4 lanes share a pixel: lane l loads channels 4l..4l+3 as one float4 (a warp reads 512 contiguous bytes), applies
@@ -493,14 +538,15 @@ __global__ void __launch_bounds__(256, 3) pw_fwd_kernel(PwArgs a) {
   const int p_begin = blockIdx.x * kPwPx, p_end = min(p_begin + kPwPx, a.hw);
   const int per_warp = kPwPx / 8;
   const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
-  const float *zn = a.z + (int64_t)n * a.hw * a.z_ld + l * 4;
+  const int64_t z0 = (int64_t)n * a.hw * a.z_ld + l * 4;
+  const int z_bf = PLAIN ? 0 : a.z_bf;
   float *yn = a.y + (int64_t)n * a.hw * 8;
   for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
     float4 zv[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int p = p0 + u * PPW + sub;
-      zv[u] = p < w_end ? ld4(zn + (int64_t)p * a.z_ld) : f4zero();
+      zv[u] = p < w_end ? ldx4(a.z, z0 + (int64_t)p * a.z_ld, z_bf) : f4zero();
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -1192,6 +1238,7 @@ struct PwBwdArgs {
   const float *wpw;       // [8][C]
   float *partials;        // pass 1: [B][gridDim.x][10C] = du sums (C), du*zhat sums (C), dWpw (8C)
   const float *bn1_coef;  // pass 2: [3][C] = a1, dbeta1/M, dgamma1/M
+  int32_t z_bf, pad_;     // z / dz stored as bf16 (pw_bwd_q_kernel only; the older per-pixel kernels are fp32)
 };
 
 // du (gradient at the BN1 output, after the ReLU mask) and side values for one pixel
@@ -1864,6 +1911,7 @@ struct DwItem {
   const float *in2;   // weight gradient: dz [B][H][W][C]
   int64_t in_ld, out_ld;
   int32_t k, flip, accumulate, in2_ld;  // in2_ld: pixel stride of in2 (0 = C)
+  int32_t in_bf, out_bf, in2_bf, pad_;  // != 0: that tensor is the bf16-stored dep-sep intermediate (z / dz)
 };
 struct DwMultiArgs {
   DwItem it[kDwMaxItems];
@@ -1893,12 +1941,12 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
   bool cok[NX];
 #pragma unroll
   for (int j = 0; j < NX; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
-  const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-  float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
+  const int64_t in0 = (int64_t)n * H * W * it.in_ld + q * 4, out0 = (int64_t)n * H * W * it.out_ld + q * 4;
   const float *wq = s_w + q * 4;
   const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
   const int64_t in_ld = it.in_ld;
   const bool rmw = it.accumulate != 0;
+  const int in_bf = it.in_bf, out_bf = it.out_bf;
   for (int i0 = 0; i0 < niter; i0 += K) {
 #pragma unroll
     for (int u = 0; u < K; ++u) {
@@ -1909,13 +1957,13 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
         if (rmw && i >= K - 1) {
 #pragma unroll
           for (int j = 0; j < NCOL; ++j)
-            old[j] = bx + j < W ? ld4(outb + ((int64_t)o * W + bx + j) * it.out_ld) : f4zero();
+            old[j] = bx + j < W ? ldx4(it.out, out0 + ((int64_t)o * W + bx + j) * it.out_ld, out_bf) : f4zero();
         }
         if (rr >= 0 && rr < H) {
           float4 xv[NX];
-          const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
+          const int64_t rowe = in0 + ((int64_t)rr * W + (bx - P)) * in_ld;
 #pragma unroll
-          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ld4(rowp + (int64_t)j * in_ld) : f4zero();
+          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? ldx4(it.in, rowe + (int64_t)j * in_ld, in_bf) : f4zero();
 #pragma unroll
           for (int ky = 0; ky < K; ++ky) {
             if ((unsigned)(i - ky) < (unsigned)R) {  // output row by0 + i - ky is inside the tile
@@ -1934,11 +1982,11 @@ SENAS_DEVFN void dw_tile_rows(const DwItem &it, const float *s_w, int n, int H, 
 #pragma unroll
           for (int j = 0; j < NCOL; ++j) {
             if (bx + j < W) {
-              float *op = outb + ((int64_t)o * W + bx + j) * it.out_ld;
               float4 v = acc[sc][j];
               if (rmw) v.x += old[j].x, v.y += old[j].y, v.z += old[j].z, v.w += old[j].w;
-              st4(op, v);
+              stx4(it.out, out0 + ((int64_t)o * W + bx + j) * it.out_ld, v, out_bf);
               if (STATS) {
+                v = roundx4(v, out_bf);
                 st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
                 st[4] += v.x * v.x, st[5] += v.y * v.y, st[6] += v.z * v.z, st[7] += v.w * v.w;
               }
@@ -2012,7 +2060,8 @@ SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, i
 #pragma unroll
     for (int j = 0; j < K; ++j) cok[j] = bx - P + j >= 0 && bx - P + j < W;
     const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-    const float *dzb = it.in2 + (int64_t)n * H * W * C + q * 4;
+    const int64_t dz0 = (int64_t)n * H * W * C + q * 4;
+    const int in2_bf = it.in2_bf;
     const int R = by1 - by0, niter = R + K - 1, r_first = by0 - P;
     const int64_t in_ld = it.in_ld;
     for (int i0 = 0; i0 < niter; i0 += K) {
@@ -2021,7 +2070,7 @@ SENAS_DEVFN void dw_wgrad_rows(const DwItem &it, int n, int H, int W, int by0, i
         const int i = i0 + u, rr = r_first + i;
         if (i < niter) {
           // dz row entering the window: output row by0 + i (slot u)
-          dzv[u] = i < R ? ld4(dzb + ((int64_t)(by0 + i) * W + bx) * C) : f4zero();
+          dzv[u] = i < R ? ldx4(it.in2, dz0 + ((int64_t)(by0 + i) * W + bx) * C, in2_bf) : f4zero();
           if (rr >= 0 && rr < H) {
             float4 xv[K];
             const float *rowp = inb + ((int64_t)rr * W + (bx - P)) * in_ld;
@@ -2081,6 +2130,232 @@ __global__ void __launch_bounds__(128) dw_wgrad_multi_kernel(DwMultiArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fused depthwise-separable candidate (dep_sep_conv_3 / dep_sep_conv_5, utils/operations.py:107-115) for NORM edges:
+// the depthwise output z is NEVER written to HBM.  Every sweep recomputes z = dw(x) from the input tile (9 / 25 FMAs per
+// element, far cheaper than a 128 B/pixel round trip of a 32-channel fp32 tensor) and keeps it in registers:
+//   DS_FWD_STATS : z                                  -> BatchNorm-1 partial sums (sum z, sum z^2 per channel)
+//   DS_FWD_Y     : z -> BN1 -> ReLU -> 1x1 (C -> 8)   -> y (8 channels) + BatchNorm-2 partial sums
+//   DS_BWD_STATS : z, dy = A g + B y + C              -> sum du, sum du zhat, dW_pw partials ([10C] per block)
+//   DS_BWD_DZ    : z, dy                              -> dz = BN1'(relu'(W_pw^T dy))  (fp32, or bf16 in bf16 mode: a plain
+//                                                        gradient value, no ReLU decision hangs on its rounding)
+// so the only per-candidate tensors in HBM are y (32 B/pixel) and, during backward, dz.  The arithmetic is exact fp32.
+//
+// Layout: lane = channel.  With NHWC and C = 32 one warp-wide load is the 128 contiguous bytes of one pixel, the
+// depthwise weights of a lane's channel (K*K floats) and every BatchNorm-1 quantity sit in registers, and all the
+// per-channel reductions (statistics, dW_pw columns) are lane-local: no shuffles until the end of the tile.  A warp walks
+// down a strip of kDsCols columns with the K in-flight output rows in registers (slot = row mod K under a K-fold
+// unroll): K*K*kDsCols FMAs per (kDsCols + K - 1) loads.  C = 8: four strips side by side in one warp (lane = strip, ch).
+// The 1x1 reduces over the channel lanes with a fixed-order transpose-reduce (8 values -> one output channel per lane).
+// grid = (tiles_x * tiles_y, B), block = 128 = 4 warps.
+// ------------------------------------------------------------------------------------------------
+enum { DS_FWD_STATS = 0, DS_FWD_Y = 1, DS_BWD_STATS = 2, DS_BWD_DZ = 3 };
+constexpr int kDsMaxItems = 6, kDsCols = 4;
+struct DsItem {
+  const float *w;                        // depthwise weight [C][K*K]
+  const float *mean1, *istd1, *g1, *b1;  // BatchNorm-1 (modes 1..3)
+  const float *wpw;                      // pointwise weight [8][C] (modes 1..3)
+  float *y;                              // [B][HW][8]: written by mode 1, read by modes 2, 3
+  const float *gm;                       // [B][HW][8] node gradient after the ReLU mask (modes 2, 3)
+  const float *coef;                     // [3][B][8] dy coefficients A, B, C (modes 2, 3)
+  const float *bn1_coef;                 // [3][C] a1, dbeta1/M, dgamma1/M (mode 3)
+  float *dz;                             // [B][HW][C] (mode 3)
+  float *partials;                       // mode 0: [B][grid.x][2C]; mode 1: [B][grid.x][16]; mode 2: [B][grid.x][10C]
+  int32_t k, dz_bf, training, flip;
+};
+struct DsArgs {
+  const float *x;  // [B][H][W][x_ld]
+  int64_t x_ld;
+  int32_t H, W, tiles_x, tile_rows, n, batch;
+  DsItem it[kDsMaxItems];
+};
+template <int C>
+struct DsGeo {
+  static constexpr int STRIPS = 32 / C;               // strips per warp
+  static constexpr int TILE_W = 4 * STRIPS * kDsCols;  // columns per block
+};
+
+// Sum v[0..8) over the C channel lanes of a strip (fixed order); on return v[0] of lane `ch` holds output channel
+// ch / (C / 8) (complete in every lane of that group of C / 8 lanes).
+template <int C>
+SENAS_DEVFN void ds_reduce8(float *v, int lane) {
+#pragma unroll
+  for (int m = C / 2, nk = 4; nk >= 1; m >>= 1, nk >>= 1) {
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int j = 0; j < nk; ++j) {
+      const float send = hi ? v[j] : v[j + nk], keep = hi ? v[j + nk] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+#pragma unroll
+  for (int m = C / 16; m >= 1; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+}
+
+template <int C, int K, int MODE>
+SENAS_DEVFN void ds_walk(const DsArgs &a, const DsItem &it, int n, int c0, int r0, int r1, int lane, float *acc_out) {
+  constexpr int P = K / 2, WT = kDsCols, NX = WT + K - 1, T = K * K, G = C / 8;
+  const int ch = lane % C;
+  const int H = a.H, W = a.W;
+  float w[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) w[t] = __ldg(it.w + ch * T + (it.flip ? T - 1 - t : t));
+  float sc = 1.f, sh = 0.f, mean1 = 0.f, istd1 = 1.f, wp[8], k0 = 0.f, k1 = 0.f, k2 = 0.f;
+#pragma unroll
+  for (int co = 0; co < 8; ++co) wp[co] = 0.f;
+  if (MODE != DS_FWD_STATS) {
+    mean1 = it.mean1[ch], istd1 = it.istd1[ch];
+    sc = it.g1[ch] * istd1, sh = it.b1[ch] - mean1 * sc;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) wp[co] = __ldg(it.wpw + co * C + ch);
+  }
+  if (MODE == DS_BWD_DZ) k0 = it.bn1_coef[ch], k1 = it.bn1_coef[C + ch], k2 = it.bn1_coef[2 * C + ch];
+  float cA[8], cB[8], cC[8];
+  if (MODE >= DS_BWD_STATS) {
+    const float *cf = it.coef + n * 8;
+    const int tot = a.batch * 8;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) cA[co] = cf[co], cB[co] = cf[tot + co], cC[co] = cf[2 * tot + co];
+  }
+  bool cok[NX];
+#pragma unroll
+  for (int j = 0; j < NX; ++j) cok[j] = c0 - P + j >= 0 && c0 - P + j < W;
+  float acc[K][WT];
+#pragma unroll
+  for (int s = 0; s < K; ++s)
+#pragma unroll
+    for (int j = 0; j < WT; ++j) acc[s][j] = 0.f;
+  const float *xb = a.x + (int64_t)n * H * W * a.x_ld + ch;
+  const int64_t x_ld = a.x_ld;
+  const int R = r1 - r0, niter = R + K - 1, r_first = r0 - P;
+  const int co_mine = ch / G;            // output channel this lane holds after ds_reduce8
+  const bool owner = (ch % G) == 0;      // one lane of the group stores it
+  for (int i0 = 0; i0 < niter; i0 += K) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      const int i = i0 + u, rr = r_first + i;
+      if (i < niter) {
+        if (rr >= 0 && rr < H) {
+          float xv[NX];
+          const float *rowp = xb + ((int64_t)rr * W + (c0 - P)) * x_ld;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) xv[j] = cok[j] ? rowp[(int64_t)j * x_ld] : 0.f;
+#pragma unroll
+          for (int ky = 0; ky < K; ++ky) {
+            if ((unsigned)(i - ky) < (unsigned)R) {  // output row r0 + i - ky is inside the tile
+              const int s = (u - ky + K) % K;
+#pragma unroll
+              for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int j = 0; j < WT; ++j) acc[s][j] = fmaf(xv[kx + j], w[ky * K + kx], acc[s][j]);
+            }
+          }
+        }
+        const int sc_ = (u + 1) % K;  // slot of the output row completed by this step
+        if (i >= K - 1) {
+          const int o = r0 + i - (K - 1);
+#pragma unroll
+          for (int j = 0; j < WT; ++j) {
+            const int col = c0 + j;
+            const bool ok = col < W;  // (uniform over the channel lanes of a strip)
+            const float z = acc[sc_][j];
+            const int64_t pix = ((int64_t)n * H + o) * W + (ok ? col : 0);
+            if (MODE == DS_FWD_STATS) {
+              if (ok) acc_out[0] += z, acc_out[1] += z * z;
+            } else if (MODE == DS_FWD_Y) {
+              const float r = fmaxf(fmaf(z, sc, sh), 0.f);
+              float v[8];
+#pragma unroll
+              for (int co = 0; co < 8; ++co) v[co] = r * wp[co];
+              ds_reduce8<C>(v, lane);
+              if (ok && owner) {
+                it.y[pix * 8 + co_mine] = v[0];
+                acc_out[0] += v[0], acc_out[1] += v[0] * v[0];
+              }
+            } else {
+              const float4 glo = ld4(it.gm + pix * 8), ghi = ld4(it.gm + pix * 8 + 4);
+              const float4 ylo = ld4(it.y + pix * 8), yhi = ld4(it.y + pix * 8 + 4);
+              const float g8[8] = {glo.x, glo.y, glo.z, glo.w, ghi.x, ghi.y, ghi.z, ghi.w};
+              const float y8[8] = {ylo.x, ylo.y, ylo.z, ylo.w, yhi.x, yhi.y, yhi.z, yhi.w};
+              float dy[8], dr = 0.f;
+#pragma unroll
+              for (int co = 0; co < 8; ++co) {
+                dy[co] = fmaf(cA[co], g8[co], fmaf(cB[co], y8[co], cC[co]));
+                dr = fmaf(dy[co], wp[co], dr);
+              }
+              const float uu = fmaf(z, sc, sh);
+              const float du = (uu > 0.f && ok) ? dr : 0.f;
+              const float zhat = (z - mean1) * istd1;
+              if (MODE == DS_BWD_STATS) {
+                const float r = ok ? fmaxf(uu, 0.f) : 0.f;
+                acc_out[0] += du, acc_out[1] += du * zhat;
+#pragma unroll
+                for (int co = 0; co < 8; ++co) acc_out[2 + co] = fmaf(dy[co], r, acc_out[2 + co]);
+              } else {
+                const float dzv = it.training ? k0 * (du - k1 - zhat * k2) : k0 * du;
+                if (it.dz_bf) {  // pack two channels per 32-bit store
+                  const float nb = __shfl_down_sync(0xffffffffu, dzv, 1);
+                  if (ok && !(lane & 1))
+                    reinterpret_cast<uint32_t *>(it.dz)[(pix * C + ch) >> 1] = senas_pack_bf2(dzv, nb);
+                } else if (ok) {
+                  it.dz[pix * C + ch] = dzv;
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < WT; ++j) acc[sc_][j] = 0.f;
+      }
+    }
+  }
+}
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(128, 3) ds_norm_kernel(DsArgs a) {
+  constexpr int STRIPS = DsGeo<C>::STRIPS, NACC = MODE == DS_BWD_STATS ? 10 : 2;
+  __shared__ float s_red[4][NACC][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n = blockIdx.y;
+  const int tx = blockIdx.x % a.tiles_x, ty = blockIdx.x / a.tiles_x;
+  const int strip = warp * STRIPS + lane / C;
+  const int c0 = tx * DsGeo<C>::TILE_W + strip * kDsCols;
+  const int r0 = ty * a.tile_rows, r1 = min(r0 + a.tile_rows, a.H);
+  for (int m = 0; m < a.n; ++m) {
+    const DsItem &it = a.it[m];
+    float acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.f;
+    // (strips that start beyond the right edge still walk: their lanes take part in the shuffles, all stores are masked)
+    if (it.k == 5) ds_walk<C, 5, MODE>(a, it, n, c0, r0, r1, lane, acc);
+    else ds_walk<C, 3, MODE>(a, it, n, c0, r0, r1, lane, acc);
+    if (MODE == DS_BWD_DZ) continue;
+    __syncthreads();  // s_red free (previous item)
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s_red[warp][j][lane] = acc[j];
+    __syncthreads();
+    float *out = it.partials + ((int64_t)n * gridDim.x + blockIdx.x) * (MODE == DS_FWD_STATS ? 2 * C : (MODE == DS_FWD_Y ? 16 : 10 * C));
+    if (MODE == DS_FWD_Y) {  // acc[0..1] = sum y, sum y^2 of output channel co in the owner lanes (ch % (C/8) == 0)
+      if (tid < 16) {
+        const int co = tid & 7, which = tid >> 3;
+        float r = 0.f;
+        for (int wv = 0; wv < 4; ++wv)
+          for (int s = 0; s < STRIPS; ++s) r += s_red[wv][which][s * C + co * (C / 8)];
+        out[tid] = r;
+      }
+    } else {  // per-channel values: combine the strips of a warp and the 4 warps in fixed order
+      for (int o = tid; o < NACC * C; o += 128) {
+        const int j = o / C, c = o - j * C;
+        float r = 0.f;
+        for (int wv = 0; wv < 4; ++wv)
+          for (int s = 0; s < STRIPS; ++s) r += s_red[wv][j][s * C + c];
+        // layouts: [sum z | sum z^2] and [sum du | sum du zhat | dW_pw[co][c]]
+        out[j * C + c] = r;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // dep-sep pointwise backward, quad layout (same as pw_fwd_kernel): LP = C/4 lanes share a pixel, lane l owns channels
 // 4l..4l+3 of z (one coalesced float4 per lane), the 8 dy values of the pixel are computed once by the group and
@@ -2120,7 +2395,8 @@ __global__ void __launch_bounds__(256, 2) pw_bwd_q_kernel(PwBwdArgs a, int px_pe
   const int p_begin = blockIdx.x * px_per_block, p_end = min(p_begin + px_per_block, a.hw);
   const int per_warp = (px_per_block + 7) / 8;
   const int w_begin = p_begin + warp * per_warp, w_end = min(w_begin + per_warp, p_end);
-  float *zn = a.z + (int64_t)n * a.hw * C + l * 4;
+  const int64_t z0 = (int64_t)n * a.hw * C + l * 4;
+  const int z_bf = a.z_bf;
   const float *gn = a.gm + (int64_t)n * a.hw * 8 + l * NDY, *yn = a.y + (int64_t)n * a.hw * 8 + l * NDY;
   for (int p0 = w_begin; p0 < w_end; p0 += PPW * UN) {
     float4 zv[UN];
@@ -2130,7 +2406,7 @@ __global__ void __launch_bounds__(256, 2) pw_bwd_q_kernel(PwBwdArgs a, int px_pe
       const int p = p0 + u * PPW + sub;
       const bool ok = p < w_end;
       const int pp = ok ? p : w_begin;
-      zv[u] = ld4(zn + (int64_t)pp * C);
+      zv[u] = ldx4(a.z, z0 + (int64_t)pp * C, z_bf);
       if (NDY == 4) {
         const float4 g4 = ld4(gn + (int64_t)pp * 8), y4 = ld4(yn + (int64_t)pp * 8);
         dyl[u][0] = cA[0] * g4.x + cB[0] * y4.x + cC[0];
@@ -2167,7 +2443,7 @@ __global__ void __launch_bounds__(256, 2) pw_bwd_q_kernel(PwBwdArgs a, int px_pe
           dzo[j] = training ? k0[j] * (du - k1[j] - zhat * k2[j]) : k0[j] * du;
         }
       }
-      if (PASS == 2 && ok) st4(zn + (int64_t)p * C, make_float4(dzo[0], dzo[1], dzo[2], dzo[3]));
+      if (PASS == 2 && ok) stx4(a.z, z0 + (int64_t)p * C, make_float4(dzo[0], dzo[1], dzo[2], dzo[3]), z_bf);
     }
   }
   if (PASS == 1) {
@@ -2379,14 +2655,15 @@ template <int K>
 SENAS_DEVFN constexpr int up_off(int kk) { return (up_par<K>(kk) + K / 2 - kk) / 2; }  // in {-1, 0, 1}
 
 // x window rows i-1, i, i+1 and columns j-1, j, j+1 (zero outside the image) -> xw[3][3]
-SENAS_DEVFN void up_load_window(const float *inb, int64_t in_ld, int H, int W, int i, int j, float4 (&xw)[3][3]) {
+SENAS_DEVFN void up_load_window(const float *in, int64_t in0, int bf, int64_t in_ld, int H, int W, int i, int j,
+                                float4 (&xw)[3][3]) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int iy = i + r - 1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int ix = j + c - 1;
-      xw[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ld4(inb + ((int64_t)iy * W + ix) * in_ld) : f4zero();
+      xw[r][c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ldx4(in, in0 + ((int64_t)iy * W + ix) * in_ld, bf) : f4zero();
     }
   }
 }
@@ -2394,12 +2671,13 @@ SENAS_DEVFN void up_load_window(const float *inb, int64_t in_ld, int H, int W, i
 template <int C, int K, bool STATS>
 SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q,
                                 float *st) {
-  const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-  float *outb = it.out + (int64_t)n * 4 * H * W * it.out_ld + q * 4;  // [2H][2W][out_ld]
+  const int64_t in0 = (int64_t)n * H * W * it.in_ld + q * 4;
+  const int64_t out0 = (int64_t)n * 4 * H * W * it.out_ld + q * 4;  // [2H][2W][out_ld]
   const float *wq = s_w + q * 4;
+  const int out_bf = it.out_bf;
   for (int i = by0; i < by1; ++i) {
     float4 xw[3][3];
-    up_load_window(inb, it.in_ld, H, W, i, j, xw);
+    up_load_window(it.in, in0, it.in_bf, it.in_ld, H, W, i, j, xw);
     float4 acc[2][2];
     acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = f4zero();
 #pragma unroll
@@ -2412,13 +2690,14 @@ SENAS_DEVFN void dw_up_fwd_rows(const DwItem &it, const float *s_w, int n, int H
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
         float4 v = acc[py][px];
-        float *op = outb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * it.out_ld;
+        const int64_t oe = out0 + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * it.out_ld;
         if (it.accumulate) {
-          const float4 old = ld4(op);
+          const float4 old = ldx4(it.out, oe, out_bf);
           v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
         }
-        st4(op, v);
+        stx4(it.out, oe, v, out_bf);
         if (STATS) {
+          v = roundx4(v, out_bf);
           st[0] += v.x, st[1] += v.y, st[2] += v.z, st[3] += v.w;
           st[4] += v.x * v.x, st[5] += v.y * v.y, st[6] += v.z * v.z, st[7] += v.w * v.w;
         }
@@ -2430,13 +2709,14 @@ template <int C, int K, bool STATS>
 SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H, int W, int by0, int by1, int j, int q,
                                float *st) {
   constexpr int P = K / 2;
-  const float *dzb = it.in + (int64_t)n * 4 * H * W * it.in_ld + q * 4;  // high-resolution input [2H][2W][in_ld]
-  float *outb = it.out + (int64_t)n * H * W * it.out_ld + q * 4;
+  const int64_t dz0 = (int64_t)n * 4 * H * W * it.in_ld + q * 4;  // high-resolution input [2H][2W][in_ld]
+  const int64_t out0 = (int64_t)n * H * W * it.out_ld + q * 4;
   const float *wq = s_w + q * 4;
   const int OH = 2 * H, OW = 2 * W;
+  const int in_bf = it.in_bf, out_bf = it.out_bf;
   for (int i = by0; i < by1; ++i) {
-    float *op = outb + ((int64_t)i * W + j) * it.out_ld;
-    float4 acc = it.accumulate ? ld4(op) : f4zero();
+    const int64_t oe = out0 + ((int64_t)i * W + j) * it.out_ld;
+    float4 acc = it.accumulate ? ldx4(it.out, oe, out_bf) : f4zero();
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int oy = 2 * i + ky - P;
@@ -2445,11 +2725,12 @@ SENAS_DEVFN void dw_up_dx_rows(const DwItem &it, const float *s_w, int n, int H,
       for (int kx = 0; kx < K; ++kx) {
         const int ox = 2 * j + kx - P;
         if (ox < 0 || ox >= OW) continue;
-        fma4(acc, ld4(dzb + ((int64_t)oy * OW + ox) * it.in_ld), ld4(wq + (ky * K + kx) * C));
+        fma4(acc, ldx4(it.in, dz0 + ((int64_t)oy * OW + ox) * it.in_ld, in_bf), ld4(wq + (ky * K + kx) * C));
       }
     }
-    st4(op, acc);
+    stx4(it.out, oe, acc, out_bf);
     if (STATS) {
+      acc = roundx4(acc, out_bf);
       st[0] += acc.x, st[1] += acc.y, st[2] += acc.z, st[3] += acc.w;
       st[4] += acc.x * acc.x, st[5] += acc.y * acc.y, st[6] += acc.z * acc.z, st[7] += acc.w * acc.w;
     }
@@ -2514,15 +2795,16 @@ SENAS_DEVFN void dw_up_wgrad_rows(const DwItem &it, int n, int H, int W, int by0
   for (int t = 0; t < T; ++t) acc[t] = f4zero();
   if (active) {
     const int64_t ld2 = it.in2_ld ? it.in2_ld : C;
-    const float *inb = it.in + (int64_t)n * H * W * it.in_ld + q * 4;
-    const float *dzb = it.in2 + (int64_t)n * 4 * H * W * ld2 + q * 4;
+    const int64_t in0 = (int64_t)n * H * W * it.in_ld + q * 4, dz0 = (int64_t)n * 4 * H * W * ld2 + q * 4;
+    const int in2_bf = it.in2_bf;
     for (int i = by0; i < by1; ++i) {
       float4 xw[3][3], dz[2][2];
-      up_load_window(inb, it.in_ld, H, W, i, j, xw);
+      up_load_window(it.in, in0, it.in_bf, it.in_ld, H, W, i, j, xw);
 #pragma unroll
       for (int py = 0; py < 2; ++py)
 #pragma unroll
-        for (int px = 0; px < 2; ++px) dz[py][px] = ld4(dzb + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * ld2);
+        for (int px = 0; px < 2; ++px)
+          dz[py][px] = ldx4(it.in2, dz0 + ((int64_t)(2 * i + py) * (2 * W) + 2 * j + px) * ld2, in2_bf);
 #pragma unroll
       for (int ky = 0; ky < K; ++ky)
 #pragma unroll

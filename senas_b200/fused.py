@@ -53,7 +53,7 @@ def candidate_slots(op):
 
 
 _scratch = {}
-_flags = {'tc_bf16': False}
+_flags = {'tc_bf16': False, 'override': None}  # override: graph flags forced by the emulator tests
 _grad_sink = [None]
 
 
@@ -172,7 +172,9 @@ class GraphRunner:
         desc.n_inputs, desc.n_nodes, desc.n_edges = self.n_inputs, self.n_nodes, len(self.edges)
         desc.c_out, desc.node_relu = 8, int(self.node_relu)
         self.tc_bf16 = _flags['tc_bf16']
-        desc.reserved = 1 if self.tc_bf16 else 0
+        desc.reserved = 1 if self.tc_bf16 else 0  # bit 0 = bf16 mode (tcgen05 convs with bf16 operands)
+        if _flags['override'] is not None:
+            desc.reserved = int(_flags['override'])
         self.params, self.sizes, self.shapes = [], [], []
         off = 0
         for e, (cands, src, dst, op_type, c_in) in enumerate(self.edges):

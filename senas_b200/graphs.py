@@ -128,7 +128,7 @@ class GraphedSearchStep:
             self._run(capture=True, arch=arch)
         finally:
             self._set_concurrent(False)
-        self._variants[arch] = (self.graphs, self._lr())
+        self._variants[arch] = (self.graphs, self._lr(), self.loss)  # (each capture has its own static loss tensor)
 
     # -- the three segments -----------------------------------------------------------------------------------
     # Segments exchange gradients only through the two flat buckets (ordinary allocations): a segment packs its
@@ -241,6 +241,7 @@ class GraphedSearchStep:
         for dst, src in zip(self.static, (xt, yt, xv, yv)):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        self.loss = var[2]
         if not self.segmented:
             graphs[0].replay()
         else:

@@ -247,3 +247,60 @@ def test_cell_ragged_emulated(emu, cell_type, B, H, W):
     names = {id(p): n for n, p in c.named_parameters()}
     for p, gp in zip(runner.params, r['g_params']):
         check('grad.' + names[id(p)], gp, store[names[id(p)]].grad)
+
+
+def test_fused_depsep_bf16_dz_emulated(emu):
+    """Recompute path in bf16 mode (minus the tensor cores, which the emulator does not have): the forward is exact fp32
+    and the only rounded tensor is the gradient dz (bf16) -- every gradient meets the 2e-2 max-norm gate."""
+    import senas_oracle as oracle
+    import senas_b200
+    from senas_b200 import fused
+    B, H, W = 2, 10, 18
+    torch.manual_seed(33)
+    c = senas_b200.Cell(3, 1, 32, 32, 32, 'up')
+    c.apply(senas_b200.weights_init)
+    for mod in c.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.3)
+    store = oracle.clone_store(c.state_dict())
+    in0, in1 = torch.randn(B, 32, H, W), torch.randn(B, 32, H // 2, W // 2).relu()
+    wn, wc = torch.softmax(torch.randn(9, 6), -1), torch.softmax(torch.randn(9, 6), -1)
+    b = torch.softmax(torch.randn(9), -1)
+    t = [v.clone().requires_grad_(True) for v in (in0, in1, wn, wc, b)]
+    ref = oracle.cell_nodes(oracle.Params(store), 'up', *t)
+    gout = torch.randn(ref.shape)
+    ref.backward(gout)
+    edges = [op._edge(s, d) for op, s, d in zip(c._ops, c._srcs, c._dsts)]
+    fused._flags['override'] = 1
+    emu.senas_set_ds_fused(1)
+    try:
+        runner = GraphRunner(edges, n_inputs=2, n_nodes=3, node_relu=True, lib=emu)
+        alpha = torch.where(c._norm_rows, wn, wc)
+        r = run_graph_raw(runner, [in0, in1], alpha, b, gout, True)
+    finally:
+        fused._flags['override'] = None
+        emu.senas_set_ds_fused(0)
+    assert max_err(r['out'], ref.detach()) <= 1e-4
+    errs = {'gin0': max_err(r['g_ins'][0], t[0].grad), 'gin1': max_err(r['g_ins'][1], t[1].grad),
+            'gbeta': max_err(r['g_beta'], t[4].grad)}
+    names = {id(p): n for n, p in c.named_parameters()}
+    for p, gp in zip(runner.params, r['g_params']):
+        errs[names[id(p)]] = max_err(gp, store[names[id(p)]].grad)
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, bad
+    assert max(errs.values()) > 1e-6  # the bf16 storage really was in effect
+
+
+@pytest.mark.parametrize('name', ['mixed_norm32', 'mixed_norm8', 'cell_up'])
+def test_fused_depsep_recompute_emulated(emu, name):
+    """The experimental recompute path of the NORM dep-sep candidates (ds_norm_kernel, senas_set_ds_fused; off by
+    default): same golden fixtures, same 1e-4 gate -- the depthwise output is never stored, every sweep recomputes it."""
+    emu.senas_set_ds_fused(1)
+    try:
+        if name.startswith('mixed_'):
+            test_mixed_op_emulated(emu, name)
+        else:
+            test_cell_nodes_emulated(emu, name, 'up')
+    finally:
+        emu.senas_set_ds_fused(0)
