@@ -169,6 +169,9 @@ int senas_flush(void *stream);
  * recomputed from the input in every sweep and never stored).  Off by default (measured slower than the spill path on
  * B200); applies to graphs planned after the call.  Environment variable SENAS_DS_FUSED sets the default. */
 int senas_set_ds_fused(int on);
+/* bf16 mode: the convolutions that are not on the tcgen05 path (8 -> 8 node edges, maps not a multiple of 64 wide) run as
+ * mma.sync m16n8k8 TF32 (1; environment variable SENAS_GATHER_MMA) or as exact fp32 FMA (0, default: see DESIGN.md). */
+int senas_set_gather_mma(int on);
 /* per-kernel-family device timing (CUDA events on the launch stream): senas_profile(1) starts a
  * recording, senas_profile(0) stops it, senas_profile_dump() waits for the recorded events and writes
  * "family launches total_ms algorithmic_flops algorithmic_bytes" lines (returns the text length). */

@@ -48,7 +48,7 @@ class BwdArgs(C.Structure):
 
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
            'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_avgpool_forward',
-           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_profile',
+           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_gather_mma', 'senas_profile',
            'senas_profile_dump']
 
 
@@ -73,6 +73,7 @@ def bind(path):
     lib.senas_set_slot.argtypes = [C.c_int]
     lib.senas_set_defer.argtypes = [C.c_int]
     lib.senas_set_ds_fused.argtypes = [C.c_int]
+    lib.senas_set_gather_mma.argtypes = [C.c_int]
     lib.senas_flush.argtypes = [C.c_void_p]
     lib.senas_profile.argtypes = [C.c_int]
     lib.senas_profile_dump.argtypes = [C.c_char_p, C.c_int64]

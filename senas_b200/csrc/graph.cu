@@ -693,10 +693,20 @@ struct Sched {
   }
 };
 
+// Opt a kernel in to more than the default 48 KB of shared memory.  The attribute is per FUNCTION and only ever raised:
+// a launch recorded in a CUDA graph is replayed with whatever value the function has at replay time, so a later, smaller
+// launch of the same kernel must not lower it (found in round 2: replayed launches of a captured step failed silently).
+// Static shared memory counts against the default as well: everything above 46 KB opts in.
 template <typename K>
 static void allow_smem(K kern, size_t bytes) {
 #ifndef SENAS_EMU
-  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static std::map<const void *, size_t> granted;
+  if (bytes <= 46 * 1024) return;
+  size_t &cur = granted[(const void *)kern];
+  if (bytes > cur) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cur = bytes;
+  }
 #else
   (void)kern, (void)bytes;
 #endif
@@ -717,22 +727,35 @@ static size_t gather_smem(const Geo &g, int NC, int pix) {
 }
 
 template <int KC, int NC, int NPH, int PIX>
-static void launch_gather(GatherArgs &a, const Geo &g, int B, void *stream) {
-  auto kern = gather_mac_kernel<KC, NC, NPH, PIX>;
-  const size_t smem = gather_smem(g, NC, PIX);
-  allow_smem(kern, smem);
+static void launch_gather(GatherArgs &a, const Geo &g, int B, void *stream, bool mma) {
+  // mma: bf16 mode -- the same tile and staging with the inner product on tensor cores (gather_mma_kernel, TF32 mma.sync)
+  const size_t smem = gather_smem(g, mma ? GatherMma<NC>::NCP : NC, PIX);
   a.tiles_x = cdiv(a.base_w, kTileW * PIX);
   dim3 grid(a.tiles_x * cdiv(a.base_h, kTileH), B);
-  SENAS_LAUNCH(kern, grid, dim3(kTileThreads), smem, stream, a);
+  if (mma) {
+    auto kern = gather_mma_kernel<KC, NC, NPH, PIX>;
+    allow_smem(kern, smem);
+    SENAS_LAUNCH(kern, grid, dim3(kTileThreads), smem, stream, a);
+  } else {
+    auto kern = gather_mac_kernel<KC, NC, NPH, PIX>;
+    allow_smem(kern, smem);
+    SENAS_LAUNCH(kern, grid, dim3(kTileThreads), smem, stream, a);
+  }
 }
 
-static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream) {
+// bf16 mode: the convolutions that are not on the tcgen05 path through mma.sync TF32 (gather_mma_kernel).  OFF by default:
+// measured 38 vs 29 TFLOP/s on the 8 -> 8 edges of the head cell but only 94.1 -> 92.1 ms per search step (the kernel is
+// bound by its serial stage -> sync -> MMA -> store structure, not by the FMA pipe), and the extra TF32 rounding on the node
+// edges flipped a near-tie of the fixed-seed genotype gate.  Opt in with SENAS_GATHER_MMA=1 / senas_set_gather_mma(1).
+static int g_gather_mma = env_flag("SENAS_GATHER_MMA", 0);
+static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream, bool mma = false) {
   const int nph = g.taps.nphase, pix = gather_pix(NC, g.si, a.base_w);
+  mma = mma && g_gather_mma;
 #define SENAS_GATHER(KC_, NC_, NPH_)                                                       \
   if (KC == KC_ && NC == NC_ && nph == NPH_) {                                             \
-    if (pix == 4 && NC_ == 8) launch_gather<KC_, NC_, NPH_, (NC_ == 8 ? 4 : 2)>(a, g, B, stream); \
-    else if (pix >= 2) launch_gather<KC_, NC_, NPH_, 2>(a, g, B, stream);                  \
-    else launch_gather<KC_, NC_, NPH_, 1>(a, g, B, stream);                                \
+    if (pix == 4 && NC_ == 8) launch_gather<KC_, NC_, NPH_, (NC_ == 8 ? 4 : 2)>(a, g, B, stream, mma); \
+    else if (pix >= 2) launch_gather<KC_, NC_, NPH_, 2>(a, g, B, stream, mma);                  \
+    else launch_gather<KC_, NC_, NPH_, 1>(a, g, B, stream, mma);                                \
     return 0;                                                                              \
   }
   SENAS_GATHER(32, 8, 1)
@@ -983,7 +1006,7 @@ static int forward_edge(Call &c, int e, bool second_pass) {
         SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_fwd.down" : (C == 8 ? "conv_fwd.n8" : (ed.op_type == SENAS_OP_UP ? "conv_fwd.up_small" : "conv_fwd.n32_small")),
                   2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                   4.0 * B * (ep.in_h * ep.in_w * C + p.hw * 8));
-        if (launch_gather_any(a, geo, C, 8, B, st)) return 1;
+        if (launch_gather_any(a, geo, C, 8, B, st, (c.d->reserved & 1) != 0)) return 1;
         break;
       }
       case SENAS_KIND_DEPSEP: {
@@ -1032,6 +1055,13 @@ static int check_common(senas_graph *g, int batch, const int32_t *ih, const int3
 
 static int check_cuda(const char *what) {
   cudaError_t e = cudaGetLastError();
+#ifndef SENAS_EMU
+  if (g_launch_err != cudaSuccess) {
+    const cudaError_t le = g_launch_err;
+    g_launch_err = cudaSuccess;
+    SENAS_FAIL("%s: launch of a '%s' kernel failed: %s", what, g_launch_err_tag, cudaGetErrorString(le));
+  }
+#endif
   if (e != cudaSuccess) SENAS_FAIL("%s: CUDA error %s", what, cudaGetErrorString(e));
   return 0;
 }
@@ -1289,7 +1319,7 @@ static int backward_edge(BwdCall &c, int e) {
           SENAS_TAG(ed.op_type == SENAS_OP_DOWN ? "conv_dgrad.down" : (C == 8 ? "conv_dgrad.n8" : (ed.op_type == SENAS_OP_UP ? "conv_dgrad.up" : "conv_dgrad.n32_small")),
                     2.0 * B * a.base_h * a.base_w * geo.taps.n * C * 8,
                     4.0 * B * (ep.in_h * ep.in_w * C + HW * 16));
-          if (launch_gather_any(a, geo, 8, C, B, sdx)) return 1;
+          if (launch_gather_any(a, geo, 8, C, B, sdx, (c.d->reserved & 1) != 0)) return 1;
           c.touched[ed.src] = true;
         }
         if (ed.grad_off[k][0] >= 0 && !(t.tc && c.a->grad_in[ed.src])) {
@@ -1821,6 +1851,10 @@ extern "C" int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int
   SENAS_TAG("stock_avgpool", 0, 4.0 * B * H * W * C * 1.25);
   SENAS_LAUNCH(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, gx, B, H, W, C);
   return check_cuda("avgpool backward");
+}
+extern "C" int senas_set_gather_mma(int on) {  // bf16 mode: mma.sync (1, default) or CUDA-core FMA (0) for the non-tcgen05 convs
+  g_gather_mma = on != 0;
+  return 0;
 }
 extern "C" int senas_set_ds_fused(int on) {  // affects graphs planned afterwards
   g_ds_fused = on != 0;

@@ -282,6 +282,203 @@ __global__ void __launch_bounds__(kTileThreads) gather_mac_kernel(GatherArgs a) 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// gather-MMA: the same tap-table convolution (forward and data gradient) as gather_mac_kernel, with the inner product on
+// the tensor cores: warp-level mma.sync m16n8k8, TF32 operands (10-bit mantissa, rounded to nearest when the tile is
+// staged), fp32 accumulation.  bf16 mode only (gate 2e-2); it takes every dense / dilated / strided / transposed
+// convolution that the tcgen05 path does not: the 8 -> 8 node edges (K = 8 per tap is exactly one k8 step, no channel
+// padding) and all maps that are not a multiple of 64 pixels wide (M = 16-pixel row segments, no strip constraint).
+// Tile, staging (8-channel chunks as float4 lo / hi per gathered pixel) and tap tables are gather_mac's; a warp owns two
+// tile rows = 2 * PIX m16 tiles.  Fragments (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3
+//   A: a0 = (row g, k t)  a1 = (row g + 8, k t)  a2 = (row g, k t + 4)  a3 = (row g + 8, k t + 4)     row = pixel
+//   B: b0 = (k t, n g)    b1 = (k t + 4, n g)                                                          n = out channel
+//   D: d0 = (row g, n 2t) d1 = (row g, n 2t + 1) d2 = (row g + 8, n 2t) d3 = (row g + 8, n 2t + 1)
+// A reads: lane (g, t) takes component t of pixel g's float4 -> 32 lanes cover 128 contiguous bytes (stride 1).
+// ------------------------------------------------------------------------------------------------
+#ifdef SENAS_EMU
+static inline float senas_tf32(float v) { return v; }  // the emulator checks the indexing in exact arithmetic
+static inline void senas_mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+  const int lane = emu::flat_tid() % 32, g = lane >> 2, t = lane & 3;
+  float add[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < 8; ++k) {
+    const float a_lo = __shfl_sync(0xffffffffu, k < 4 ? a[0] : a[2], g * 4 + (k & 3));   // A[g][k]
+    const float a_hi = __shfl_sync(0xffffffffu, k < 4 ? a[1] : a[3], g * 4 + (k & 3));   // A[g + 8][k]
+    const float b_0 = __shfl_sync(0xffffffffu, k < 4 ? b[0] : b[1], (2 * t) * 4 + (k & 3));      // B[k][2t]
+    const float b_1 = __shfl_sync(0xffffffffu, k < 4 ? b[0] : b[1], (2 * t + 1) * 4 + (k & 3));  // B[k][2t + 1]
+    add[0] += a_lo * b_0, add[1] += a_lo * b_1, add[2] += a_hi * b_0, add[3] += a_hi * b_1;
+  }
+  for (int i = 0; i < 4; ++i) d[i] += add[i];
+}
+#else
+SENAS_DEVFN float senas_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+SENAS_DEVFN void senas_mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+}
+#endif
+
+template <int NC>
+struct GatherMma {
+  static constexpr int NCP = NC == 8 ? 8 : NC + 8;  // weight row stride in shared memory (conflict-free B fragments)
+};
+
+template <int KC, int NC, int NPH, int PIX>
+__global__ void __launch_bounds__(kTileThreads) gather_mma_kernel(GatherArgs a) {
+  constexpr int NCH = KC / 8, NT = NC / 8, MT = 2 * PIX, NCP = GatherMma<NC>::NCP;
+  constexpr bool kPhaseOuter = (NCH == 1);
+  constexpr int NLIVE = kPhaseOuter ? 1 : NPH;
+  constexpr int TW = kTileW * PIX;
+  SENAS_DYN_SMEM(float4, smem);
+  __shared__ float s_coef[24];
+  __shared__ float s_st[4][16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int n = blockIdx.y, tile = blockIdx.x;
+  const int by0 = (tile / a.tiles_x) * kTileH, bx0 = (tile % a.tiles_x) * TW;
+  const int R = (kTileH - 1) * a.si + (a.taps.max_dy - a.taps.min_dy) + 1;
+  const int Cc = (TW - 1) * a.si + (a.taps.max_dx - a.taps.min_dx) + 1;
+  const int npx = R * Cc;
+  float4 *s_lo = smem, *s_hi = smem + npx;
+  const float *f_lo = reinterpret_cast<const float *>(s_lo), *f_hi = reinterpret_cast<const float *>(s_hi);
+  float *s_w = reinterpret_cast<float *>(smem + 2 * npx);
+  const bool affine = a.src2 != nullptr;
+  if (affine) {
+    if (tid < 24) {
+      const float *t = tid < 8 ? a.coefA : (tid < 16 ? a.coefB : a.coefC);
+      s_coef[tid] = t[n * 8 + (tid & 7)];
+    }
+    __syncthreads();
+  }
+  float acc[NLIVE][MT][NT][4];
+#pragma unroll
+  for (int p = 0; p < NLIVE; ++p)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[p][m][j][i] = 0.f;
+  float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
+
+  const int gy0 = by0 * a.si + a.taps.min_dy, gx0 = bx0 * a.si + a.taps.min_dx;
+  const float *srcn = a.src + (int64_t)n * a.src_h * a.src_w * a.src_ld;
+  const float *src2n = affine ? a.src2 + (int64_t)n * a.src_h * a.src_w * a.src2_ld : nullptr;
+  float *dstn = a.dst + (int64_t)n * a.dst_h * a.dst_w * a.dst_ld;
+
+  // m-tile m of this warp: tile row 2 * warp + m / PIX, columns (m % PIX) * 16 .. + 15
+  auto epilogue = [&](int m, int ph, float (&r)[NT][4]) {
+    const int by = by0 + 2 * warp + m / PIX;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int bx = bx0 + (m % PIX) * 16 + g + half * 8;
+      const int oy = by * a.so + (ph >> 1), ox = bx * a.so + (ph & 1);
+      if (by < a.base_h && bx < a.base_w && oy < a.dst_h && ox < a.dst_w) {
+        float *o = dstn + ((int64_t)oy * a.dst_w + ox) * a.dst_ld + 2 * tq;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          float v0 = r[j][2 * half], v1 = r[j][2 * half + 1];
+          if (a.accumulate) v0 += o[j * 8], v1 += o[j * 8 + 1];
+          o[j * 8] = v0, o[j * 8 + 1] = v1;
+          if (NC == 8) st_s[0] += v0, st_s[1] += v1, st_q[0] += v0 * v0, st_q[1] += v1 * v1;
+        }
+      }
+    }
+  };
+
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (ch > 0) __syncthreads();
+    for (int i = tid; i < npx; i += kTileThreads) {
+      const int r = i / Cc, c = i - r * Cc;
+      const int gy = gy0 + r, gx = gx0 + c;
+      float4 lo = f4zero(), hi = f4zero();
+      if (gy >= 0 && gy < a.src_h && gx >= 0 && gx < a.src_w) {
+        const int64_t pix = (int64_t)gy * a.src_w + gx;
+        const float *p = srcn + pix * a.src_ld + ch * 8;
+        lo = ld4(p), hi = ld4(p + 4);
+        if (affine) {
+          const float *q = src2n + pix * a.src2_ld;
+          const float4 ylo = ld4(q), yhi = ld4(q + 4);
+          lo.x = s_coef[0] * lo.x + s_coef[8] * ylo.x + s_coef[16];
+          lo.y = s_coef[1] * lo.y + s_coef[9] * ylo.y + s_coef[17];
+          lo.z = s_coef[2] * lo.z + s_coef[10] * ylo.z + s_coef[18];
+          lo.w = s_coef[3] * lo.w + s_coef[11] * ylo.w + s_coef[19];
+          hi.x = s_coef[4] * hi.x + s_coef[12] * yhi.x + s_coef[20];
+          hi.y = s_coef[5] * hi.y + s_coef[13] * yhi.y + s_coef[21];
+          hi.z = s_coef[6] * hi.z + s_coef[14] * yhi.z + s_coef[22];
+          hi.w = s_coef[7] * hi.w + s_coef[15] * yhi.w + s_coef[23];
+        }
+      }
+      s_lo[i] = make_float4(senas_tf32(lo.x), senas_tf32(lo.y), senas_tf32(lo.z), senas_tf32(lo.w));
+      s_hi[i] = make_float4(senas_tf32(hi.x), senas_tf32(hi.y), senas_tf32(hi.z), senas_tf32(hi.w));
+    }
+    for (int i = tid; i < a.taps.n * 8 * NC; i += kTileThreads) {
+      const int nn = i % NC, kk = (i / NC) & 7, t = i / (NC * 8);
+      s_w[(t * 8 + kk) * NCP + nn] =
+          senas_tf32(__ldg(a.w + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)(ch * 8 + kk) * a.ws_k + (int64_t)nn * a.ws_n));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ph = 0; ph < NPH; ++ph) {
+      const int pl = kPhaseOuter ? 0 : ph;
+      if (kPhaseOuter && NPH > 1) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[0][m][j][i] = 0.f;
+      }
+      for (int t = a.taps.pstart[ph]; t < a.taps.pstart[ph + 1]; ++t) {
+        float bf[NT][2];
+        const float *wt = s_w + t * 8 * NCP;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) bf[j][0] = wt[tq * NCP + j * 8 + g], bf[j][1] = wt[(tq + 4) * NCP + j * 8 + g];
+        const int tap_off = (a.taps.dy[t] - a.taps.min_dy) * Cc + (a.taps.dx[t] - a.taps.min_dx);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int row = 2 * warp + m / PIX, col = (m % PIX) * 16;
+          const int i0 = tap_off + row * a.si * Cc + (col + g) * a.si, i1 = i0 + 8 * a.si;
+          const float af[4] = {f_lo[i0 * 4 + tq], f_lo[i1 * 4 + tq], f_hi[i0 * 4 + tq], f_hi[i1 * 4 + tq]};
+#pragma unroll
+          for (int j = 0; j < NT; ++j) senas_mma_tf32(acc[pl][m][j], af, bf[j]);
+        }
+      }
+      if (kPhaseOuter) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) epilogue(m, ph, acc[0][m]);
+      }
+    }
+  }
+  if (!kPhaseOuter) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int ph = 0; ph < NPH; ++ph) epilogue(m, ph, acc[ph][m]);
+  }
+  if (a.partials != nullptr) {  // uniform.  lane (g, tq) holds channels 2tq, 2tq + 1: sum over g, then over the warps
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {
+      st_s[0] += __shfl_xor_sync(0xffffffffu, st_s[0], m), st_s[1] += __shfl_xor_sync(0xffffffffu, st_s[1], m);
+      st_q[0] += __shfl_xor_sync(0xffffffffu, st_q[0], m), st_q[1] += __shfl_xor_sync(0xffffffffu, st_q[1], m);
+    }
+    if (lane < 4) {
+      s_st[warp][2 * lane] = st_s[0], s_st[warp][2 * lane + 1] = st_s[1];
+      s_st[warp][8 + 2 * lane] = st_q[0], s_st[warp][8 + 2 * lane + 1] = st_q[1];
+    }
+    __syncthreads();
+    if (tid < 16)
+      a.partials[((int64_t)n * gridDim.x + blockIdx.x) * 16 + tid] =
+          (s_st[0][tid] + s_st[1][tid]) + (s_st[2][tid] + s_st[3][tid]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // convolution weight gradient: dW[t][ci][co] = sum_b x[b*si + d_t][ci] * dy[b*so + phase_t][co]
 // thread = (ci, tap group); x read straight from global/L1 (32 consecutive ci = one 128 B line),

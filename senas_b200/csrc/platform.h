@@ -33,10 +33,18 @@ static inline int prof_begin(const char *name, double flops, double bytes, void 
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
 }
+// first launch that the runtime refused (bad configuration, too much shared memory ...): reported by check_cuda() with
+// the family tag of the kernel, so that a launch that never ran cannot pass silently
+static cudaError_t g_launch_err = cudaSuccess;
+static const char *g_launch_err_tag = "";
 #define SENAS_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
   do {                                                                                      \
     const int pr_ = g_prof_on ? prof_begin(g_tag, g_tag_flops, g_tag_bytes, (stream)) : -1; \
     kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                 \
+    {                                                                                       \
+      const cudaError_t le_ = cudaPeekAtLastError();                                        \
+      if (le_ != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = le_, g_launch_err_tag = g_tag; \
+    }                                                                                       \
     if (pr_ >= 0) cudaEventRecord(g_prof[pr_].e1, (cudaStream_t)(stream));                  \
     ++g_launch_count;                                                                       \
     g_tag = "other", g_tag_flops = g_tag_bytes = 0;                                         \

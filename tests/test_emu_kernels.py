@@ -304,3 +304,24 @@ def test_fused_depsep_recompute_emulated(emu, name):
             test_cell_nodes_emulated(emu, name, 'up')
     finally:
         emu.senas_set_ds_fused(0)
+
+
+@pytest.mark.parametrize('name', ['mixed_norm32', 'mixed_norm8', 'mixed_down32', 'mixed_down32_odd', 'mixed_up32', 'cell_up',
+                                  'cell_down'])
+def test_gather_mma_indexing_emulated(emu, name):
+    """Opt-in (senas_set_gather_mma): bf16 mode routes every convolution that is not on the tcgen05 path through
+    gather_mma_kernel (mma.sync m16n8k8 TF32).  The emulator evaluates the MMA from the documented fragment layouts in exact arithmetic (no TF32 rounding),
+    so the golden fixtures hold at the fp32 gate: tile / tap / phase / fragment indexing and the epilogue statistics."""
+    from senas_b200 import fused
+    fused._flags['override'] = 1
+    emu.senas_set_gather_mma(1)
+    n0 = emu.senas_launch_count()
+    try:
+        if name.startswith('mixed_'):
+            test_mixed_op_emulated(emu, name)
+        else:
+            test_cell_nodes_emulated(emu, name, name.split('_')[1])
+    finally:
+        fused._flags['override'] = None
+        emu.senas_set_gather_mma(0)
+    assert emu.senas_launch_count() > n0

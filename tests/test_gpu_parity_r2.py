@@ -164,6 +164,42 @@ def test_mixed_op_config2_size_vs_oracle(op_id, c_in, H):
         del mg, xg, out
 
 
+@pytest.mark.parametrize('op_id,c_in,H', [(3, 8, 64), (3, 8, 128), (2, 32, 64), (1, 32, 32), (3, 32, 32)])
+def test_gather_mma_opt_in_vs_oracle(op_id, c_in, H):
+    """senas_set_gather_mma(1): the convolutions that are not on the tcgen05 path as mma.sync m16n8k8 TF32 (8 -> 8 node edges,
+    maps narrower than 64 pixels; forward, data gradient, with phases and strides) against the oracle at the 2e-2 gate of
+    the reduced-precision mode.  (2, 32, 64) is the case whose 49 KB tile needs the shared-memory opt-in.)  Off by
+    default, see DESIGN.md."""
+    B = 16
+    m = _randomised_mixed(c_in, op_id, 500 + op_id + c_in + H)
+    store = oracle.clone_store(m.state_dict())
+    gen = torch.Generator().manual_seed(7 * H + op_id)
+    x = torch.randn(B, c_in, H, H, generator=gen)
+    alpha = torch.softmax(torch.randn(6, generator=gen), -1)
+    xo, ao = x.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], xo, ao, True)
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout)
+    lib = senas_b200._lib.get()
+    senas_b200.set_conv_mode('bf16')
+    lib.senas_set_gather_mma(1)
+    try:
+        mg = copy.deepcopy(m).to(DEV)
+        xg, ag = x.to(DEV).requires_grad_(True), alpha.to(DEV).requires_grad_(True)
+        out = mg(xg, ag, ag)
+        out.backward(gout.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.senas_set_gather_mma(0)
+    check('out', out, ref.detach(), 2e-2)
+    flip_tolerant('gx', xg.grad, xo.grad, 2e-2, flips=8, footprint=25)
+    check('galpha', ag.grad, ao.grad, 2e-2)
+    for n, p in mg.named_parameters():
+        check('grad.' + n, p.grad, store[n].grad, 2e-2)
+    # and it is not the exact path: TF32 rounding is visible
+    assert max_err(out, ref.detach()) > 1e-6
+
+
 def test_head_cell_config2_size_vs_oracle():
     """The head up-cell of the config-2 supernet (in0 16x32x256x256, in1 16x32x128x128): node loop + concat against the
     oracle in fp32 mode.  Every node ends in a ReLU: among 1e8 pre-activations some lie within fp32 rounding of 0 and
