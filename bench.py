@@ -330,9 +330,16 @@ def run_ours(args, rank, world, local_rank):
     crit = SegmentationLosses('dice_ce', group=group)
     w_opt = torch.optim.SGD(model.parameters(), lr=5e-3, momentum=0.9, weight_decay=3e-4)
     a_opt = torch.optim.Adam(model.arch_parameters(), lr=1e-4, betas=(0.5, 0.999), weight_decay=1e-3)
-    buckets = None
+    buckets, comm = None, None
     if world > 1:
         broadcast_parameters(model)
+        if not args.no_comm:  # NCCL communicator owned by libsenas_b200: its all-reduces are captured into the step's graph
+            try:
+                from senas_b200.comm import Comm
+                comm = Comm(group=group, device=dev)
+            except Exception as e:
+                print(f'senas_b200.Comm unavailable ({type(e).__name__}: {e}); torch.distributed all-reduces between graphs',
+                      file=sys.stderr)
 
     def make_eager_reducers():                    # eager DP path: NCCL all-reduces overlapped with backward
         fused_red = FusedGradReducer()            # cells: flat gradient buffers straight from the kernels
@@ -375,11 +382,15 @@ def run_ours(args, rank, world, local_rank):
             if world > 1:  # graphed DP path: local dice per rank, gradients averaged (senas_b200/graphs.py)
                 crit = SegmentationLosses('dice_ce')
             graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
-                                                   warmup=3, group=group,
+                                                   warmup=3, group=group, comm=comm,
                                                    capture_error_mode='thread_local' if world > 1 else 'global',
                                                    concurrent_cells=not args.serial_cells, defer_wgrad=args.defer_wgrad)
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
+            if world > 1:
+                graph_note = ('cuda-graph (one graph per step with both NCCL gradient all-reduces captured inside, '
+                              'libsenas_b200 communicator)' if comm is not None else
+                              'cuda-graph (three graphs per step, two torch.distributed all-reduces between them)')
             search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731
         except Exception as e:  # keep measuring, but say so
             graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
@@ -425,6 +436,7 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = timed(e2e, args.steps)
     clk = clocks.stop() if clocks else None
 
+    mem_main = torch.cuda.max_memory_allocated() / 2 ** 30
     # per-kernel-family device time (CUDA events on the launch stream), one more step
     lib.senas_profile(1)
     barrier()
@@ -434,7 +446,55 @@ def run_ours(args, rank, world, local_rank):
     prof = _lib.profile_dump(lib)
     total_ms = sum(v['ms'] for v in prof.values()) or 1.0
 
+    # BASELINE config 3: global batch 128 at N = 2 / 4 / 8 (64 / 32 / 16 images per GPU).  The weak-scaling line above
+    # keeps 16 images per GPU at every N (N = 8 IS config 3); at N = 2, 4 the config-3 point is measured here as well, on
+    # a second captured step of the larger per-GPU batch.
+    config3 = None
+    if world == 8 and B * world == 128:
+        config3 = {'global_batch': 128, 'per_gpu_batch': B, 'same_as_value': True}
+    elif world in (2, 4) and graphed is not None and not args.no_config3:
+        try:
+            graphed.release()
+            del search_step
+            torch.cuda.empty_cache()
+            B3 = 128 // world
+            host3 = [synth(B3, size, 4321 + 17 * rank + i, False) for i in range(2)]
+            dev3 = [(x.to(dev), y.to(dev)) for x, y in host3]
+            step3 = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*dev3[0], *dev3[1]), grad_clip=5.0, warmup=2,
+                                                 group=group, comm=comm, capture_error_mode='thread_local',
+                                                 concurrent_cells=not args.serial_cells)
+            for _ in range(2):
+                step3(*dev3[0], *dev3[1])
+            n3 = min(args.steps, 10)
+            ms3 = timed(lambda i: step3(*dev3[0], *dev3[1]), n3) / n3
+            config3 = {'global_batch': 128, 'per_gpu_batch': B3, 'ms_per_step': ms3, 'value': 128 / (ms3 * 1e-3),
+                       'unit': 'images/s', 'steps': n3, 'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
+            step3.release()
+            del step3
+        except Exception as e:
+            config3 = {'failed': f'{type(e).__name__}: {str(e)[:200]}'}
+    def teardown():
+        """Every rank: graphs first, then the communicator, then the process group; a watchdog ends the process if a
+        collective teardown blocks (the JSON line is already out by then)."""
+        if world <= 1:
+            return
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        try:
+            if graphed is not None:
+                graphed.release()
+            torch.cuda.synchronize()
+            if comm is not None:
+                comm.destroy()
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
     if rank != 0:
+        teardown()
         return
     pk = peaks()
     gB = B * world
@@ -483,6 +543,9 @@ def run_ours(args, rank, world, local_rank):
                 'h2d_bytes_per_step': 2 * B * size * size * (4 + 8), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'roofline': roof, 'kernel_families': families, 'clocks': clk,
     }
+    if config3 is not None:
+        out['config3'] = config3
+    out['peak_mem_gb'] = mem_main
     if world == 1 and not args.no_cpu:
         # the unmodified reference on the host cores: ONE search step at the full batch after a tiny warm-up
         cpu_reference_sample(64, 1, 1, 0)                      # thread pool / allocator warm-up on a tiny input
@@ -506,8 +569,7 @@ def run_ours(args, rank, world, local_rank):
     os.dup2(real_stdout, 1)
     print(json.dumps(out), flush=True)
     os.dup2(2, 1)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
@@ -526,6 +588,8 @@ def main():
     ap.add_argument('--no-ref-gpu', action='store_true', help='skip the reference-on-B200 (stock PyTorch) leg')
     ap.add_argument('--no-fp32-line', action='store_true', help='skip the fp32-mode measurement beside the bf16 one')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-comm', action='store_true', help='data parallel: keep the all-reduces outside the graphs (torch.distributed)')
+    ap.add_argument('--no-config3', action='store_true', help='N = 2, 4: skip the BASELINE config-3 leg (global batch 128)')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
     ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')
     ap.add_argument('--conv-mode', default='bf16', choices=['fp32', 'bf16'],

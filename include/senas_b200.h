@@ -169,6 +169,16 @@ int senas_flush(void *stream);
  * recomputed from the input in every sweep and never stored).  Off by default (measured slower than the spill path on
  * B200); applies to graphs planned after the call.  Environment variable SENAS_DS_FUSED sets the default. */
 int senas_set_ds_fused(int on);
+
+/* Data-parallel gradient exchange, one process per GPU (replaces the reference's in-process replica path,
+ * search/senas_search.py:262-279 and utils/utils.py:233-237, broken as shipped).  NCCL over NVLink 5 / NVSwitch, bound
+ * with dlopen at the first call (no link-time dependency).  senas_comm_unique_id fills 128 bytes on one rank; the host
+ * distributes them (any channel) and every rank calls senas_comm_init with its CUDA device current.  The all-reduce is an
+ * in-place fp32 SUM enqueued on `stream`; it may be captured into a CUDA graph together with the kernels around it. */
+int senas_comm_unique_id(void *id128);
+int senas_comm_init(const void *id128, int rank, int world, void **comm);
+int senas_comm_allreduce(void *comm, float *buf, int64_t count, void *stream);
+int senas_comm_destroy(void *comm);
 /* bf16 mode: the convolutions that are not on the tcgen05 path (8 -> 8 node edges, maps not a multiple of 64 wide) run as
  * mma.sync m16n8k8 TF32 (1; environment variable SENAS_GATHER_MMA) or as exact fp32 FMA (0, default: see DESIGN.md). */
 int senas_set_gather_mma(int on);

@@ -48,7 +48,8 @@ class BwdArgs(C.Structure):
 
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
            'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_avgpool_forward',
-           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_gather_mma', 'senas_profile',
+           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_gather_mma', 'senas_comm_unique_id', 'senas_comm_init',
+           'senas_comm_allreduce', 'senas_comm_destroy', 'senas_profile',
            'senas_profile_dump']
 
 
@@ -74,6 +75,10 @@ def bind(path):
     lib.senas_set_defer.argtypes = [C.c_int]
     lib.senas_set_ds_fused.argtypes = [C.c_int]
     lib.senas_set_gather_mma.argtypes = [C.c_int]
+    lib.senas_comm_unique_id.argtypes = [C.c_void_p]
+    lib.senas_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.senas_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.senas_comm_destroy.argtypes = [C.c_void_p]
     lib.senas_flush.argtypes = [C.c_void_p]
     lib.senas_profile.argtypes = [C.c_int]
     lib.senas_profile_dump.argtypes = [C.c_char_p, C.c_int64]

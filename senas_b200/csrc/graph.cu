@@ -32,6 +32,7 @@ static int tc_rows(int H, int W, int B, int span_y) {
   return best_rows;
 }
 #include "conv_tc.cuh"
+#include "comm.cuh"
 
 #ifdef SENAS_EMU
 static void *dev_upload(const void *h, size_t n) {
@@ -185,14 +186,29 @@ static const int kDwRows = 4;       // output rows per block in the sliding-wind
 static int gather_pix(int NC, int si, int base_w);
 // grouped depthwise kernels: columns per tile (forward / data gradient: kDwCols per thread; weight gradient: 1 per thread) and
 // rows per tile, the largest of 32/16/8/4 that still gives the 148 SMs at least four blocks each
-static int dw_tiles_x(int C, int w, bool wgrad) { return cdiv(w, (wgrad ? 1 : kDwCols) * (128 / (C / 4))); }
-static int dw_rows(int C, int B, int h, int w, bool wgrad) {
-  const int tx = dw_tiles_x(C, w, wgrad);
+// lane = channel kernels (dwl_*): NORM edges whose map is at least half a tile wide (narrower maps would idle warps)
+// SENAS_DW_LANE bit mask: 1 / 2 = weight gradient (C = 32 / 8), 4 / 8 = forward, 16 / 32 = data gradient.  Measured per bit
+// on the head cell / a 128 x 128 up cell (scripts/lane_ab.sh, profiles/README.md): the weight gradient wins (1.56 -> 1.28
+// ms, 0.54 -> 0.43 ms), forward and data gradient lose 5-20 % in place although the isolated forward kernel is faster
+// (scripts/ubench/dwbench.cu) -- default 3.
+enum { DWL_WGRAD = 0, DWL_FWD = 2, DWL_DX = 4 };
+static int g_dw_lane = env_flag("SENAS_DW_LANE", 3);
+static int dwl_tile_w(int C) { return C == 32 ? DwLane<32>::TILE_W : DwLane<8>::TILE_W; }
+static bool dw_lane_ok(int C, int w, int what) {
+  return ((g_dw_lane >> what) & (C == 32 ? 1 : 2)) && 2 * w >= dwl_tile_w(C);
+}
+static int dw_tiles_x(int C, int w, bool wgrad, bool lane = false) {
+  return lane ? cdiv(w, dwl_tile_w(C)) : cdiv(w, (wgrad ? 1 : kDwCols) * (128 / (C / 4)));
+}
+static int dw_rows(int C, int B, int h, int w, bool wgrad, bool lane = false) {
+  const int tx = dw_tiles_x(C, w, wgrad, lane);
   for (int r = 32; r > 4; r /= 2)
     if (tx * cdiv(h, r) * B >= 4 * 148) return r;
   return 4;
 }
-static int dw_nblk(int C, int B, int h, int w, bool wgrad) { return dw_tiles_x(C, w, wgrad) * cdiv(h, dw_rows(C, B, h, w, wgrad)); }
+static int dw_nblk(int C, int B, int h, int w, bool wgrad, bool lane = false) {
+  return dw_tiles_x(C, w, wgrad, lane) * cdiv(h, dw_rows(C, B, h, w, wgrad, lane));
+}
 
 // fused dep-sep kernels (ds_norm_kernel): tile = DsGeo<C>::TILE_W columns x rows, the largest of 32/16/8 rows that still
 // gives the 148 SMs a few blocks each
@@ -387,7 +403,7 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           const int bh = geo.base_is_out ? p->out_h : ep.in_h, bw = geo.base_is_out ? p->out_w : ep.in_w;
           t.nblk1 = cdiv(bh * bw, 128 / (C / 4));
           t.dwg = ed.op_type != SENAS_OP_DOWN || (ep.in_h == 2 * p->out_h && ep.in_w == 2 * p->out_w && C == 32);
-          if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false);  // dw_multi_kernel grid
+          if (ed.op_type == SENAS_OP_NORM) t.nblk1 = dw_nblk(C, B, bh, bw, false, dw_lane_ok(C, bw, DWL_FWD));  // dw(l)_multi_kernel grid
           if (ed.op_type == SENAS_OP_UP) t.nblk1 = dw_nblk(C, B, bh, bw, true);     // dw_up_multi_kernel grid (input grid)
           if (ed.op_type == SENAS_OP_DOWN && t.dwg) t.nblk1 = dw_nblk(C, B, p->out_h, p->out_w, true);  // (output grid)
           t.nblk = cdiv(HW, kPwPx);  // pw_fwd_kernel grid
@@ -405,7 +421,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           tmp_need = std::max<int64_t>(tmp_need, std::max(pw_tmp, dw_tmp));
           if (t.dwg)  // grouped weight gradient: one partial per block and convolution
             tmp_need = std::max<int64_t>(tmp_need, (int64_t)B * dw_nblk(C, B, ed.op_type == SENAS_OP_DOWN ? p->out_h : bh,
-                                                                        ed.op_type == SENAS_OP_DOWN ? p->out_w : bw, true) * kDwMaxItems * C * 25);
+                                                                        ed.op_type == SENAS_OP_DOWN ? p->out_w : bw, true,
+                                                                        ed.op_type == SENAS_OP_NORM && dw_lane_ok(C, bw, DWL_WGRAD)) * kDwMaxItems * C * 25);
           break;
         }
         default:
@@ -828,7 +845,8 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
   }
   if (a.n == 0) return 0;
   const bool col1 = up || down;  // one column per thread, tiles on the low-resolution grid
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1), a.tile_rows = dw_rows(C, c.B, h, w, col1);
+  const bool lane = !up && !down && dw_lane_ok(C, w, DWL_FWD);
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1, lane), a.tile_rows = dw_rows(C, c.B, h, w, col1, lane);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
   void *st = c.S.stream(c.S.pick());
@@ -840,6 +858,12 @@ static int forward_dw_group(Call &c, int src, int only_edge) {
     SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
   } else if (down) {  // z[o] = sum x[2o + k - P] w[k]: the stride-2 gather, with statistics
     auto kern = dw_up_multi_kernel<32, false, true>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  } else if (lane && C == 32) {
+    auto kern = dwl_multi_kernel<32, true>;
+    SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
+  } else if (lane) {
+    auto kern = dwl_multi_kernel<8, true>;
     SENAS_LAUNCH(kern, grid, dim3(128), 0, st, a);
   } else if (C == 32) {
     auto kern = dw_multi_kernel<32, true>;
@@ -1583,10 +1607,12 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   }
   if (a.n == 0) return 0;
   const bool col1 = up || down;  // tiles on the low-resolution grid, one column per thread
-  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1), a.tile_rows = dw_rows(C, c.B, h, w, col1);
+  bool lane = !up && !down && dw_lane_ok(C, w, DWL_DX), lane_w = !up && !down && dw_lane_ok(C, w, DWL_WGRAD);
+  for (int m = 0; m < a.n; ++m) lane = lane && !a.it[m].in_bf, lane_w = lane_w && !a.it[m].in_bf;  // (fp32 dz only)
+  a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1, lane), a.tile_rows = dw_rows(C, c.B, h, w, col1, lane);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
-  nblk = dw_nblk(C, c.B, h, w, col1);  // (t.nblk1 is the statistics grid: the fused dep-sep kernels tile differently)
+  nblk = dw_nblk(C, c.B, h, w, col1, lane);  // (t.nblk1 is the statistics grid: the fused dep-sep kernels tile differently)
   dim3 grid(nblk, c.B);
   if (up && C != 32) SENAS_FAIL("UP depthwise: c_in %d unsupported", C);
   float *dx = c.dstate[src];
@@ -1604,6 +1630,12 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     } else if (down) {  // dx[2i + p] += sum dz[i + d] w: the scatter onto the high-resolution grid
       auto kern = dw_up_multi_kernel<32, true, false>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    } else if (lane && C == 32) {
+      auto kern = dwl_multi_kernel<32, false>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
+    } else if (lane) {
+      auto kern = dwl_multi_kernel<8, false>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
     } else if (C == 32) {
       auto kern = dw_multi_kernel<32, false>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, c.S.stream(dxl), g);
@@ -1617,8 +1649,8 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     DwMultiArgs g = a;
     float *tmp = c.tmp(ln);
     void *st = c.S.stream(ln);
-    g.tiles_x = dw_tiles_x(C, w, true), g.tile_rows = dw_rows(C, c.B, h, w, true);
-    nblk = dw_nblk(C, c.B, h, w, true);
+    g.tiles_x = dw_tiles_x(C, w, true, lane_w), g.tile_rows = dw_rows(C, c.B, h, w, true, lane_w);
+    nblk = dw_nblk(C, c.B, h, w, true, lane_w);
     grid = dim3(nblk, c.B);
     const int64_t per = (int64_t)c.B * nblk * C * 25;
     for (int m = 0; m < g.n; ++m) {
@@ -1631,6 +1663,12 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     SENAS_TAG("dw_wgrad", 2.0 * c.B * h * w * taps * C, 4.0 * c.B * h * w * C * (1 + g.n * (up ? 4 : 1)));
     if (up || down) {
       auto kern = dw_up_wgrad_multi_kernel<32>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
+    } else if (lane_w && C == 32) {
+      auto kern = dwl_wgrad_multi_kernel<32>;
+      SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
+    } else if (lane_w) {
+      auto kern = dwl_wgrad_multi_kernel<8>;
       SENAS_LAUNCH(kern, grid, dim3(128), 0, st, g);
     } else if (C == 32) {
       auto kern = dw_wgrad_multi_kernel<32>;
@@ -1852,6 +1890,65 @@ extern "C" int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int
   SENAS_LAUNCH(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, gy, gx, B, H, W, C);
   return check_cuda("avgpool backward");
 }
+// ------------------------------------------------------------------------------------------------
+// C ABI: gradient exchange (NCCL over NVLink / NVSwitch), one process per GPU
+// ------------------------------------------------------------------------------------------------
+extern "C" int senas_comm_unique_id(void *id128) {
+#ifdef SENAS_EMU
+  (void)id128;
+  SENAS_FAIL("no NCCL in the emulator build");
+#else
+  auto &a = senas_comm::api();
+  if (!a.ok) SENAS_FAIL("comm: %s", a.why.c_str());
+  if (!id128) SENAS_FAIL("comm: null id buffer");
+  const int rc = a.GetUniqueId(reinterpret_cast<senas_comm::UniqueId *>(id128));
+  if (rc) SENAS_FAIL("ncclGetUniqueId: %s", a.GetErrorString ? a.GetErrorString(rc) : "error");
+  return 0;
+#endif
+}
+extern "C" int senas_comm_init(const void *id128, int rank, int world, void **comm) {
+#ifdef SENAS_EMU
+  (void)id128, (void)rank, (void)world, (void)comm;
+  SENAS_FAIL("no NCCL in the emulator build");
+#else
+  auto &a = senas_comm::api();
+  if (!a.ok) SENAS_FAIL("comm: %s", a.why.c_str());
+  if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) SENAS_FAIL("comm_init: bad arguments");
+  senas_comm::UniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  senas_comm::Comm c = nullptr;
+  const int rc = a.CommInitRank(&c, world, id, rank);  // binds to the CURRENT device of the calling thread
+  if (rc) SENAS_FAIL("ncclCommInitRank: %s", a.GetErrorString ? a.GetErrorString(rc) : "error");
+  *comm = c;
+  return 0;
+#endif
+}
+// in-place fp32 sum over all ranks, enqueued on `stream` (capturable into a CUDA graph)
+extern "C" int senas_comm_allreduce(void *comm, float *buf, int64_t count, void *stream) {
+#ifdef SENAS_EMU
+  (void)comm, (void)buf, (void)count, (void)stream;
+  SENAS_FAIL("no NCCL in the emulator build");
+#else
+  auto &a = senas_comm::api();
+  if (!a.ok) SENAS_FAIL("comm: %s", a.why.c_str());
+  if (!comm || !buf || count < 0) SENAS_FAIL("comm_allreduce: bad arguments");
+  const int rc = a.AllReduce(buf, buf, (size_t)count, senas_comm::kFloat32, senas_comm::kSum, (senas_comm::Comm)comm,
+                             (cudaStream_t)stream);
+  if (rc) SENAS_FAIL("ncclAllReduce: %s", a.GetErrorString ? a.GetErrorString(rc) : "error");
+  return 0;
+#endif
+}
+extern "C" int senas_comm_destroy(void *comm) {
+#ifdef SENAS_EMU
+  (void)comm;
+  return 0;
+#else
+  auto &a = senas_comm::api();
+  if (comm && a.ok) a.CommDestroy((senas_comm::Comm)comm);
+  return 0;
+#endif
+}
+
 extern "C" int senas_set_gather_mma(int on) {  // bf16 mode: mma.sync (1, default) or CUDA-core FMA (0) for the non-tcgen05 convs
   g_gather_mma = on != 0;
   return 0;

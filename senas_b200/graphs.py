@@ -6,15 +6,20 @@ step time).  Capturing forward, loss, backward, gradient clipping and both optim
 kernels cost.  libsenas_b200 is capture-safe: it allocates nothing, never synchronises, and all its plans / scratch
 buffers are created during the warm-up iterations that precede the capture.
 
-Data parallel (one process per GPU): NCCL collectives are kept OUT of the graphs (capturing them deadlocked on this
-stack); the step is captured as three graphs and the two gradient exchanges run eagerly between them, each as ONE
-all-reduce of a flat bucket that the graphs pack / unpack themselves:
+Data parallel (one process per GPU).  The step consists of three segments that exchange gradients only through two
+flat buckets they pack / unpack themselves:
 
-    graph 1: arch pass (fwd, loss, bwd)            -> pack arch grads (174 floats, pre-scaled 1/world)
+    segment 1: arch pass (fwd, loss, bwd)            -> pack arch grads (174 floats, pre-scaled 1/world)
     all-reduce(bucket_arch)
-    graph 2: unpack, Adam on alpha/beta/gamma, weight pass (fwd, loss, bwd) -> pack all grads (1.97 M floats)
+    segment 2: unpack, Adam on alpha/beta/gamma, weight pass (fwd, loss, bwd) -> pack all grads (1.97 M floats)
     all-reduce(bucket_all)
-    graph 3: unpack, clip_grad_norm_, SGD
+    segment 3: unpack, clip_grad_norm_, SGD
+
+With ``comm`` (senas_b200.comm.Comm, the NCCL communicator owned by libsenas_b200) the two all-reduces are captured
+INTO the graph: the whole data-parallel step is ONE replayed graph, no host round trip between the segments.  Without
+it (``group`` only) the collectives of ``torch.distributed`` stay outside -- capturing those deadlocked on this stack
+(watchdog thread) -- and the step is three graphs with two eager all-reduces between them (round-1 path, kept as the
+fallback).
 
 BatchNorm statistics and the soft-dice sums stay local to each rank (replica semantics of the reference's DataParallel
 path for BN; per-shard dice is the stated choice of SURVEY.md H8 for the graphed path), gradients are averaged.
@@ -35,7 +40,7 @@ class GraphedSearchStep:
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
                  force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False,
-                 restore_state=True):
+                 restore_state=True, comm=None):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
         # small latency-bound cells with the large one of the level (senas_b200/supernet.py).  Only while warming up
@@ -44,8 +49,8 @@ class GraphedSearchStep:
         self._net = getattr(model, 'net', None)
         self._concurrent = bool(concurrent_cells) and self._net is not None and hasattr(self._net, 'concurrent_cells')
         self.model, self.criterion, self.w_opt, self.a_opt = model, criterion, w_opt, a_opt
-        self.grad_clip, self.group = grad_clip, group
-        self.world = dist.get_world_size(group) if group is not None else 1
+        self.grad_clip, self.group, self.comm = grad_clip, group, comm
+        self.world = comm.world if comm is not None else (dist.get_world_size(group) if group is not None else 1)
         self.segmented = self.world > 1 or force_segments
         self.capture_error_mode = capture_error_mode
         for g in a_opt.param_groups:  # Adam keeps `step` on the device when capturable
@@ -86,6 +91,12 @@ class GraphedSearchStep:
             self._set_concurrent(False)
         if snap is not None:
             self._restore(snap)
+
+    def release(self):
+        """Destroy the captured graphs (required before the NCCL communicator they captured is destroyed)."""
+        self._variants = {}
+        self.graphs = []
+        torch.cuda.synchronize()
 
     # -- state ------------------------------------------------------------------------------------------------
     def _set_concurrent(self, on):
@@ -202,6 +213,22 @@ class GraphedSearchStep:
     def _run(self, capture, arch=True):
         self._arch = bool(arch)
         segs = (self._seg1, self._seg2, self._seg3)
+        if self.segmented and self.comm is not None and self.world > 1:  # one graph with the NCCL all-reduces inside
+            def whole():
+                self._seg1()
+                if self._arch:
+                    self.comm.all_reduce_(self.bucket_arch)
+                self._seg2()
+                self.comm.all_reduce_(self.bucket_all)
+                self._seg3()
+            if capture:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode=self.capture_error_mode):
+                    whole()
+                self.graphs = [g]
+            else:
+                whole()
+            return
         if not self.segmented:  # nothing to exchange: one graph
             if capture:
                 g = torch.cuda.CUDAGraph()
@@ -242,7 +269,7 @@ class GraphedSearchStep:
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
         self.loss = var[2]
-        if not self.segmented:
+        if len(graphs) == 1:  # single GPU, or data parallel with the all-reduces captured (comm)
             graphs[0].replay()
         else:
             graphs[0].replay()

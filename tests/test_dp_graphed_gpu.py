@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, result):
+def _worker(rank, world, port, result, use_comm):
     import torch.distributed as dist
     import senas_b200
     from senas_b200.dp import broadcast_parameters
@@ -69,8 +69,13 @@ def _worker(rank, world, port, result):
     want_loss = loss.item()
     # --- the graphed DP step -----------------------------------------------------------------------------------
     m2, w2, a2 = new_model()
+    comm = None
+    if use_comm:  # NCCL communicator of libsenas_b200: both all-reduces captured inside ONE graph
+        from senas_b200.comm import Comm
+        comm = Comm(group=dist.group.WORLD, device=dev)
     step = senas_b200.GraphedSearchStep(m2, crit, w2, a2, (xt, yt, xv, yv), grad_clip=5.0, warmup=2,
-                                        group=dist.group.WORLD, capture_error_mode='thread_local')
+                                        group=dist.group.WORLD, comm=comm, capture_error_mode='thread_local')
+    assert len(step.graphs) == (1 if use_comm else 3), len(step.graphs)
     for k, v in m2.state_dict().items():
         assert torch.equal(v, init[k]), f'warm-up left a trace in {k}'
     got_loss = step(xt, yt, xv, yv).item()
@@ -98,16 +103,21 @@ def _worker(rank, world, port, result):
     dist.broadcast(ref, 0)
     errs['rank_divergence'] = (flat - ref).abs().max().item()
     result[rank] = errs
+    step.release()  # graphs before the communicator they captured
+    if comm is not None:
+        comm.destroy()
+    dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
-def test_graphed_dp_step_equals_mean_of_local_gradients():
+@pytest.mark.parametrize('use_comm', [True, False])
+def test_graphed_dp_step_equals_mean_of_local_gradients(use_comm):
     import torch.multiprocessing as mp
     world = 2
     mgr = mp.Manager()
     result = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), result), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), result, use_comm), nprocs=world, join=True)
     assert len(result) == world
     for rank, e in result.items():
         assert e['loss'] <= 2e-5, (rank, e)
