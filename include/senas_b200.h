@@ -35,7 +35,7 @@ extern "C" {
 #define SENAS_MAX_CAND 6   /* candidates per MixedOp = alpha columns (utils/operations.py:23-48) */
 #define SENAS_SLOTS 12     /* parameter/buffer slots per candidate, see table below */
 #define SENAS_MAX_EDGES 16
-#define SENAS_MAX_NODES 4
+#define SENAS_MAX_NODES 3 /* (a 4th node would have 5 incoming edges = 30 candidate terms; the search configs use 3) */
 #define SENAS_FLAG_TC_BF16 1
 
 /* OpType ids: the reference's OpType.value['id'] (utils/operations.py:51-54) */

@@ -7,7 +7,7 @@ is not sm_100, importing the hot path raises.
 import ctypes as C
 import os
 
-MAX_CAND, SLOTS, MAX_EDGES, MAX_NODES = 6, 12, 16, 4
+MAX_CAND, SLOTS, MAX_EDGES, MAX_NODES = 6, 12, 16, 3
 OP_UP, OP_DOWN, OP_NORM = 1, 2, 3
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')

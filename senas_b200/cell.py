@@ -57,6 +57,15 @@ class Cell(nn.Module):
     def __init__(self, meta_node_num, double_down, c_in0, c_in1, c_out, cell_type):
         super().__init__()
         self.k = 4  # "shrink": every MixedOp works on c_out / 4 channels (cell.py:53)
+        # what libsenas_b200 has kernels for (every senas config: init_channels 32, meta_node_num 3, no channel doubling);
+        # say so here instead of failing at the first forward
+        if meta_node_num < 1 or meta_node_num > 3:
+            raise NotImplementedError(f'senas_b200.Cell: meta_node_num = {meta_node_num} is not supported (1..3; the '
+                                      'reference configs use 3): a node with 5 incoming MixedOps has 30 candidate terms')
+        cp = int((c_out // double_down) // self.k) if cell_type == 'down' else int(c_out // self.k)
+        if cp != 8 or c_in1 != 32:
+            raise NotImplementedError(f'senas_b200.Cell: c_in1 = {c_in1}, c_out / 4 = {cp}: the kernels cover the 32-channel '
+                                      'search supernet (MixedOps 32 -> 8 and 8 -> 8; double_down_channel=False)')
         self._meta_node_num = meta_node_num
         self._input_num = 2
         if cell_type == 'down':

@@ -140,8 +140,17 @@ def build_ops(op_name, op_type, c_in=None, c_ot=None, dp=0):
     raise NotImplementedError()
 
 
+def _not_on_search_path(name):
+    def make(c_in, c_ot, op_type, dp):
+        raise NotImplementedError(f"'{name}' is registered by the reference (utils/operations.py:12,15) but is in none of its "
+                                  'candidate lists (DownOps / UpOps / NormOps, :23-48); senas_b200 has no kernel for it')
+    return make
+
+
 OPS = {
     'none': lambda c_in, c_ot, op_type, dp: AdapterBlock(c_in, c_ot, ZeroOp(stride=1), KIND_NONE),
+    'max_pool': _not_on_search_path('max_pool'),
+    'conv_3': _not_on_search_path('conv_3'),
     'identity': lambda c_in, c_ot, op_type, dp: AdapterBlock(c_in, c_ot, nn.Identity(), KIND_IDENTITY),
     'avg_pool': lambda c_in, c_ot, op_type, dp: build_ops('avg_pool', op_type, c_in, c_ot),
     'up_sample': lambda c_in, c_ot, op_type, dp: AdapterBlock(

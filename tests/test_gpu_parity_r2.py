@@ -521,3 +521,22 @@ def test_search_arc_untouched_same_genotype():
         d = (getattr(gpu.model, n).detach().cpu() - arch_cpu[n]).abs().max().item()
         assert d < 4.5e-4, (n, d)
     assert repr(gpu.model.genotype()) == geno_cpu
+
+
+@pytest.mark.parametrize('op_id,c_in', [(3, 32), (3, 8), (2, 32), (1, 32)])
+def test_nan_input_poisons_the_mixed_op_like_the_reference(op_id, c_in):
+    """the reference's 'none' candidate is ``x.mul(0.)`` -> BatchNorm, so a NaN / Inf anywhere in x
+    turns its batch statistics and hence its whole output into NaN; here 'none' is folded analytically (BN(0) = beta, no
+    kernel).  The observable behaviour is the same because every other candidate of the MixedOp carries the NaN into
+    its own batch statistics: the MixedOp output is NaN everywhere in the reference (oracle) and here."""
+    m = _randomised_mixed(c_in, op_id, 900 + op_id + c_in)
+    store = oracle.clone_store(m.state_dict(), requires_grad=False)
+    torch.manual_seed(5)
+    x = torch.randn(2, c_in, 16, 16)
+    x[1, 3, 5, 7] = float('nan')
+    alpha = torch.softmax(torch.randn(6), -1)
+    with torch.no_grad():
+        ref = oracle.mixed_op(oracle.Params(store), OP_NAME[op_id], x, alpha, True)
+        out = m.to(DEV)(x.to(DEV), alpha.to(DEV), alpha.to(DEV))
+    assert torch.isnan(ref).all()
+    assert torch.isnan(out).all()

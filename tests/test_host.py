@@ -120,3 +120,22 @@ def test_graph_descriptor_validation():
     d.c_out, d.edge[0].c_in, d.edge[0].op_type = 8, 24, 3
     assert lib.senas_graph_create(ctypes.byref(d), ctypes.byref(h)) != 0
     assert b'c_in' in lib.senas_last_error()
+
+
+def test_unsupported_configurations_fail_at_construction():
+    """the reference's NAS defaults (meta_node_num=4, double_down_channel=True) are outside what the kernels
+    cover; say so in the constructor, not at the first forward.  'max_pool' / 'conv_3' are registry keys of the reference
+    that no candidate list uses."""
+    import pytest
+    import senas_b200
+    from senas_b200.ops import OPS, OpType
+    with pytest.raises(NotImplementedError, match='meta_node_num'):
+        senas_b200.Cell(4, 1, 32, 32, 32, 'up')
+    with pytest.raises(NotImplementedError, match='32-channel'):
+        senas_b200.Cell(3, 2, 32, 32, 64, 'up')
+    with pytest.raises(NotImplementedError):
+        senas_b200.NAS(1, 32, 2, depth=5)  # the reference's defaults: 4 nodes, doubled channels
+    for name in ('max_pool', 'conv_3'):
+        with pytest.raises(NotImplementedError, match='candidate lists'):
+            OPS[name](32, 8, OpType.NORM, 0)
+    senas_b200.NAS(1, 32, 2, depth=3, meta_node_num=3, use_sharing=False, double_down_channel=False)  # supported
