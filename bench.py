@@ -384,12 +384,14 @@ def run_ours(args, rank, world, local_rank):
             graphed = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*devb[0], *devb[1]), grad_clip=5.0,
                                                    warmup=3, group=group, comm=comm,
                                                    capture_error_mode='thread_local' if world > 1 else 'global',
-                                                   concurrent_cells=not args.serial_cells, defer_wgrad=args.defer_wgrad)
+                                                   concurrent_cells=not args.serial_cells, defer_wgrad=args.defer_wgrad,
+                                                   overlap=not args.no_overlap, fused_optim=not args.no_fused_optim)
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
             if world > 1:
-                graph_note = ('cuda-graph (one graph per step with both NCCL gradient all-reduces captured inside, '
-                              'libsenas_b200 communicator)' if comm is not None else
+                graph_note = ('cuda-graph (one graph per step; NCCL all-reduces of the libsenas_b200 communicator captured '
+                              'inside: per-cell weight-gradient buckets on a side stream overlapped with backward, one '
+                              'bucket for the rest, one for the arch gradients)' if comm is not None else
                               'cuda-graph (three graphs per step, two torch.distributed all-reduces between them)')
             search_step = lambda xt, yt, xv, yv: graphed(xt, yt, xv, yv)  # noqa: E731
         except Exception as e:  # keep measuring, but say so
@@ -462,7 +464,8 @@ def run_ours(args, rank, world, local_rank):
             dev3 = [(x.to(dev), y.to(dev)) for x, y in host3]
             step3 = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*dev3[0], *dev3[1]), grad_clip=5.0, warmup=2,
                                                  group=group, comm=comm, capture_error_mode='thread_local',
-                                                 concurrent_cells=not args.serial_cells)
+                                                 concurrent_cells=not args.serial_cells, overlap=not args.no_overlap,
+                                                 fused_optim=not args.no_fused_optim)
             for _ in range(2):
                 step3(*dev3[0], *dev3[1])
             n3 = min(args.steps, 10)
@@ -589,6 +592,8 @@ def main():
     ap.add_argument('--no-fp32-line', action='store_true', help='skip the fp32-mode measurement beside the bf16 one')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-comm', action='store_true', help='data parallel: keep the all-reduces outside the graphs (torch.distributed)')
+    ap.add_argument('--no-overlap', action='store_true', help='data parallel: one post-backward weight-gradient bucket instead of per-cell buckets overlapped with backward')
+    ap.add_argument('--no-fused-optim', action='store_true', help='clip_grad_norm_ / SGD / Adam of PyTorch inside the graph instead of the flat-buffer kernels of libsenas_b200 (row f4)')
     ap.add_argument('--no-config3', action='store_true', help='N = 2, 4: skip the BASELINE config-3 leg (global batch 128)')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
     ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')

@@ -169,12 +169,63 @@ int senas_flush(void *stream);
  * recomputed from the input in every sweep and never stored).  Off by default (measured slower than the spill path on
  * B200); applies to graphs planned after the call.  Environment variable SENAS_DS_FUSED sets the default. */
 int senas_set_ds_fused(int on);
+/* bf16 mode: store the depthwise output z of the dep-sep chains (and the gradient dz written over it) as bf16: half the
+ * traffic of the chain's six sweeps; statistics, ReLU mask and all consumers read the same rounded values.  Affects
+ * graphs planned afterwards. */
+int senas_set_z_bfloat(int on);
 
 /* Data-parallel gradient exchange, one process per GPU (replaces the reference's in-process replica path,
  * search/senas_search.py:262-279 and utils/utils.py:233-237, broken as shipped).  NCCL over NVLink 5 / NVSwitch, bound
  * with dlopen at the first call (no link-time dependency).  senas_comm_unique_id fills 128 bytes on one rank; the host
  * distributes them (any channel) and every rank calls senas_comm_init with its CUDA device current.  The all-reduce is an
  * in-place fp32 SUM enqueued on `stream`; it may be captured into a CUDA graph together with the kernels around it. */
+/* SURVEY 8f rows f4 / f3 (the blocks between the cells), flat fp32 device buffers, 16-byte aligned.
+ * senas_sgd_clip_step: torch.nn.utils.clip_grad_norm_(max_norm, 2) + torch.optim.SGD(momentum, weight_decay).step() of
+ *   experiments/search_arc.py:282-293 as two launches: grad is scaled in place by min(1, max_norm / (||grad|| + 1e-6)),
+ *   momentum = mom * momentum + (grad + wd * param), param -= lr * momentum.  lr_dev points to ONE device float (a
+ *   scheduler rewrites it; nothing is baked into a captured graph).  scratch: >= 296 floats (norm partials, fixed
+ *   summation order); max_norm <= 0 disables clipping; norm_out (optional) receives the unclipped norm.
+ * senas_adam_step: torch.optim.Adam(betas, eps, weight_decay).step() on the architecture parameters; `step` is a device
+ *   float that the call increments (Adam's bias-correction counter).
+ * senas_mix_forward / backward: out[:, c0:c0+C] = w[0] * a + w[1] * b over npix NHWC pixels (b may be NULL: w[0] * a; then w may be NULL too: a plain copy) --
+ *   the gamma-weighted skip mix of search/senas_search.py:96-107 written straight into the concat buffer that feeds the
+ *   cell's ShrinkBlock; backward returns da = w[0] * g, db = w[1] * g (dense [npix][C], either may be NULL) and
+ *   dw[0..1] = <g, a>, <g, b>; scratch: >= 1184 floats. */
+int senas_sgd_clip_step(float *param, float *grad, float *momentum, int64_t n, const float *lr_dev, float mom, float wd,
+                        float max_norm, float *scratch, float *norm_out, void *stream);
+int senas_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n,
+                    const float *lr_dev, float beta1, float beta2, float eps, float wd, void *stream);
+int senas_mix_forward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, float *out, int64_t out_ld,
+                      int32_t c0, int32_t C, int64_t npix, void *stream);
+int senas_mix_backward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, const float *g, int64_t g_ld,
+                       int32_t c0, int32_t C, int64_t npix, float *da, float *db, float *dw, float *scratch, void *stream);
+/* the Cell's pre / post blocks -- ShrinkBlock (utils/operations.py:206-218: ReLU -> Conv2d 3x3 c_in ->
+ * 32, padding 1, no bias -> BatchNorm2d) and RectifyBlock (:221-232: the same without the ReLU, c_in = 24) as one op on the
+ * tcgen05 kernels (bf16 operands, fp32 accumulation; the 2e-2 mode).  All tensors NHWC fp32; x may be a strided view
+ * (x_ld = its pixel stride, e.g. a slice of / the whole concat buffer).  weight: PyTorch Conv2d layout [32][c_in][3][3].
+ * w must be a multiple of 64; c_in in {24, 32, 64, 96, 128}.  saved / scratch: senas_convbn_workspace bytes; `saved` lives
+ * from forward to backward (pre-BN output y, batch statistics, the bf16 copy of x), scratch is free after each call.
+ * Training mode updates running_mean / running_var / num_batches_tracked in place like nn.BatchNorm2d. */
+typedef struct {
+  int32_t batch, h, w, c_in, relu_in, training;
+  const float *x; int64_t x_ld;
+  const float *weight, *gamma, *beta;
+  float *running_mean, *running_var; int64_t *num_batches_tracked;
+  float momentum, eps;
+  float *out;                                   /* forward: [batch][h][w][32] */
+  void *saved, *scratch;
+  const float *grad_out; int64_t grad_out_ld;   /* backward inputs */
+  float *grad_x;                                /* backward: [batch][h][w][c_in] dense, or NULL */
+  float *grad_weight, *grad_gamma, *grad_beta;  /* backward: [32][c_in][3][3], [32], [32] */
+  void *stream;
+} senas_convbn_args_t;
+int senas_convbn_workspace(int32_t batch, int32_t h, int32_t w, int32_t c_in, int64_t *saved_bytes, int64_t *scratch_bytes);
+int senas_convbn_forward(const senas_convbn_args_t *a);
+int senas_convbn_backward(const senas_convbn_args_t *a);
+/* gradient of one skip tensor: out[pix][c] = sum_j coef_j * g[pix][off_j + c] over the (up to 3) channel slices of the
+ * concat gradient it reached; off_j < 0: term absent; w_j == NULL: coefficient 1, else *w_j (device float). */
+int senas_mix_dx(const float *g, int64_t g_ld, const float *w0, int32_t off0, const float *w1, int32_t off1, const float *w2,
+                 int32_t off2, float *out, int32_t C, int64_t npix, void *stream);
 int senas_comm_unique_id(void *id128);
 int senas_comm_init(const void *id128, int rank, int world, void **comm);
 int senas_comm_allreduce(void *comm, float *buf, int64_t count, void *stream);

@@ -13,6 +13,7 @@ from .build import build  # noqa: F401
 from .patch import patch_reference  # noqa: F401
 from .fused import set_conv_mode, get_conv_mode  # noqa: F401
 from .graphs import GraphedSearchStep  # noqa: F401
+from .optim import FusedSearchOptim  # noqa: F401
 
 __version__ = '0.1.0'
 

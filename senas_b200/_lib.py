@@ -46,10 +46,22 @@ class BwdArgs(C.Structure):
                 ('grad_params', C.c_void_p), ('stream', C.c_void_p)]
 
 
+class ConvBnArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('c_in', C.c_int32), ('relu_in', C.c_int32),
+                ('training', C.c_int32), ('x', C.c_void_p), ('x_ld', C.c_int64), ('weight', C.c_void_p), ('gamma', C.c_void_p),
+                ('beta', C.c_void_p), ('running_mean', C.c_void_p), ('running_var', C.c_void_p),
+                ('num_batches_tracked', C.c_void_p), ('momentum', C.c_float), ('eps', C.c_float), ('out', C.c_void_p),
+                ('saved', C.c_void_p), ('scratch', C.c_void_p), ('grad_out', C.c_void_p), ('grad_out_ld', C.c_int64),
+                ('grad_x', C.c_void_p), ('grad_weight', C.c_void_p), ('grad_gamma', C.c_void_p), ('grad_beta', C.c_void_p),
+                ('stream', C.c_void_p)]
+
+
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
            'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_avgpool_forward',
-           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_gather_mma', 'senas_comm_unique_id', 'senas_comm_init',
-           'senas_comm_allreduce', 'senas_comm_destroy', 'senas_profile',
+           'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_z_bfloat', 'senas_set_gather_mma', 'senas_comm_unique_id', 'senas_comm_init',
+           'senas_comm_allreduce', 'senas_comm_destroy', 'senas_sgd_clip_step', 'senas_adam_step', 'senas_mix_forward',
+           'senas_mix_backward', 'senas_mix_dx', 'senas_convbn_workspace', 'senas_convbn_forward', 'senas_convbn_backward',
+           'senas_profile',
            'senas_profile_dump']
 
 
@@ -74,12 +86,27 @@ def bind(path):
     lib.senas_set_slot.argtypes = [C.c_int]
     lib.senas_set_defer.argtypes = [C.c_int]
     lib.senas_set_ds_fused.argtypes = [C.c_int]
+    lib.senas_set_z_bfloat.argtypes = [C.c_int]
     lib.senas_set_gather_mma.argtypes = [C.c_int]
     lib.senas_comm_unique_id.argtypes = [C.c_void_p]
     lib.senas_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.senas_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.senas_comm_destroy.argtypes = [C.c_void_p]
     lib.senas_flush.argtypes = [C.c_void_p]
+    lib.senas_convbn_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.senas_convbn_forward.argtypes = [C.POINTER(ConvBnArgs)]
+    lib.senas_convbn_backward.argtypes = [C.POINTER(ConvBnArgs)]
+    lib.senas_mix_dx.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                 C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+    lib.senas_sgd_clip_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.senas_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.senas_mix_forward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
+    lib.senas_mix_backward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     lib.senas_profile.argtypes = [C.c_int]
     lib.senas_profile_dump.argtypes = [C.c_char_p, C.c_int64]
     lib.senas_profile_dump.restype = C.c_int64

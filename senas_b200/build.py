@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'graph.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'kernels.cuh'), os.path.join(HERE, 'csrc', 'platform.h'), os.path.join(HERE, 'csrc', 'conv_tc.cuh'),
+DEPS = [SRC, os.path.join(HERE, 'csrc', 'kernels.cuh'), os.path.join(HERE, 'csrc', 'platform.h'), os.path.join(HERE, 'csrc', 'conv_tc.cuh'), os.path.join(HERE, 'csrc', 'comm.cuh'), os.path.join(HERE, 'csrc', 'optim.cuh'), os.path.join(HERE, 'csrc', 'convbn.cuh'),
         os.path.join(os.path.dirname(HERE), 'include', 'senas_b200.h')]
 OUT = os.path.join(HERE, 'lib', 'libsenas_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared',

@@ -41,10 +41,14 @@ class MixedOp(nn.Module):
     def _edge(self, src, dst):
         return (list(self._ops), src, dst, self._op_type.value['id'], self._c_in)
 
-    def forward(self, x, alpha_normal, alpha_up_dn):
-        _require_cuda(x, 'MixedOp')
+    def _ensure_runner(self):
         if self._runner is None:
             self._runner = GraphRunner([self._edge(0, 0)], n_inputs=1, n_nodes=1, node_relu=False)
+        return self._runner
+
+    def forward(self, x, alpha_normal, alpha_up_dn):
+        _require_cuda(x, 'MixedOp')
+        self._ensure_runner()
         w = alpha_normal if self._op_type == OpType.NORM else alpha_up_dn
         return self._runner.apply([x], w.reshape(1, -1), None, self.training)
 
@@ -102,12 +106,16 @@ class Cell(nn.Module):
         self._runner = None
         return super()._apply(fn, *a, **k)
 
-    def nodes(self, in0, in1, weights_norm, weights_chg, betas):
-        """Node loop + concat (cell.py:95-110) on pre-processed inputs -> [B, 8*nodes, H, W]."""
-        _require_cuda(in1, 'Cell')
+    def _ensure_runner(self):
         if self._runner is None:
             edges = [op._edge(s, d) for op, s, d in zip(self._ops, self._srcs, self._dsts)]
             self._runner = GraphRunner(edges, n_inputs=2, n_nodes=self._meta_node_num, node_relu=True)
+        return self._runner
+
+    def nodes(self, in0, in1, weights_norm, weights_chg, betas):
+        """Node loop + concat (cell.py:95-110) on pre-processed inputs -> [B, 8*nodes, H, W]."""
+        _require_cuda(in1, 'Cell')
+        self._ensure_runner()
         if self._norm_rows.device != weights_norm.device:
             self._norm_rows = self._norm_rows.to(weights_norm.device)
         alpha = torch.where(self._norm_rows, weights_norm, weights_chg)  # row used by each edge (cell.py:33-36)

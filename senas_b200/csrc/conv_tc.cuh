@@ -45,6 +45,11 @@ struct TcConvArgs {
   int32_t img_mul, img_add;      // image index of the TMA source = n * img_mul + img_add (phase-major packed dy of UP)
   int32_t M;                     // pixels per MMA = strip width: 128, or 64 for maps that are a multiple of 64 wide only
   int32_t acc_y, no_stats;       // mode 0 in several launches (DOWN: one per input phase): y += , statistics on the last
+  // ConvBn blocks (convbn.cuh, SURVEY row f1: ShrinkBlock / RectifyBlock 3x3 convs, 32 output channels = 4 terms):
+  int32_t y_ld;                  // mode 0: pixel stride of y (0 = 8: one dense tensor per term; 32: one NHWC tensor)
+  int32_t cin_valid;             // input channels that exist in this 32-channel slice (0 = 32; RectifyBlock: 24): weights of
+                                 // the others are staged as 0 and mode 1 does not store them
+  const float *mask;             // mode 1: dx = mask > 0 ? dx : 0 (ReLU in front of the conv), same geometry as out32
   TapTable taps;
 };
 
@@ -152,7 +157,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float f = 0.f;
-      if (g < a.nterms) {
+      const int cin = a.mode == 0 ? kc * 8 + j : nn;  // input channel of this element
+      if (g < a.nterms && (a.cin_valid == 0 || cin < a.cin_valid)) {
         const int kk = a.mode == 0 ? kc * 8 + j : j, cn = a.mode == 0 ? (nn & 7) : nn;
         f = __ldg(a.w[g] + (int64_t)a.taps.widx[t] * a.ws_t + (int64_t)kk * a.ws_k + (int64_t)cn * a.ws_n);
       }
@@ -262,12 +268,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
         if (a.mode == 1) {
           if (!lane_ok) continue;
           float *o = a.out32 + (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.out_ld;
+          const int nvalid = a.cin_valid ? a.cin_valid : kTcN;
 #pragma unroll
           for (int j = 0; j < kTcN; j += 4) {
+            if (j >= nvalid) continue;
             float4 u = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (a.accumulate) {
               const float4 w4 = ld4(o + j);
               u.x += w4.x, u.y += w4.y, u.z += w4.z, u.w += w4.w;
+            }
+            if (a.mask) {
+              const float4 m4 = ld4(a.mask + (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.out_ld + j);
+              u.x = m4.x > 0.f ? u.x : 0.f, u.y = m4.y > 0.f ? u.y : 0.f, u.z = m4.z > 0.f ? u.z : 0.f, u.w = m4.w > 0.f ? u.w : 0.f;
             }
             st4(o + j, u);
           }
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(const __grid
 #pragma unroll
           for (int g = 0; g < kTcMaxTerms; ++g) {
             if (g < a.nterms) {
-              float *o = a.y[g] + pix * 8;
+              float *o = a.y[g] + pix * (a.y_ld ? a.y_ld : 8);
               if (a.acc_y) {
                 const float4 lo = ld4(o), hi = ld4(o + 4);
                 v[g * 8] += lo.x, v[g * 8 + 1] += lo.y, v[g * 8 + 2] += lo.z, v[g * 8 + 3] += lo.w;
@@ -513,6 +525,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_wgrad_kernel(const __gr
 struct TcWgradReduceArgs {
   const float *partials;
   int32_t nrows, t_begin, t_count, nterms, ws_t, ws_ci, ws_co;
+  int32_t cin_valid;  // input channels that exist (0 = 32)
   float *dst[kTcMaxTerms];
   TapTable taps;
 };
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(TcWgradReduceArgs 
   const float s = block_rows_sum(a.partials, a.nrows, V, col);
   if (threadIdx.x < 32 && col < V) {
     const int m = col & 31, ci = (col >> 5) & 31, t = col >> 10, g = m >> 3, co = m & 7;
-    if (g < a.nterms)
+    if (g < a.nterms && (a.cin_valid == 0 || ci < a.cin_valid))
       a.dst[g][(int64_t)a.taps.widx[a.t_begin + t] * a.ws_t + (int64_t)ci * a.ws_ci + (int64_t)co * a.ws_co] = s;
   }
 }
@@ -593,7 +606,7 @@ static int tc_encode(CUtensorMap *tmap, const __nv_bfloat16 *p, int B, int H, in
 // floats.  dy rows come from image n * dy_mul + dy_add of dyb (NORM: 1, 0; UP: 4, phase).
 static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dyb, int B, int H, int W, const TapTable &taps,
                                 int t0, int t1, int dy_mul, int dy_add, float *partials, float *const *dst, int nterms,
-                                int ws_ci, int ws_co, void *stream, int x_mul = 1, int x_add = 0) {
+                                int ws_ci, int ws_co, void *stream, int x_mul = 1, int x_add = 0, int cin_valid = 0) {
   TcWgradArgs a;
   memset(&a, 0, sizeof(a));
   a.H = H, a.W = W, a.rows_per_cta = tc_rows(H, W, B, taps.max_dy - taps.min_dy);
@@ -618,7 +631,7 @@ static int launch_conv_tc_wgrad(const __nv_bfloat16 *xb, const __nv_bfloat16 *dy
     TcWgradReduceArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.partials = partials, ra.nrows = (int)(grid.x * B), ra.t_begin = tb, ra.t_count = a.t_count, ra.nterms = nterms;
-    ra.ws_t = 1, ra.ws_ci = ws_ci, ra.ws_co = ws_co, ra.taps = taps;
+    ra.ws_t = 1, ra.ws_ci = ws_ci, ra.ws_co = ws_co, ra.taps = taps, ra.cin_valid = cin_valid;
     for (int g = 0; g < nterms; ++g) ra.dst[g] = dst[g];
     SENAS_TAG("reduce", 0, 0);
     SENAS_LAUNCH(tc_wgrad_reduce_kernel, dim3((a.t_count * 1024 + 31) / 32), dim3(256), 0, stream, ra);

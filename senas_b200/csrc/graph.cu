@@ -33,6 +33,8 @@ static int tc_rows(int H, int W, int B, int span_y) {
 }
 #include "conv_tc.cuh"
 #include "comm.cuh"
+#include "optim.cuh"
+#include "convbn.cuh"
 
 #ifdef SENAS_EMU
 static void *dev_upload(const void *h, size_t n) {
@@ -218,6 +220,9 @@ static int dw_nblk(int C, int B, int h, int w, bool wgrad, bool lane = false) {
 // (profiles/README.md, round 2).  Kept behind the switch with its emulator tests as the starting point for a version with
 // the pointwise halves on tensor cores.
 static int g_ds_fused = env_flag("SENAS_DS_FUSED", 0);
+// bf16 mode: the depthwise output z of the grouped dep-sep chains (and the gradient dz written over it) is STORED as bf16
+// (statistics, the ReLU mask and every consumer see the same rounded values, so forward and backward stay consistent).
+static int g_z_bf16 = env_flag("SENAS_Z_BF16", 0);
 static int ds_tile_w(int C) { return C == 32 ? DsGeo<32>::TILE_W : DsGeo<8>::TILE_W; }
 static int ds_rows(int C, int B, int h, int w) {
   const int tx = cdiv(w, ds_tile_w(C));
@@ -411,6 +416,8 @@ static int build_plan(senas_graph *g, int B, const int32_t *ih, const int32_t *i
           if (t.fused) {  // only dz lives in the buffer (backward); bf16 in bf16 mode: a gradient value, no mask depends on it
             t.nblk1 = t.nblk = ds_nblk(C, B, bh, bw);
             t.zb = (d.reserved & 1) != 0;
+          } else if (g_z_bf16 && t.dwg && (d.reserved & 1) && (HW * C) % 2 == 0) {
+            t.zb = true;
           }
           t.z_off = take(sv, t.zb ? ((int64_t)B * HW * C + 1) / 2 : (int64_t)B * HW * C);
           t.mean1_off = take(sv, C), t.istd1_off = take(sv, C);
@@ -1288,7 +1295,7 @@ static int backward_edge(BwdCall &c, int e) {
           c.S.dep(dxl, ln);
           if (want_dw) {
             SENAS_TAG("reduce", 0, 0);
-            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(8 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)dwp,
+            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(8 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)dwp,
                          gp + ed.grad_off[k][0], nb * B, 8 * C);
           }
           break;
@@ -1322,7 +1329,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_AD_DW(32, AD_UP)
           const int n = 8 * C;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(grid.x * B), n);
         }
         break;
@@ -1434,7 +1441,7 @@ static int backward_edge(BwdCall &c, int e) {
             const int k2 = ks[q];
             float *base = tmp + q * per, *sums = base + (int64_t)B * nb * 10 * C;
             SENAS_TAG("reduce", 0, 0);
-            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)base, sums,
+            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)base, sums,
                          nb * B, 10 * C);
             SENAS_TAG("pw_bfin", 0, 0);
             SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums, C, (float)B * (float)HW,
@@ -1475,7 +1482,7 @@ static int backward_edge(BwdCall &c, int e) {
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
         SENAS_TAG("reduce", 0, 0);
-        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp, sums1,
+        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)tmp, sums1,
                      (int)(nblk_cc * B), 10 * C);
         SENAS_TAG("pw_bfin", 0, 0);
         SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums1, C, (float)B * (float)HW, a.g1,
@@ -1567,7 +1574,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_FAIL("dw wgrad: unsupported c_in %d k %d", C, t.k);
           const int n = C * T;
           SENAS_TAG("reduce", 0, 0);
-          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)tmp,
+          SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(n, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)tmp,
                        gp + ed.grad_off[k][0], (int)(g3.x * B), n);
         }
         break;
@@ -1608,7 +1615,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
   if (a.n == 0) return 0;
   const bool col1 = up || down;  // tiles on the low-resolution grid, one column per thread
   bool lane = !up && !down && dw_lane_ok(C, w, DWL_DX), lane_w = !up && !down && dw_lane_ok(C, w, DWL_WGRAD);
-  for (int m = 0; m < a.n; ++m) lane = lane && !a.it[m].in_bf, lane_w = lane_w && !a.it[m].in_bf;  // (fp32 dz only)
+  for (int m = 0; m < a.n; ++m) lane = lane && !a.it[m].in_bf;  // (forward / data-gradient lane kernels: fp32 dz only)
   a.H = h, a.W = w, a.tiles_x = dw_tiles_x(C, w, col1, lane), a.tile_rows = dw_rows(C, c.B, h, w, col1, lane);
   double taps = 0;
   for (int m = 0; m < a.n; ++m) taps += a.it[m].k * a.it[m].k;
@@ -1680,7 +1687,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     for (int m = 0; m < g.n; ++m) {
       const int nn = C * g.it[m].k * g.it[m].k;
       SENAS_TAG("reduce", 0, 0);
-      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(nn, kRowsReduceCols), 1), dim3(256), 0, st, (const float *)(tmp + m * per),
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(nn, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)(tmp + m * per),
                    c.a->grad_params + goff[m], (int)(nblk * c.B), nn);
     }
   }
@@ -1729,7 +1736,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
     {
       const int V = (1 + np.nterms) * 8;
       SENAS_TAG("reduce", 0, 0);
-      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(V, kRowsReduceCols), c.B), dim3(256), 0, c.stream,
+      SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(V, kRowsReduceCols), c.B), dim3(kRowsReduceThreads), 0, c.stream,
                    (const float *)(c.scratch + np.bpart_off), c.scratch + np.bsum_off, np.nblk, V);
     }
     SENAS_TAG("node_bfin", 0, 0);
@@ -1891,6 +1898,202 @@ extern "C" int senas_avgpool_backward(const float *gy, float *gx, int32_t B, int
   return check_cuda("avgpool backward");
 }
 // ------------------------------------------------------------------------------------------------
+// C ABI: SURVEY rows f4 / f3 (optim.cuh) -- fused clip + SGD, Adam over flat buffers; gamma mix into the concat buffer
+// ------------------------------------------------------------------------------------------------
+extern "C" int senas_sgd_clip_step(float *param, float *grad, float *momentum, int64_t n, const float *lr_dev,
+                                   float mom, float wd, float max_norm, float *scratch, float *norm_out, void *stream) {
+  if (!param || !grad || !momentum || !lr_dev || n < 1) SENAS_FAIL("sgd step: bad arguments");
+  if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum) & 15) SENAS_FAIL("sgd step: buffers must be 16-byte aligned");
+  if (max_norm > 0.f && !scratch) SENAS_FAIL("sgd step: clipping needs a scratch buffer of %d floats", kOptBlocks);
+  const int blocks = (int)std::min<int64_t>(kOptBlocks, ((n >> 2) + 255) / 256 + 1);
+  if (max_norm > 0.f) {
+    SENAS_TAG("opt_sqnorm", 2.0 * n, 4.0 * n);
+    SENAS_LAUNCH(opt_sqnorm_kernel, dim3(blocks), dim3(256), 0, stream, (const float *)grad, n, scratch);
+  }
+  SENAS_TAG("opt_sgd", 6.0 * n, 24.0 * n);
+  SENAS_LAUNCH(opt_sgd_kernel, dim3(blocks), dim3(256), 0, stream, param, grad, momentum, n, lr_dev, mom, wd, max_norm,
+               (const float *)scratch, blocks, norm_out);
+  return check_cuda("sgd step");
+}
+extern "C" int senas_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n,
+                               const float *lr_dev, float beta1, float beta2, float eps, float wd, void *stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || !lr_dev || n < 1) SENAS_FAIL("adam step: bad arguments");
+  SENAS_TAG("opt_adam", 12.0 * n, 28.0 * n);
+  SENAS_LAUNCH(opt_adam_kernel, dim3(1), dim3(256), 0, stream, param, grad, exp_avg, exp_avg_sq, step, n, lr_dev, beta1, beta2,
+               eps, wd);
+  return check_cuda("adam step");
+}
+extern "C" int senas_mix_forward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, float *out,
+                                 int64_t out_ld, int32_t c0, int32_t C, int64_t npix, void *stream) {
+  if (!a || !out || (b && !w) || C < 4 || (C & 3) || (c0 & 3) || (a_ld & 3) || (b_ld & 3) || (out_ld & 3) || npix < 1)
+    SENAS_FAIL("mix forward: bad arguments");
+  MixArgs q;
+  q.a = a, q.b = b, q.w = w, q.out = out, q.npix = npix, q.a_ld = a_ld, q.b_ld = b_ld, q.out_ld = out_ld, q.C = C, q.c0 = c0;
+  const int64_t total = npix * (C / 4);
+  SENAS_TAG("mix_fwd", 0, 4.0 * npix * C * (b ? 3 : 2));
+  SENAS_LAUNCH(mix_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, q);
+  return check_cuda("mix forward");
+}
+extern "C" int senas_mix_backward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, const float *g,
+                                  int64_t g_ld, int32_t c0, int32_t C, int64_t npix, float *da, float *db, float *dw,
+                                  float *scratch, void *stream) {
+  if (!a || !g || !w || !dw || !scratch || C < 4 || (C & 3) || (c0 & 3) || (a_ld & 3) || (b_ld & 3) || (g_ld & 3) || npix < 1)
+    SENAS_FAIL("mix backward: bad arguments");
+  MixBwdArgs q;
+  q.a = a, q.b = b, q.w = w, q.g = g, q.da = da, q.db = db, q.partials = scratch;
+  q.npix = npix, q.a_ld = a_ld, q.b_ld = b_ld, q.g_ld = g_ld, q.C = C, q.c0 = c0;
+  const int64_t total = npix * (C / 4);
+  const int blocks = (int)std::min<int64_t>(kOptBlocks * 2, (total + 255) / 256);
+  SENAS_TAG("mix_bwd", 0, 4.0 * npix * C * (b ? 5 : 3));
+  SENAS_LAUNCH(mix_bwd_kernel, dim3(blocks), dim3(256), 0, stream, q);
+  SENAS_TAG("reduce", 0, 0);
+  SENAS_LAUNCH(mix_bwd_final_kernel, dim3(1), dim3(32), 0, stream, (const float *)scratch, blocks, dw);
+  return check_cuda("mix backward");
+}
+// ------------------------------------------------------------------------------------------------
+// C ABI: SURVEY row f1 (convbn.cuh) -- ShrinkBlock / RectifyBlock: [ReLU ->] Conv2d 3x3 (c_in -> 32) -> BatchNorm2d
+// ------------------------------------------------------------------------------------------------
+extern "C" int senas_convbn_workspace(int32_t B, int32_t H, int32_t W, int32_t c_in, int64_t *saved_bytes,
+                                      int64_t *scratch_bytes) {
+#ifdef SENAS_EMU
+  (void)B, (void)H, (void)W, (void)c_in, (void)saved_bytes, (void)scratch_bytes;
+  SENAS_FAIL("convbn: tcgen05 path, not in the emulator build");
+#else
+  CbnGeo g;
+  if (cbn_geo(B, H, W, c_in, &g)) SENAS_FAIL("convbn: unsupported geometry B=%d H=%d W=%d c_in=%d (W %% 64 == 0, c_in in {24,32,64,96,128})", B, H, W, c_in);
+  if (saved_bytes) *saved_bytes = g.saved_floats * 4;
+  if (scratch_bytes) *scratch_bytes = g.scratch_floats * 4;
+  return 0;
+#endif
+}
+extern "C" int senas_convbn_forward(const senas_convbn_args_t *a) {
+#ifdef SENAS_EMU
+  (void)a;
+  SENAS_FAIL("convbn: tcgen05 path, not in the emulator build");
+#else
+  if (!a || !a->x || !a->weight || !a->gamma || !a->beta || !a->out || !a->saved || !a->scratch) SENAS_FAIL("convbn forward: null argument");
+  CbnGeo g;
+  if (cbn_geo(a->batch, a->h, a->w, a->c_in, &g)) SENAS_FAIL("convbn forward: unsupported geometry");
+  if ((a->x_ld & 3) || ((uintptr_t)a->x & 15) || ((uintptr_t)a->out & 15) || ((uintptr_t)a->saved & 15) || ((uintptr_t)a->scratch & 15))
+    SENAS_FAIL("convbn forward: alignment");
+  if (!a->training && (!a->running_mean || !a->running_var)) SENAS_FAIL("convbn forward: eval mode needs running statistics");
+  float *saved = (float *)a->saved, *scratch = (float *)a->scratch;
+  float *y = saved + g.y_off, *stats = saved + g.stats_off;
+  __nv_bfloat16 *xb = reinterpret_cast<__nv_bfloat16 *>(saved + g.xb_off);
+  void *st = a->stream;
+  SENAS_TAG("cbn_cast", 0, g.npix * (4.0 * a->c_in + 64.0 * g.nslices));
+  SENAS_LAUNCH(cbn_cast_kernel, dim3((unsigned)((g.npix * g.nslices * 4 + 255) / 256)), dim3(256), 0, st, a->x, a->x_ld, a->c_in,
+               a->relu_in, xb, g.npix, g.nslices);
+  const Geo geo = make_geo(3, 1, SENAS_OP_NORM, DIR_FWD);
+  const int T = 9, s_ci = T, s_co = a->c_in * T;
+  for (int sl = 0; sl < g.nslices; ++sl) {
+    TcConvArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.nterms = 4, ta.mode = 0;
+    for (int t = 0; t < 4; ++t) {
+      ta.w[t] = a->weight + (int64_t)t * 8 * s_co + (int64_t)sl * 32 * s_ci;
+      ta.y[t] = y + 8 * t, ta.partials[t] = scratch + g.part_off + (int64_t)t * a->batch * g.ctas * 16;
+    }
+    ta.y_ld = 32, ta.ws_t = 1, ta.ws_k = s_ci, ta.ws_n = s_co;
+    ta.cin_valid = std::min(32, a->c_in - 32 * sl);
+    ta.H = a->h, ta.W = a->w, ta.Ho = a->h, ta.Wo = a->w, ta.so = 1;
+    ta.rows_per_cta = g.rows, ta.row_chunks = g.chunks, ta.taps = geo.taps;
+    ta.acc_y = sl > 0, ta.no_stats = sl + 1 < g.nslices;
+    SENAS_TAG("convbn_fwd", 2.0 * g.npix * T * ta.cin_valid * 32, g.npix * (64.0 + 128.0 * (sl > 0 ? 2 : 1)));
+    const int rc = launch_conv_tc(xb + (int64_t)sl * g.npix * 32, a->batch, ta, st);
+    if (rc) SENAS_FAIL("convbn forward: tcgen05 launch failed (code %d)", rc);
+  }
+  const float M = (float)g.npix;
+  if (a->training) {
+    SENAS_TAG("reduce", 0, 0);
+    SENAS_LAUNCH(rows_reduce_kernel, dim3(2, 4), dim3(kRowsReduceThreads), 0, st, (const float *)(scratch + g.part_off),
+                 scratch + g.sums_off, a->batch * g.ctas, 16);
+  }
+  SENAS_TAG("bn_finalize", 0, 0);
+  SENAS_LAUNCH(cbn_finalize_kernel, dim3(1), dim3(32), 0, st, (const float *)(scratch + g.sums_off), M, a->gamma, a->beta,
+               a->running_mean, a->running_var, a->num_batches_tracked, a->momentum, a->eps, a->training, stats);
+  SENAS_TAG("convbn_apply", 0, g.npix * 256.0);
+  SENAS_LAUNCH(cbn_apply_kernel, dim3((unsigned)((g.npix * 8 + 255) / 256)), dim3(256), 0, st, (const float *)y, (const float *)stats,
+               a->out, g.npix);
+  return check_cuda("convbn forward");
+#endif
+}
+extern "C" int senas_convbn_backward(const senas_convbn_args_t *a) {
+#ifdef SENAS_EMU
+  (void)a;
+  SENAS_FAIL("convbn: tcgen05 path, not in the emulator build");
+#else
+  if (!a || !a->x || !a->weight || !a->gamma || !a->grad_out || !a->saved || !a->scratch || !a->grad_weight || !a->grad_gamma ||
+      !a->grad_beta)
+    SENAS_FAIL("convbn backward: null argument");
+  CbnGeo g;
+  if (cbn_geo(a->batch, a->h, a->w, a->c_in, &g)) SENAS_FAIL("convbn backward: unsupported geometry");
+  if ((a->grad_out_ld & 3) || ((uintptr_t)a->grad_out & 15) || (a->grad_x && ((uintptr_t)a->grad_x & 15))) SENAS_FAIL("convbn backward: alignment");
+  float *saved = (float *)a->saved, *scratch = (float *)a->scratch;
+  const float *y = saved + g.y_off, *stats = saved + g.stats_off;
+  const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(saved + g.xb_off);
+  __nv_bfloat16 *dyb = reinterpret_cast<__nv_bfloat16 *>(scratch + g.dy_off);
+  float *sums = scratch + g.sums_off, *coef = scratch + g.coef_off, *bpart = scratch + g.bpart_off;
+  void *st = a->stream;
+  SENAS_TAG("convbn_bstats", 0, g.npix * 256.0);
+  SENAS_LAUNCH(cbn_bwd_stats_kernel, dim3(g.bwd_blocks), dim3(256), 0, st, a->grad_out, a->grad_out_ld, y, stats, g.npix, g.bwd_px,
+               bpart);
+  SENAS_TAG("reduce", 0, 0);
+  SENAS_LAUNCH(rows_reduce_kernel, dim3(8, 1), dim3(kRowsReduceThreads), 0, st, (const float *)bpart, sums, g.bwd_blocks, 64);
+  SENAS_TAG("bn_finalize", 0, 0);
+  SENAS_LAUNCH(cbn_bwd_finalize_kernel, dim3(1), dim3(32), 0, st, (const float *)sums, (float)g.npix, stats, a->training,
+               a->grad_gamma, a->grad_beta, coef);
+  SENAS_TAG("pack_dy", 0, g.npix * (256.0 + 64.0));
+  SENAS_LAUNCH(cbn_pack_dy_kernel, dim3((unsigned)((g.npix * 4 + 255) / 256)), dim3(256), 0, st, a->grad_out, a->grad_out_ld, y,
+               (const float *)coef, dyb, g.npix);
+  const int T = 9, s_ci = T, s_co = a->c_in * T;
+  const Geo gf = make_geo(3, 1, SENAS_OP_NORM, DIR_FWD), gd = make_geo(3, 1, SENAS_OP_NORM, DIR_DGRAD);
+  for (int sl = 0; sl < g.nslices; ++sl) {
+    const int cv = std::min(32, a->c_in - 32 * sl);
+    if (a->grad_x) {
+      TcConvArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.nterms = 4, ta.mode = 1;
+      for (int t = 0; t < 4; ++t) ta.w[t] = a->weight + (int64_t)t * 8 * s_co + (int64_t)sl * 32 * s_ci;
+      ta.ws_t = 1, ta.ws_k = s_co, ta.ws_n = s_ci, ta.cin_valid = cv;
+      ta.H = a->h, ta.W = a->w, ta.Ho = a->h, ta.Wo = a->w, ta.so = 1;
+      ta.out32 = a->grad_x + 32 * sl, ta.out_ld = a->c_in, ta.accumulate = 0;
+      ta.mask = a->relu_in ? a->x + 32 * sl : nullptr;
+      if (a->relu_in && a->x_ld != a->c_in) SENAS_FAIL("convbn backward: the ReLU mask needs x dense (x_ld == c_in)");
+      ta.rows_per_cta = g.rows, ta.row_chunks = g.chunks, ta.taps = gd.taps;
+      SENAS_TAG("convbn_dgrad", 2.0 * g.npix * T * cv * 32, g.npix * (64.0 + 4.0 * cv));
+      const int rc = launch_conv_tc(dyb, a->batch, ta, st);
+      if (rc) SENAS_FAIL("convbn backward: tcgen05 dgrad launch failed (code %d)", rc);
+    }
+    float *dst[kTcMaxTerms];
+    for (int t = 0; t < 4; ++t) dst[t] = a->grad_weight + (int64_t)t * 8 * s_co + (int64_t)sl * 32 * s_ci;
+    const int rcw = launch_conv_tc_wgrad(xb + (int64_t)sl * g.npix * 32, dyb, a->batch, a->h, a->w, gf.taps, 0, T, 1, 0,
+                                         scratch + g.wpart_off, dst, 4, s_ci, s_co, st, 1, 0, cv);
+    if (rcw) SENAS_FAIL("convbn backward: tcgen05 wgrad launch failed (code %d)", rcw);
+  }
+  return check_cuda("convbn backward");
+#endif
+}
+extern "C" int senas_mix_dx(const float *g, int64_t g_ld, const float *w0, int32_t off0, const float *w1, int32_t off1,
+                            const float *w2, int32_t off2, float *out, int32_t C, int64_t npix, void *stream) {
+  // term j is present iff off_j >= 0; a present term with a NULL weight has coefficient 1
+  if (!g || !out || C < 4 || (C & 3) || (g_ld & 3) || npix < 1) SENAS_FAIL("mix dx: bad arguments");
+  MixDxArgs q;
+  q.g = g, q.g_ld = g_ld, q.out = out, q.C = C, q.npix = npix;
+  const float *w[3] = {w0, w1, w2};
+  const int32_t off[3] = {off0, off1, off2};
+  int n = 0;
+  for (int j = 0; j < 3; ++j) {
+    q.w[j] = w[j], q.off[j] = off[j] < 0 ? 0 : off[j], q.on[j] = off[j] >= 0;
+    if (off[j] >= 0 && (off[j] & 3)) SENAS_FAIL("mix dx: channel offsets must be multiples of 4");
+    n += q.on[j];
+  }
+  const int64_t total = npix * (C / 4);
+  SENAS_TAG("mix_bwd", 0, 4.0 * npix * C * (n + 1));
+  SENAS_LAUNCH(mix_dx_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, q);
+  return check_cuda("mix dx");
+}
+// ------------------------------------------------------------------------------------------------
 // C ABI: gradient exchange (NCCL over NVLink / NVSwitch), one process per GPU
 // ------------------------------------------------------------------------------------------------
 extern "C" int senas_comm_unique_id(void *id128) {
@@ -1955,6 +2158,10 @@ extern "C" int senas_set_gather_mma(int on) {  // bf16 mode: mma.sync (1, defaul
 }
 extern "C" int senas_set_ds_fused(int on) {  // affects graphs planned afterwards
   g_ds_fused = on != 0;
+  return 0;
+}
+extern "C" int senas_set_z_bfloat(int on) {  // affects graphs planned afterwards (bf16 mode only)
+  g_z_bf16 = on != 0;
   return 0;
 }
 extern "C" int senas_set_defer(int on) {

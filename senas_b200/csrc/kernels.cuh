@@ -585,8 +585,16 @@ SENAS_DEVFN float block_rows_sum(const float *src, int rows, int V, int col) {
   __shared__ float s_rs[8][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float r = 0.f;
-  if (col < V)
-    for (int b = warp; b < rows; b += 8) r += src[(int64_t)b * V + col];
+  if (col < V) {
+    float r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    int b = warp;
+    for (; b + 24 < rows; b += 32) {  // four loads in flight (these reductions are pure load latency)
+      r += src[(int64_t)b * V + col], r1 += src[(int64_t)(b + 8) * V + col];
+      r2 += src[(int64_t)(b + 16) * V + col], r3 += src[(int64_t)(b + 24) * V + col];
+    }
+    for (; b < rows; b += 8) r += src[(int64_t)b * V + col];
+    r = (r + r1) + (r2 + r3);
+  }
   __syncthreads();
   s_rs[warp][lane] = r;
   __syncthreads();
@@ -596,27 +604,39 @@ SENAS_DEVFN float block_rows_sum(const float *src, int rows, int V, int col) {
   return t;
 }
 
-// dst[group][V] = sum over rows of src[group][rows][V];  grid = (ceil(V/8), groups), block = 256 = 32 row lanes x 8
+// dst[group][V] = sum over rows of src[group][rows][V];  grid = (ceil(V/8), groups), block = 1024 = 128 row lanes x 8
 // columns (a 32-byte sector per row and block): V is a few hundred at most, so 32 columns per block left the reduction of
-// a few thousand partial rows to ~10-25 blocks.  Fixed order: lane r sums rows r, r+32, ...; lanes combined 0..31.
-constexpr int kRowsReduceCols = 8;
-__global__ void __launch_bounds__(256) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
-  __shared__ float s_rr[32][kRowsReduceCols + 1];
+// a few thousand partial rows to ~10-25 blocks.  These launches sit on every candidate's backward chain (statistics ->
+// reduce -> coefficients -> dz), i.e. their latency is step time: 128 row lanes with 4 loads in flight each instead of 32
+// (ncu, round 2: 15 us at 2048 rows x 320 columns, long-scoreboard stalls 50 per issue -- pure load latency).
+// Fixed order: lane r sums rows r, r+128, ... in four interleaved chains; lanes combined 16 at a time, then 8.
+constexpr int kRowsReduceCols = 8, kRowsReduceLanes = 128, kRowsReduceThreads = kRowsReduceCols * kRowsReduceLanes;
+__global__ void __launch_bounds__(kRowsReduceThreads) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
+  __shared__ float s_rr[kRowsReduceLanes][kRowsReduceCols + 1];
+  __shared__ float s_r2[8][kRowsReduceCols + 1];
+  constexpr int L = kRowsReduceLanes;
   const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3, col = blockIdx.x * kRowsReduceCols + cl;
   const float *p = src + (int64_t)blockIdx.y * rows * V + col;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
   if (col < V) {
     int b = rl;
-    for (; b + 96 < rows; b += 128) {
-      r0 += p[(int64_t)b * V], r1 += p[(int64_t)(b + 32) * V], r2 += p[(int64_t)(b + 64) * V], r3 += p[(int64_t)(b + 96) * V];
+    for (; b + 3 * L < rows; b += 4 * L) {
+      r0 += p[(int64_t)b * V], r1 += p[(int64_t)(b + L) * V], r2 += p[(int64_t)(b + 2 * L) * V], r3 += p[(int64_t)(b + 3 * L) * V];
     }
-    for (; b < rows; b += 32) r0 += p[(int64_t)b * V];
+    for (; b < rows; b += L) r0 += p[(int64_t)b * V];
   }
   s_rr[rl][cl] = (r0 + r1) + (r2 + r3);
   __syncthreads();
+  if (threadIdx.x < 64) {  // (column, group of 16 lanes)
+    const int c = threadIdx.x & 7, g = threadIdx.x >> 3;
+    float t = 0.f;
+    for (int r = 0; r < 16; ++r) t += s_rr[g * 16 + r][c];
+    s_r2[g][c] = t;
+  }
+  __syncthreads();
   if (threadIdx.x < kRowsReduceCols && col < V) {
     float t = 0.f;
-    for (int r = 0; r < 32; ++r) t += s_rr[r][threadIdx.x];
+    for (int g = 0; g < 8; ++g) t += s_r2[g][threadIdx.x];
     dst[(int64_t)blockIdx.y * V + col] = t;
   }
 }
@@ -2467,6 +2487,8 @@ SENAS_DEVFN void dwl_wgrad_walk(const DwItem &it, int n, int H, int W, int c0, i
     for (int j = 0; j < WT; ++j) dzr[s][j] = 0.f;
   const float *xb = it.in + (int64_t)n * H * W * it.in_ld + ch;
   const float *dzb = it.in2 + (int64_t)n * H * W * C + ch;
+  const uint16_t *dzh = reinterpret_cast<const uint16_t *>(it.in2) + (int64_t)n * H * W * C + ch;  // bf16-stored dz
+  const int dz_bf = it.in2_bf;
   const int64_t in_ld = it.in_ld;
   const int R = r1 - r0, niter = R + K - 1, r_first = r0 - P;
   for (int i0 = 0; i0 < niter; i0 += K) {
@@ -2476,7 +2498,9 @@ SENAS_DEVFN void dwl_wgrad_walk(const DwItem &it, int n, int H, int W, int c0, i
       if (i < niter) {
 #pragma unroll
         for (int j = 0; j < WT; ++j)  // dz row entering the window: output row r0 + i (slot u)
-          dzr[u][j] = (i < R && c0 + j < W) ? dzb[((int64_t)(r0 + i) * W + c0 + j) * C] : 0.f;
+          dzr[u][j] = (i < R && c0 + j < W) ? (dz_bf ? senas_bits_f((uint32_t)dzh[((int64_t)(r0 + i) * W + c0 + j) * C] << 16)
+                                                     : dzb[((int64_t)(r0 + i) * W + c0 + j) * C])
+                                            : 0.f;
         if (rr >= 0 && rr < H) {
           float xv[NX];
           const float *rowp = xb + ((int64_t)rr * W + (c0 - P)) * in_ld;

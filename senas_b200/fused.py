@@ -164,6 +164,9 @@ class GraphRunner:
         self.edges, self.n_inputs, self.n_nodes, self.node_relu = edges, n_inputs, n_nodes, node_relu
         self.handle = None
         self._plans = {}
+        # optional caller-owned destination of the flat parameter-gradient buffer (senas_b200.optim: a slice of the
+        # gradient arena, so the cell's weight gradients are produced in place -- no per-call allocation, no packing copy)
+        self.grad_buffer = None
         self._build()
 
     def _build(self):
@@ -269,7 +272,11 @@ class GraphRunner:
         n_edges = len(self.edges)
         g_alpha = torch.empty((n_edges, 6), dtype=torch.float32, device=self.device)
         g_beta = torch.empty((n_edges,), dtype=torch.float32, device=self.device) if beta is not None else None
-        g_params = torch.empty((self.grad_floats,), dtype=torch.float32, device=self.device)
+        g_params = self.grad_buffer
+        if g_params is None:
+            g_params = torch.empty((self.grad_floats,), dtype=torch.float32, device=self.device)
+        elif g_params.numel() != self.grad_floats or g_params.device != self.device or not g_params.is_contiguous():
+            raise RuntimeError('senas_b200: GraphRunner.grad_buffer does not match the graph\'s gradient layout')
         g_ins = [torch.empty_like(t, memory_format=torch.channels_last) if need else None
                  for t, need in zip(ins, need_in)]
         a = _lib.BwdArgs()

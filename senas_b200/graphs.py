@@ -15,8 +15,13 @@ flat buckets they pack / unpack themselves:
     all-reduce(bucket_all)
     segment 3: unpack, clip_grad_norm_, SGD
 
-With ``comm`` (senas_b200.comm.Comm, the NCCL communicator owned by libsenas_b200) the two all-reduces are captured
-INTO the graph: the whole data-parallel step is ONE replayed graph, no host round trip between the segments.  Without
+With ``comm`` (senas_b200.comm.Comm, the NCCL communicator owned by libsenas_b200) the all-reduces are captured
+INTO the graph: the whole data-parallel step is ONE replayed graph, no host round trip between the segments, and the
+weight gradients are **bucketed per cell and overlapped with backward**: every fused cell hands its flat gradient
+buffer (0.1 M floats) to ``_sink`` the moment its backward kernels are enqueued; a side stream scales it by 1/world and
+all-reduces it in place while autograd continues with the cells below (the graph records this as a branch that joins
+before gradient clipping).  Only the parameters outside the cells (stems, Shrink/Rectify blocks, head: 0.3 M of the
+1.97 M floats) are reduced after backward, as one bucket.  ``overlap=False`` keeps the single post-backward bucket.  Without
 it (``group`` only) the collectives of ``torch.distributed`` stay outside -- capturing those deadlocked on this stack
 (watchdog thread) -- and the step is three graphs with two eager all-reduces between them (round-1 path, kept as the
 fallback).
@@ -40,7 +45,7 @@ class GraphedSearchStep:
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
                  force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False,
-                 restore_state=True, comm=None):
+                 restore_state=True, comm=None, overlap=True, fused_optim=False):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
         # small latency-bound cells with the large one of the level (senas_b200/supernet.py).  Only while warming up
@@ -62,11 +67,34 @@ class GraphedSearchStep:
                 self.params.append(p)
         self.arch = [p for g in a_opt.param_groups for p in g['params']]
         dev = self.params[0].device
-        if self.segmented:
+        self.overlap = bool(overlap) and comm is not None and self.world > 1
+        self.n_rest = 0
+        # clip + SGD / Adam as flat-buffer kernels of libsenas_b200 (senas_b200/optim.py).  Parameters,
+        # gradients and momentum move into arenas; the cells' weight gradients are produced in the gradient arena.
+        self.fopt = None
+        if fused_optim:
+            from .optim import FusedSearchOptim
+            self.fopt = FusedSearchOptim(model, w_opt, a_opt, grad_clip)
+            self.params = self.fopt.params
+            self._comm_stream = torch.cuda.Stream() if self.overlap else None
+            if self.segmented:
+                self.bucket_arch = self.fopt.flat_g[:self.fopt.n_arch]
+                self.bucket_all = self.fopt.flat_g
+                self.n_rest = self.fopt.n_rest
+                self.all_views = [self.fopt.grad_views[id(p)] for p in self.params]
+        elif self.segmented:
             self.bucket_arch = torch.zeros(sum(p.numel() for p in self.arch), device=dev)
             self.bucket_all = torch.zeros(sum(p.numel() for p in self.params), device=dev)
             self.arch_views = _flat_views(self.bucket_arch, self.arch)
-            self.all_views = _flat_views(self.bucket_all, self.params)
+            # flat layout [parameters outside the fused cells | parameters of the fused cells]: with ``overlap`` the
+            # second part arrives already averaged (per-cell all-reduces issued during backward), only the first part
+            # is all-reduced after backward
+            owned = self._owned_ids() if self.overlap else set()
+            order = [p for p in self.params if id(p) not in owned] + [p for p in self.params if id(p) in owned]
+            self.n_rest = sum(p.numel() for p in self.params if id(p) not in owned)
+            where = dict(zip((id(p) for p in order), _flat_views(self.bucket_all, order)))
+            self.all_views = [where[id(p)] for p in self.params]
+            self._comm_stream = torch.cuda.Stream() if self.overlap else None
         # The warm-up iterations are real optimizer steps (they create the optimizer state tensors whose addresses the
         # graphs bake in, let cudnn.benchmark pick algorithms and size the library's scratch).  With ``restore_state``
         # the model (weights, BatchNorm buffers, arch parameters) and both optimizers are put back afterwards, in
@@ -91,12 +119,35 @@ class GraphedSearchStep:
             self._set_concurrent(False)
         if snap is not None:
             self._restore(snap)
+        if self.fopt is not None:
+            if snap is not None:
+                self.fopt.load_from_torch_state()  # (warm-up steps ran on the arenas: back to the optimizers' own state)
+            self.fopt.publish_state()
 
     def release(self):
         """Destroy the captured graphs (required before the NCCL communicator they captured is destroyed)."""
         self._variants = {}
         self.graphs = []
         torch.cuda.synchronize()
+
+    def _owned_ids(self):
+        """ids of the parameters whose gradients come back in the fused graphs' flat buffers (every MixedOp candidate)."""
+        from .cell import MixedOp
+        return {id(p) for m in self.model.modules() if isinstance(m, MixedOp) for p in m.parameters()}
+
+    def _sink(self, runner, flat):
+        """Called from a fused cell's backward right after its kernels were enqueued (fused.set_grad_sink): average this
+        cell's weight gradients over the ranks on the side stream while backward goes on.  Autograd adopts views of
+        ``flat`` as p.grad (the weight pass starts from p.grad = None), so the reduced values are what clip / SGD see."""
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            flat.mul_(1.0 / self.world)
+            self.comm.all_reduce_(flat, stream=cs)
+
+    def flat_grads(self):
+        """The (averaged, after the step: clipped) gradients of the last weight pass in ``model.parameters()`` order."""
+        return torch.cat([v.reshape(-1) for v in self.all_views])
 
     # -- state ------------------------------------------------------------------------------------------------
     def _set_concurrent(self, on):
@@ -157,7 +208,13 @@ class GraphedSearchStep:
             p.grad = None
         self.a_opt.zero_grad(set_to_none=True)
         self._backward(self.criterion(self.model(xv), yv))
-        if self.segmented:
+        if self.fopt is not None:
+            self.fopt.pack_rest(self.fopt.arch, self.fopt.arch_grad_views)
+            if self.world > 1:
+                self.bucket_arch.mul_(1.0 / self.world)
+            for p in self.params:
+                p.grad = None
+        elif self.segmented:
             torch._foreach_copy_(self.arch_views, [p.grad for p in self.arch])
             self.bucket_arch.mul_(1.0 / self.world)
             for p in self.params:
@@ -189,21 +246,44 @@ class GraphedSearchStep:
     def _seg2(self):
         xt, yt, xv, yv = self.static
         if self._arch:
-            if self.segmented:
-                for p, v in zip(self.arch, self.arch_views):
-                    p.grad = v
-            self.a_opt.step()
+            if self.fopt is not None:
+                self.fopt.adam_step()
+            else:
+                if self.segmented:
+                    for p, v in zip(self.arch, self.arch_views):
+                        p.grad = v
+                self.a_opt.step()
         self.w_opt.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(xt), yt)
-        self._backward(loss)
-        if self.segmented:
+        if self.overlap:
+            from . import fused
+            fused.set_grad_sink(self._sink)
+            try:
+                self._backward(loss)
+            finally:
+                fused.set_grad_sink(None)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)  # join the all-reduce branch
+        else:
+            self._backward(loss)
+        if self.fopt is not None:
+            if not self._capturing and not self.fopt.check_direct():
+                raise RuntimeError('senas_b200: autograd did not adopt the arena views of the fused cells\' gradients')
+            self.fopt.pack_rest()  # the cells' gradients are already in the arena
+            if self.world > 1:
+                (self.bucket_all[:self.n_rest] if self.overlap else self.bucket_all).mul_(1.0 / self.world)
+            for p in self.params:
+                p.grad = None
+        elif self.segmented:
             torch._foreach_copy_(self.all_views, [p.grad for p in self.params])
-            self.bucket_all.mul_(1.0 / self.world)
+            (self.bucket_all[:self.n_rest] if self.overlap else self.bucket_all).mul_(1.0 / self.world)
             for p in self.params:
                 p.grad = None
         self.loss = loss.detach()
 
     def _seg3(self):
+        if self.fopt is not None:
+            self.fopt.sgd_step()
+            return
         if self.segmented:
             for p, v in zip(self.params, self.all_views):
                 p.grad = v
@@ -212,6 +292,7 @@ class GraphedSearchStep:
 
     def _run(self, capture, arch=True):
         self._arch = bool(arch)
+        self._capturing = bool(capture)
         segs = (self._seg1, self._seg2, self._seg3)
         if self.segmented and self.comm is not None and self.world > 1:  # one graph with the NCCL all-reduces inside
             def whole():
@@ -219,7 +300,7 @@ class GraphedSearchStep:
                 if self._arch:
                     self.comm.all_reduce_(self.bucket_arch)
                 self._seg2()
-                self.comm.all_reduce_(self.bucket_all)
+                self.comm.all_reduce_(self.bucket_all[:self.n_rest] if self.overlap else self.bucket_all)
                 self._seg3()
             if capture:
                 g = torch.cuda.CUDAGraph()
@@ -261,7 +342,9 @@ class GraphedSearchStep:
         fused.check_scratch(self._scratch_ptrs)
         arch = bool(arch)
         var = self._variants.get(arch)
-        if var is None or var[1] != self._lr():
+        if self.fopt is not None:
+            self.fopt.sync_lr()  # device scalars: no re-capture
+        if var is None or (self.fopt is None and var[1] != self._lr()):
             self._capture(arch)
             var = self._variants[arch]
         graphs = var[0]

@@ -184,6 +184,82 @@ class StemConvBn(nn.Sequential):
         return self[1](self[0](x).contiguous(memory_format=torch.channels_last))
 
 
+class _ConvBnFn(torch.autograd.Function):
+    """[ReLU ->] Conv2d 3x3 (c_in -> 32) -> BatchNorm2d through ``senas_convbn_forward/backward`` (SURVEY row f1,
+    utils/operations.py:206-232): tcgen05 implicit GEMM with the BatchNorm statistics out of the conv epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, norm, relu_in):
+        import ctypes as C
+        from . import _lib, fused
+        lib = _lib.get()
+        x = x.contiguous(memory_format=torch.channels_last)
+        B, c_in, H, W = x.shape
+        sb, scb = C.c_int64(), C.c_int64()
+        _lib.check(lib, lib.senas_convbn_workspace(B, H, W, c_in, C.byref(sb), C.byref(scb)))
+        dev = x.device
+        out = torch.empty((B, 32, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        saved = torch.empty(sb.value, dtype=torch.uint8, device=dev)
+        slot = fused.get_slot()
+        scratch = fused.scratch_for(dev, scb.value, ('convbn', slot))
+        a = _lib.ConvBnArgs()
+        a.batch, a.h, a.w, a.c_in, a.relu_in, a.training = B, H, W, c_in, int(relu_in), int(norm.training)
+        a.x, a.x_ld = x.data_ptr(), c_in
+        a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        a.running_mean, a.running_var = norm.running_mean.data_ptr(), norm.running_var.data_ptr()
+        a.num_batches_tracked = norm.num_batches_tracked.data_ptr()
+        a.momentum, a.eps = float(norm.momentum), float(norm.eps)
+        a.out, a.saved, a.scratch = out.data_ptr(), saved.data_ptr(), scratch.data_ptr()
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib, lib.senas_convbn_forward(C.byref(a)))
+        ctx.save_for_backward(x, weight, gamma, beta)
+        ctx.saved_buf, ctx.slot, ctx.relu_in, ctx.training = saved, slot, int(relu_in), int(norm.training)
+        ctx.bn = (float(norm.momentum), float(norm.eps))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from . import _lib, fused
+        lib = _lib.get()
+        x, weight, gamma, beta = ctx.saved_tensors
+        g = g.contiguous(memory_format=torch.channels_last)
+        B, c_in, H, W = x.shape
+        dev = x.device
+        sb, scb = C.c_int64(), C.c_int64()
+        _lib.check(lib, lib.senas_convbn_workspace(B, H, W, c_in, C.byref(sb), C.byref(scb)))
+        scratch = fused.scratch_for(dev, scb.value, ('convbn', ctx.slot))
+        gx = torch.empty_like(x, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
+        gw, gg, gb = torch.empty_like(weight), torch.empty_like(gamma), torch.empty_like(beta)
+        a = _lib.ConvBnArgs()
+        a.batch, a.h, a.w, a.c_in, a.relu_in, a.training = B, H, W, c_in, ctx.relu_in, ctx.training
+        a.x, a.x_ld = x.data_ptr(), c_in
+        a.weight, a.gamma, a.beta = weight.data_ptr(), gamma.data_ptr(), beta.data_ptr()
+        a.momentum, a.eps = ctx.bn
+        a.saved, a.scratch = ctx.saved_buf.data_ptr(), scratch.data_ptr()
+        a.grad_out, a.grad_out_ld = g.data_ptr(), 32
+        a.grad_x = gx.data_ptr() if gx is not None else None
+        a.grad_weight, a.grad_gamma, a.grad_beta = gw.data_ptr(), gg.data_ptr(), gb.data_ptr()
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib, lib.senas_convbn_backward(C.byref(a)))
+        return gx, gw, gg, gb, None, None
+
+
+def _convbn_on_tensor_cores(x, conv, norm):
+    """The fused tcgen05 path covers the bf16 conv mode (2e-2 gate), maps that are a multiple of 64 pixels wide and the
+    channel counts of the search supernet; everything else (exact fp32 mode, narrow maps) keeps PyTorch's modules."""
+    from . import fused
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and fused.get_conv_mode() == 'bf16' and fused_convbn[0]
+            and x.shape[3] % 64 == 0 and conv.out_channels == 32 and conv.in_channels in (24, 32, 64, 96, 128)
+            and norm.affine and norm.track_running_stats and norm.momentum is not None)
+
+
+import os as _os
+fused_convbn = [_os.environ.get('SENAS_NO_CONVBN', '0') != '1']  # switch (A/B runs, tests): False keeps cuDNN / ATen for the Shrink / Rectify blocks in every mode
+
+
 class ShrinkBlock(nn.Module):
     def __init__(self, c_in, c_ot):
         super().__init__()
@@ -192,6 +268,8 @@ class ShrinkBlock(nn.Module):
         self.norm = nn.BatchNorm2d(c_ot)
 
     def forward(self, x):
+        if _convbn_on_tensor_cores(x, self.conv, self.norm):
+            return _ConvBnFn.apply(x, self.conv.weight, self.norm.weight, self.norm.bias, self.norm, True)
         return self.norm(self.conv(self.act(x)))
 
 
@@ -203,6 +281,8 @@ class RectifyBlock(nn.Module):
         self.norm = nn.BatchNorm2d(c_ot)
 
     def forward(self, x):
+        if _convbn_on_tensor_cores(x, self.conv, self.norm):
+            return _ConvBnFn.apply(x, self.conv.weight, self.norm.weight, self.norm.bias, self.norm, False)
         return self.norm(self.conv(x))
 
 

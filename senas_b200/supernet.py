@@ -8,6 +8,8 @@ Everything outside the cells (stems, gamma-mixed skip concat, head conv) is stoc
 rows f1/f3 of SURVEY.md section 8 ("next").  Activations travel in ``channels_last`` (NHWC)
 memory so the cells read and write them without layout conversion.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -67,6 +69,7 @@ class SenasSearch(nn.Module):
     # the small latency-bound cells hide under the large one in the captured graph.  Same operations on the same data:
     # results do not depend on the setting.
     concurrent_cells = False
+    fused_mix = os.environ.get('SENAS_NO_MIX', '0') != '1'  # gamma mix + concat through libsenas_b200 (row f3); False: torch.lerp / torch.cat
     gamma_rows_sum_to_one = False  # set by NAS (which softmaxes gamma); a direct caller may pass any gamma
 
     def _cell_stream(self, j, device):
@@ -104,6 +107,10 @@ class SenasSearch(nn.Module):
                 try:
                     with (torch.cuda.stream(st) if st is not None else _nullctx()):
                         parts = [out[0][j]]
+                        if self.fused_mix and x.is_cuda and gidx:
+                            in0 = mix_concat(gamma, gidx, [out[k][j] for k in range(i)])
+                            row.append(self.blocks[i][j](in0, out[i - 1][j + 1], alpha_up_nm, alpha_up, beta_up))
+                            continue
                         for k, g in enumerate(gidx):
                             if self.gamma_rows_sum_to_one:
                                 # softmax pairs (NAS.forward, senas_search.py:260): a*g0 + b*g1 == lerp(a, b, g1), one
@@ -124,6 +131,76 @@ class SenasSearch(nn.Module):
         if self._supervision:
             return [head(s0, out[i][0] if i else out[0][0], alpha_up_nm, alpha_up, beta_up) for i in range(depth)]
         return [head(s0, out[depth - 1][0], alpha_up_nm, alpha_up, beta_up)]
+
+
+class _MixConcat(torch.autograd.Function):
+    """``cat([T0, g[0]*T0 + g[1]*T1, ...], dim=1)`` (search/senas_search.py:96-107) written by
+    libsenas_b200 straight into one NHWC concat buffer: one launch per 32-channel slot, no intermediate mix tensors, no
+    ``torch.cat``; backward = one launch per skip tensor (its up to three slices of the concat gradient, weighted) plus the
+    two dot products per gamma pair (fixed-order reduction)."""
+
+    @staticmethod
+    def forward(ctx, gamma, gidx, *ts):
+        from . import _lib
+        lib = _lib.get()
+        ts = [t.contiguous(memory_format=torch.channels_last) for t in ts]
+        B, C, H, W = ts[0].shape
+        n = len(ts)
+        gamma = gamma.contiguous()
+        out = torch.empty((B, C * n, H, W), dtype=torch.float32, device=ts[0].device, memory_format=torch.channels_last)
+        st = torch.cuda.current_stream(out.device).cuda_stream
+        npix = B * H * W
+        with torch.cuda.device(out.device):
+            for s in range(n):
+                if s == 0:
+                    rc = lib.senas_mix_forward(ts[0].data_ptr(), C, None, 0, None, out.data_ptr(), C * n, 0, C, npix, st)
+                else:
+                    rc = lib.senas_mix_forward(ts[s - 1].data_ptr(), C, ts[s].data_ptr(), C, gamma.data_ptr() + 8 * gidx[s - 1],
+                                               out.data_ptr(), C * n, C * s, C, npix, st)
+                _lib.check(lib, rc)
+        ctx.gidx, ctx.n, ctx.shape = list(gidx), n, (B, C, H, W)
+        ctx.save_for_backward(gamma, *ts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        lib = _lib.get()
+        gamma, *ts = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        n, gidx = ctx.n, ctx.gidx
+        g = g.contiguous(memory_format=torch.channels_last)
+        dev = g.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        npix = B * H * W
+        dgamma = torch.zeros_like(gamma)
+        scratch = torch.empty(1184 * max(n - 1, 1), dtype=torch.float32, device=dev)
+        gp = gamma.data_ptr()
+        outs = []
+        with torch.cuda.device(dev):
+            for s in range(1, n):  # d gamma[g][0] = <g_s, T_{s-1}>, d gamma[g][1] = <g_s, T_s>
+                _lib.check(lib, lib.senas_mix_backward(ts[s - 1].data_ptr(), C, ts[s].data_ptr(), C, gp + 8 * gidx[s - 1],
+                                                       g.data_ptr(), C * n, C * s, C, npix, None, None,
+                                                       dgamma.data_ptr() + 8 * gidx[s - 1], scratch.data_ptr() + 4 * 1184 * (s - 1), st))
+            for k in range(n):
+                if not ctx.needs_input_grad[2 + k]:
+                    outs.append(None)
+                    continue
+                d = torch.empty((B, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+                # slices T_k reached: slot 0 (k == 0, coefficient 1), `a` of slot k + 1, `b` of slot k
+                w0, o0 = (None, 0) if k == 0 else (None, -1)
+                w1, o1 = (gp + 8 * gidx[k], C * (k + 1)) if k + 1 < n else (None, -1)
+                w2, o2 = (gp + 8 * gidx[k - 1] + 4, C * k) if k >= 1 else (None, -1)
+                _lib.check(lib, lib.senas_mix_dx(g.data_ptr(), C * n, w0, o0, w1, o1, w2, o2, d.data_ptr(), C, npix, st))
+                outs.append(d)
+        return (dgamma, None, *outs)
+
+
+def mix_concat(gamma, gidx, tensors):
+    """``cat([T0, gamma[g0,0]*T0 + gamma[g0,1]*T1, gamma[g1,0]*T1 + gamma[g1,1]*T2, ...], 1)`` for CUDA fp32 tensors."""
+    if len(tensors) == 1:
+        return tensors[0]
+    return _MixConcat.apply(gamma.float(), tuple(gidx), *tensors)
 
 
 class _nullctx:

@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, result, use_comm):
+def _worker(rank, world, port, result, use_comm, overlap=True):
     import torch.distributed as dist
     import senas_b200
     from senas_b200.dp import broadcast_parameters
@@ -74,13 +74,14 @@ def _worker(rank, world, port, result, use_comm):
         from senas_b200.comm import Comm
         comm = Comm(group=dist.group.WORLD, device=dev)
     step = senas_b200.GraphedSearchStep(m2, crit, w2, a2, (xt, yt, xv, yv), grad_clip=5.0, warmup=2,
-                                        group=dist.group.WORLD, comm=comm, capture_error_mode='thread_local')
+                                        group=dist.group.WORLD, comm=comm, capture_error_mode='thread_local', overlap=overlap)
+    assert step.overlap == (bool(use_comm) and overlap)
     assert len(step.graphs) == (1 if use_comm else 3), len(step.graphs)
     for k, v in m2.state_dict().items():
         assert torch.equal(v, init[k]), f'warm-up left a trace in {k}'
     got_loss = step(xt, yt, xv, yv).item()
     torch.cuda.synchronize()
-    got_clipped = step.bucket_all.clone()  # averaged over ranks by the all-reduce, then clipped in place by graph 3
+    got_clipped = step.flat_grads()  # averaged over ranks by the all-reduces, then clipped in place by graph 3
     got = m2.state_dict()
     errs = {}
     scale = want_clipped.abs().max().item()
@@ -94,7 +95,10 @@ def _worker(rank, world, port, result, use_comm):
         upd_w, upd_g = (v - init[k]).double(), (got[k] - init[k]).double()
         s = upd_w.abs().max().item()
         if s > 1e-12 and not k.startswith(('alphas', 'betas', 'gamma')):
-            worst_upd = max(worst_upd, (upd_g - upd_w).abs().max().item() / s)
+            # an update of a BatchNorm weight (1.0) by lr * grad ~ 1e-5 is ~150 ulps of the parameter: one ulp of rounding
+            # in p - lr * buf is 1/147 of the update (seen on the box), so allow 2 ulps of the parameter on top
+            ulp = 2 * 1.1920929e-07 * v.abs().max().item()
+            worst_upd = max(worst_upd, max((upd_g - upd_w).abs().max().item() - ulp, 0.0) / s)
     errs['update'] = worst_upd
     errs['unclipped_norm'] = want_grads.norm().item()
     # every rank must hold the same weights after the step
@@ -111,13 +115,16 @@ def _worker(rank, world, port, result, use_comm):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
-@pytest.mark.parametrize('use_comm', [True, False])
-def test_graphed_dp_step_equals_mean_of_local_gradients(use_comm):
+@pytest.mark.parametrize('use_comm,overlap', [(True, True), (True, False), (False, False)])
+def test_graphed_dp_step_equals_mean_of_local_gradients(use_comm, overlap):
+    """(True, True): per-cell buckets all-reduced on a side stream while backward runs, inside the one captured graph
+    (the benched path); (True, False): one post-backward bucket inside the graph; (False, False): three graphs with
+    torch.distributed all-reduces between them."""
     import torch.multiprocessing as mp
     world = 2
     mgr = mp.Manager()
     result = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), result, use_comm), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), result, use_comm, overlap), nprocs=world, join=True)
     assert len(result) == world
     for rank, e in result.items():
         assert e['loss'] <= 2e-5, (rank, e)

@@ -357,6 +357,11 @@ def test_graphed_search_step_matches_eager(mode, segments):
                     assert (got[k] - v).abs().max().item() <= 2.5e-4, k
                 else:
                     scale = max((v - init[k]).abs().max().item(), 1e-3 * v.abs().max().item(), 1e-7)
+                    if mode == 'bf16' and k.endswith('running_mean'):
+                        # the batch mean of a 1x1 conv of a normalised input is ~0: its running-mean update is at the
+                        # level of the bf16 rounding noise of the O(1) activations behind it (cudnn.benchmark may pick
+                        # another fprop algorithm for the stem in this run, which re-rolls that rounding): absolute floor
+                        scale = max(scale, 1e-3)
                     e = ((got[k] - init[k]) - (v - init[k])).abs().max().item() / scale
                     assert e <= 5e-3, f'step 0 {k}: update differs by {e:.2e}'
         else:
