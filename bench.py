@@ -385,7 +385,8 @@ def run_ours(args, rank, world, local_rank):
                                                    warmup=3, group=group, comm=comm,
                                                    capture_error_mode='thread_local' if world > 1 else 'global',
                                                    concurrent_cells=not args.serial_cells, defer_wgrad=args.defer_wgrad,
-                                                   overlap=not args.no_overlap, fused_optim=not args.no_fused_optim)
+                                                   overlap=not args.no_overlap, fused_optim=not args.no_fused_optim,
+                                                   arch_grads_only=args.arch_grads_only)
             launches_per_step = (lib.senas_launch_count() - n_before) // 4   # 3 warm-up steps + 1 capture pass
             graph_note = 'cuda-graph (whole search step captured once, replayed per step)'
             if world > 1:
@@ -465,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
             step3 = senas_b200.GraphedSearchStep(model, crit, w_opt, a_opt, (*dev3[0], *dev3[1]), grad_clip=5.0, warmup=2,
                                                  group=group, comm=comm, capture_error_mode='thread_local',
                                                  concurrent_cells=not args.serial_cells, overlap=not args.no_overlap,
-                                                 fused_optim=not args.no_fused_optim)
+                                                 fused_optim=not args.no_fused_optim, arch_grads_only=args.arch_grads_only)
             for _ in range(2):
                 step3(*dev3[0], *dev3[1])
             n3 = min(args.steps, 10)
@@ -541,7 +542,9 @@ def run_ours(args, rank, world, local_rank):
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.conv_mode == 'bf16' else 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD.format(B=B, S=size, G=gB),
-                   'parallelism': f'dp{world}', 'launch': graph_note, 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)'},
+                   'parallelism': f'dp{world}', 'launch': graph_note, 'conv_mode': args.conv_mode + (' (tcgen05 bf16 operands, fp32 accumulate)' if args.conv_mode == 'bf16' else ' (exact FMA)'), 'l2': 'no flush: each step streams several GB of activations (>> 126 MB L2)',
+                   'arch_step': ('alpha/beta/gamma gradients only (opt-in --arch-grads-only: the weight gradients the reference computes and discards in the architecture step are not computed)' if args.arch_grads_only else 'full backward, as the reference (weight gradients computed and discarded)'),
+                   'between_cells': ('fused: ' + ', '.join(n for n, on in (('flat-arena clip+SGD/Adam (f4)', not args.no_fused_optim and graphed is not None), ('gamma-mix concat (f3)', os.environ.get('SENAS_NO_MIX', '0') != '1'), ('Shrink/Rectify ConvBn on tcgen05 (f1)', os.environ.get('SENAS_NO_CONVBN', '0') != '1' and args.conv_mode == 'bf16')) if on))},
         'e2e': {'value': value_e2e, 'unit': 'images/s', 'ms_per_step': ms_step_e2e,
                 'h2d_bytes_per_step': 2 * B * size * size * (4 + 8), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'roofline': roof, 'kernel_families': families, 'clocks': clk,
@@ -594,6 +597,7 @@ def main():
     ap.add_argument('--no-comm', action='store_true', help='data parallel: keep the all-reduces outside the graphs (torch.distributed)')
     ap.add_argument('--no-overlap', action='store_true', help='data parallel: one post-backward weight-gradient bucket instead of per-cell buckets overlapped with backward')
     ap.add_argument('--no-fused-optim', action='store_true', help='clip_grad_norm_ / SGD / Adam of PyTorch inside the graph instead of the flat-buffer kernels of libsenas_b200 (row f4)')
+    ap.add_argument('--arch-grads-only', action='store_true', help='opt-in: the architecture step computes alpha / beta / gamma gradients only (the reference also computes, then discards, every weight gradient there)')
     ap.add_argument('--no-config3', action='store_true', help='N = 2, 4: skip the BASELINE config-3 leg (global batch 128)')
     ap.add_argument('--serial-cells', action='store_true', help='do not run independent cells of a level on separate streams')
     ap.add_argument('--defer-wgrad', action='store_true', help='leave the weight-gradient lanes of a fused backward running (joined by the next call of the slot)')

@@ -128,6 +128,11 @@ typedef struct {
   float *grad_beta;            /* [n_edges] or NULL */
   float *grad_params;          /* flat buffer of desc.grad_floats floats, fully written */
   void *stream;
+  int32_t skip_wgrad;          /* != 0: the caller wants data / alpha / beta gradients only (the architecture step of
+                                * search_arc.py:268-271 discards every weight gradient: model_optimizer.zero_grad() follows):
+                                * no convolution / depthwise / 1x1 weight-gradient kernel is launched and grad_params is
+                                * left UNDEFINED */
+  int32_t reserved_;
 } senas_bwd_args_t;
 
 const char *senas_version(void);
@@ -216,7 +221,7 @@ typedef struct {
   void *saved, *scratch;
   const float *grad_out; int64_t grad_out_ld;   /* backward inputs */
   float *grad_x;                                /* backward: [batch][h][w][c_in] dense, or NULL */
-  float *grad_weight, *grad_gamma, *grad_beta;  /* backward: [32][c_in][3][3], [32], [32] */
+  float *grad_weight, *grad_gamma, *grad_beta;  /* backward: [32][c_in][3][3] (NULL: not wanted), [32], [32] */
   void *stream;
 } senas_convbn_args_t;
 int senas_convbn_workspace(int32_t batch, int32_t h, int32_t w, int32_t c_in, int64_t *saved_bytes, int64_t *scratch_bytes);

@@ -30,11 +30,13 @@ xs = [torch.randn(B, 1, 256, 256, generator=g).to(dev) for _ in range(2)]
 ys = [(torch.rand(B, 256, 256, generator=g) > 0.8).long().to(dev) for _ in range(2)]
 
 
+# the product sequence (arena optimizer, fused mix / ConvBn blocks): the segments of GraphedSearchStep, launched eagerly
+gs = senas_b200.GraphedSearchStep(m, crit, w, a, (xs[0], ys[0], xs[1], ys[1]), warmup=1, fused_optim=True)
+gs.static = [xs[0], ys[0], xs[1], ys[1]]
+
+
 def step():
-    for p in m.parameters():
-        p.grad = None
-    a.zero_grad(); crit(m(xs[1]), ys[1]).backward(); a.step()
-    w.zero_grad(); l = crit(m(xs[0]), ys[0]); l.backward(); torch.nn.utils.clip_grad_norm_(m.parameters(), 5); w.step()
+    gs._run(capture=False, arch=True)
 
 
 step()  # warm-up: plans, scratch, cudnn.benchmark

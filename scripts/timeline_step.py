@@ -26,7 +26,7 @@ crit = SegmentationLosses('dice_ce')
 g = torch.Generator().manual_seed(1)
 xs = [torch.randn(B, 1, 256, 256, generator=g).to(dev) for _ in range(2)]
 ys = [(torch.rand(B, 256, 256, generator=g) > 0.8).long().to(dev) for _ in range(2)]
-step = senas_b200.GraphedSearchStep(m, crit, w, a, (xs[0], ys[0], xs[1], ys[1]), concurrent_cells=conc)
+step = senas_b200.GraphedSearchStep(m, crit, w, a, (xs[0], ys[0], xs[1], ys[1]), concurrent_cells=conc, fused_optim=True)
 for _ in range(2):
     step(xs[0], ys[0], xs[1], ys[1])
 torch.cuda.synchronize()

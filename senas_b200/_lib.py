@@ -43,7 +43,7 @@ class BwdArgs(C.Structure):
                 ('out', C.c_void_p), ('out_ld', C.c_int64), ('grad_out', C.c_void_p), ('grad_out_ld', C.c_int64),
                 ('saved', C.c_void_p), ('scratch', C.c_void_p), ('grad_in', C.c_void_p * 2),
                 ('grad_in_ld', C.c_int64 * 2), ('grad_alpha', C.c_void_p), ('grad_beta', C.c_void_p),
-                ('grad_params', C.c_void_p), ('stream', C.c_void_p)]
+                ('grad_params', C.c_void_p), ('stream', C.c_void_p), ('skip_wgrad', C.c_int32), ('reserved_', C.c_int32)]
 
 
 class ConvBnArgs(C.Structure):

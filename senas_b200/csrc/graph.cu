@@ -1272,7 +1272,7 @@ static int backward_edge(BwdCall &c, int e) {
         const int kk = t.kind == SENAS_KIND_IDENTITY ? AD_IDENTITY : (t.kind == SENAS_KIND_AVG_POOL ? AD_POOL : AD_UP);
         const int in_px = ep.in_h * ep.in_w;
         if (C == 32) {  // one quad-layout sweep over the input grid: dx += W^T.dy and dW partials
-          const bool up = kk != AD_IDENTITY, want_dw = ed.grad_off[k][0] >= 0;  // up: dy first goes through U^T / P^T
+          const bool up = kk != AD_IDENTITY, want_dw = ed.grad_off[k][0] >= 0 && !c.a->skip_wgrad;  // up: dy first goes through U^T / P^T
           float *du = tmp, *dwp = tmp + (up ? (int64_t)B * in_px * 8 : 0);
           if (kk == AD_UP) {
             SENAS_TAG("adapter_dx", 0, 4.0 * B * HW * 16);
@@ -1315,7 +1315,7 @@ static int backward_edge(BwdCall &c, int e) {
           else SENAS_FAIL("adapter dx: unsupported kind/c_in");
           c.touched[ed.src] = true;
         }
-        if (a.w != nullptr && ed.grad_off[k][0] >= 0) {
+        if (a.w != nullptr && ed.grad_off[k][0] >= 0 && !c.a->skip_wgrad) {
           const int gpx = kk == AD_POOL ? HW : in_px;
           dim3 grid(cdiv(gpx, 128 * kPxTilesPerBlock), B);
 #define SENAS_AD_DW(CC, KK)                                    \
@@ -1353,7 +1353,7 @@ static int backward_edge(BwdCall &c, int e) {
           if (launch_gather_any(a, geo, 8, C, B, sdx, (c.d->reserved & 1) != 0)) return 1;
           c.touched[ed.src] = true;
         }
-        if (ed.grad_off[k][0] >= 0 && !(t.tc && c.a->grad_in[ed.src])) {
+        if (ed.grad_off[k][0] >= 0 && !(t.tc && c.a->grad_in[ed.src]) && !c.a->skip_wgrad) {
           Geo geo = make_geo(t.k, t.dil, ed.op_type, DIR_FWD);
           WgradArgs a;
           memset(&a, 0, sizeof(a));
@@ -1533,7 +1533,7 @@ static int backward_edge(BwdCall &c, int e) {
           }
           c.touched[ed.src] = true;
         }
-        {
+        if (!c.a->skip_wgrad) {
           Geo geo = make_geo(t.k, 1, ed.op_type, DIR_FWD);
           w.x = x, w.x_ld = x_ld, w.partials = tmp, w.batch = B, w.chunk = kDwChunk;
           w.base_h = geo.base_is_out ? p.out_h : ep.in_h, w.base_w = geo.base_is_out ? p.out_w : ep.in_w;
@@ -1652,7 +1652,7 @@ static int backward_dw_group(BwdCall &c, int src, int only_edge) {
     }
     c.touched[src] = true;
   }
-  {
+  if (!c.a->skip_wgrad) {
     DwMultiArgs g = a;
     float *tmp = c.tmp(ln);
     void *st = c.S.stream(ln);
@@ -1832,7 +1832,7 @@ extern "C" int senas_graph_backward(senas_graph_t *g, const senas_bwd_args_t *a)
       c.touched[g2.src] = true;
     }
     // weight gradients of the group from the same packed dy (pixels = GEMM-K)
-    {
+    if (!a->skip_wgrad) {
       float *dst[kTcMaxTerms] = {nullptr, nullptr, nullptr, nullptr};
       for (int i = 0; i < g2.nterms; ++i) dst[i] = a->grad_params + d.edge[g2.edge[i]].grad_off[g2.cand[i]][0];
       int ws_ci, ws_co;
@@ -2023,8 +2023,7 @@ extern "C" int senas_convbn_backward(const senas_convbn_args_t *a) {
   (void)a;
   SENAS_FAIL("convbn: tcgen05 path, not in the emulator build");
 #else
-  if (!a || !a->x || !a->weight || !a->gamma || !a->grad_out || !a->saved || !a->scratch || !a->grad_weight || !a->grad_gamma ||
-      !a->grad_beta)
+  if (!a || !a->x || !a->weight || !a->gamma || !a->grad_out || !a->saved || !a->scratch || !a->grad_gamma || !a->grad_beta)
     SENAS_FAIL("convbn backward: null argument");
   CbnGeo g;
   if (cbn_geo(a->batch, a->h, a->w, a->c_in, &g)) SENAS_FAIL("convbn backward: unsupported geometry");
@@ -2065,6 +2064,7 @@ extern "C" int senas_convbn_backward(const senas_convbn_args_t *a) {
       const int rc = launch_conv_tc(dyb, a->batch, ta, st);
       if (rc) SENAS_FAIL("convbn backward: tcgen05 dgrad launch failed (code %d)", rc);
     }
+    if (!a->grad_weight) continue;  // (architecture step: no weight gradient wanted)
     float *dst[kTcMaxTerms];
     for (int t = 0; t < 4; ++t) dst[t] = a->grad_weight + (int64_t)t * 8 * s_co + (int64_t)sl * 32 * s_ci;
     const int rcw = launch_conv_tc_wgrad(xb + (int64_t)sl * g.npix * 32, dyb, a->batch, a->h, a->w, gf.taps, 0, T, 1, 0,

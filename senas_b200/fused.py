@@ -55,6 +55,15 @@ def candidate_slots(op):
 _scratch = {}
 _flags = {'tc_bf16': False, 'override': None}  # override: graph flags forced by the emulator tests
 _grad_sink = [None]
+_skip_wgrad = [False]
+
+
+def set_skip_wgrad(on):
+    """While set, every fused backward computes data / alpha / beta gradients only and returns no parameter gradients
+    (``senas_bwd_args_t.skip_wgrad``): for the architecture step, whose weight gradients the reference discards
+    (experiments/search_arc.py:268-271: ``architect.step`` is followed by ``model_optimizer.zero_grad()``)."""
+    _skip_wgrad[0] = bool(on)
+
 
 
 def set_grad_sink(fn):
@@ -292,6 +301,7 @@ class GraphRunner:
         a.grad_alpha = g_alpha.data_ptr()
         a.grad_beta = g_beta.data_ptr() if g_beta is not None else None
         a.grad_params, a.stream = g_params.data_ptr(), self._stream()
+        a.skip_wgrad = int(_skip_wgrad[0])
         self.lib.senas_set_slot(slot)
         held = _held.pop(slot, None)
         _lib.check(self.lib, self.lib.senas_graph_backward(self.handle, C.byref(a)))
@@ -337,6 +347,8 @@ class _GraphFn(torch.autograd.Function):
         g_ins, g_alpha, g_beta, g_params = runner.backward(ins, alpha, beta, out, _nhwc(grad_out.float()),
                                                            ctx.saved_buf, ctx.training, need_in, ctx.slot)
         ctx.saved_buf = None  # the library overwrote parts of it (dz in place of z)
+        if _skip_wgrad[0]:  # (grad_params is undefined: the caller asked for no parameter gradients)
+            return (None, None, g_alpha, g_beta, g_ins[0], g_ins[1] if in1 is not None else None, *([None] * len(runner.params)))
         if _grad_sink[0] is not None:
             _grad_sink[0](runner, g_params)
         grads = [g.view(s) for g, s in zip(torch.split(g_params, runner.sizes), runner.shapes)]

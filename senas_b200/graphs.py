@@ -45,7 +45,7 @@ class GraphedSearchStep:
 
     def __init__(self, model, criterion, w_opt, a_opt, example, grad_clip=5.0, warmup=3, group=None,
                  force_segments=False, capture_error_mode='global', concurrent_cells=True, defer_wgrad=False,
-                 restore_state=True, comm=None, overlap=True, fused_optim=False):
+                 restore_state=True, comm=None, overlap=True, fused_optim=False, arch_grads_only=False):
         self.static = [t.clone() for t in example]
         # independent cells of one level of the UNet++ triangle on separate streams: the captured graph overlaps the
         # small latency-bound cells with the large one of the level (senas_b200/supernet.py).  Only while warming up
@@ -68,6 +68,12 @@ class GraphedSearchStep:
         self.arch = [p for g in a_opt.param_groups for p in g['params']]
         dev = self.params[0].device
         self.overlap = bool(overlap) and comm is not None and self.world > 1
+        # opt-in: the architecture step asks autograd for the alpha / beta / gamma gradients only.  The reference's arch
+        # step (search/senas_search.py Architecture.step: loss.backward()) also produces every weight gradient and
+        # search_arc.py:271 zeroes them before any use; with this flag they are never computed (torch.autograd.grad on
+        # the arch parameters + senas_bwd_args_t.skip_wgrad).  Same parameters after the step; OFF by default because it
+        # is work the reference performs inside the step.
+        self.arch_grads_only = bool(arch_grads_only)
         self.n_rest = 0
         # clip + SGD / Adam as flat-buffer kernels of libsenas_b200 (senas_b200/optim.py).  Parameters,
         # gradients and momentum move into arenas; the cells' weight gradients are produced in the gradient arena.
@@ -207,7 +213,18 @@ class GraphedSearchStep:
         for p in self.params:
             p.grad = None
         self.a_opt.zero_grad(set_to_none=True)
-        self._backward(self.criterion(self.model(xv), yv))
+        if self.arch_grads_only:
+            from . import fused
+            loss = self.criterion(self.model(xv), yv)
+            fused.set_skip_wgrad(True)
+            try:
+                grads = torch.autograd.grad(loss, self.arch, allow_unused=True)
+            finally:
+                fused.set_skip_wgrad(False)
+            for p, g in zip(self.arch, grads):
+                p.grad = g if g is not None else torch.zeros_like(p)
+        else:
+            self._backward(self.criterion(self.model(xv), yv))
         if self.fopt is not None:
             self.fopt.pack_rest(self.fopt.arch, self.fopt.arch_grad_views)
             if self.world > 1:

@@ -231,7 +231,9 @@ class _ConvBnFn(torch.autograd.Function):
         _lib.check(lib, lib.senas_convbn_workspace(B, H, W, c_in, C.byref(sb), C.byref(scb)))
         scratch = fused.scratch_for(dev, scb.value, ('convbn', ctx.slot))
         gx = torch.empty_like(x, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
-        gw, gg, gb = torch.empty_like(weight), torch.empty_like(gamma), torch.empty_like(beta)
+        skip_w = fused._skip_wgrad[0]  # architecture step: data gradient only
+        gw = None if skip_w else torch.empty_like(weight)
+        gg, gb = torch.empty_like(gamma), torch.empty_like(beta)
         a = _lib.ConvBnArgs()
         a.batch, a.h, a.w, a.c_in, a.relu_in, a.training = B, H, W, c_in, ctx.relu_in, ctx.training
         a.x, a.x_ld = x.data_ptr(), c_in
@@ -240,10 +242,13 @@ class _ConvBnFn(torch.autograd.Function):
         a.saved, a.scratch = ctx.saved_buf.data_ptr(), scratch.data_ptr()
         a.grad_out, a.grad_out_ld = g.data_ptr(), 32
         a.grad_x = gx.data_ptr() if gx is not None else None
-        a.grad_weight, a.grad_gamma, a.grad_beta = gw.data_ptr(), gg.data_ptr(), gb.data_ptr()
+        a.grad_weight = gw.data_ptr() if gw is not None else None
+        a.grad_gamma, a.grad_beta = gg.data_ptr(), gb.data_ptr()
         a.stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib, lib.senas_convbn_backward(C.byref(a)))
+        if skip_w:
+            return gx, None, None, None, None, None
         return gx, gw, gg, gb, None, None
 
 
