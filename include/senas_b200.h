@@ -200,6 +200,15 @@ int senas_sgd_clip_step(float *param, float *grad, float *momentum, int64_t n, c
                         float max_norm, float *scratch, float *norm_out, void *stream);
 int senas_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *step, int64_t n,
                     const float *lr_dev, float beta1, float beta2, float eps, float wd, void *stream);
+/* SegmentationLosses('dice_ce') of the search configuration (utils/loss/loss.py:45-70,124-159): mean cross entropy *
+ * ce_scale + soft dice over the classes >= 1 (smooth 1e-5), forward (2 launches) and backward (1 launch).  logits / grad_logits:
+ * element offset n * sn + c * sc + pixel * sp (NCHW: sn = C HW, sc = HW, sp = 1; channels_last: sn = C HW, sc = 1, sp = C);
+ * target [B][HW] int64; loss: one float; coef: 3 C + 1 floats kept for backward; scratch: >= 296 * 25 floats;
+ * grad_loss: device scalar (the upstream gradient).  classes <= 8. */
+int senas_dice_ce_forward(const float *logits, const int64_t *target, int32_t B, int32_t C, int64_t HW, int64_t sn, int64_t sc,
+                          int64_t sp, float ce_scale, float smooth, float *loss, float *coef, float *scratch, void *stream);
+int senas_dice_ce_backward(const float *logits, const int64_t *target, int32_t B, int32_t C, int64_t HW, int64_t sn, int64_t sc,
+                           int64_t sp, const float *coef, const float *grad_loss, float *grad_logits, void *stream);
 int senas_mix_forward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, float *out, int64_t out_ld,
                       int32_t c0, int32_t C, int64_t npix, void *stream);
 int senas_mix_backward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, const float *g, int64_t g_ld,

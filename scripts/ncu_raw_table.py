@@ -29,6 +29,8 @@ def f(r, k):
 
 
 def mb(r, k):
+    if M[k] not in ix:
+        return float('nan')
     v = f(r, k)
     return v * {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1, 'Gbyte': 1e3}.get(units[ix[M[k]]], 1)
 
@@ -40,12 +42,12 @@ for r in data:
     a.append(r)
 tu = {'ns': 1e-3, 'us': 1, 'ms': 1e3}.get(units[ix[M['t']]], 1)
 print(f'{len(data)} kernels, {sum(f(r, "t") for r in data) * tu / 1e3:.2f} ms')
-print(f"{'kernel':38s} {'grid':>6s}  n    us/ea   sm%  dram% warps issue regs   l1%  lts%  fma%  lsu% tens%  MB/ea  GB/s | stalls/issue long short mio lg bar wait")
+print(f"{'kernel':38s} {'grid':>6s}  n    us/ea   sm%  dram% warps issue regs   l1%  lts%  fma%  lsu% tens%  MB/ea  TB/s | stalls/issue long short mio lg bar wait")
 for (name, grid), rs in sorted(agg.items(), key=lambda kv: -sum(f(r, 't') for r in kv[1]))[:top]:
     n = len(rs)
     av = lambda k: sum(f(r, k) for r in rs) / n
     t = av('t') * tu
     m = sum(mb(r, 'rd') + mb(r, 'wr') for r in rs) / n
     print(f"{name[:38]:38s} {grid:>6s} {n:2d} {t:8.1f} {av('sm'):5.1f} {av('dram'):5.1f} {av('warps'):5.1f} {av('issue'):5.1f} {av('regs'):4.0f} "
-          f"{av('l1'):5.1f} {av('lts'):5.1f} {av('fma'):5.1f} {av('lsu'):5.1f} {av('tensor'):5.1f} {m:7.1f} {m / t * 1e3 / 1e3:6.0f} | "
+          f"{av('l1'):5.1f} {av('lts'):5.1f} {av('fma'):5.1f} {av('lsu'):5.1f} {av('tensor'):5.1f} {m:7.1f} {m / t:6.2f} | "
           f"{av('long_sb'):5.2f} {av('short_sb'):5.2f} {av('mio'):5.2f} {av('lg'):5.2f} {av('bar'):5.2f} {av('wait'):5.2f}")

@@ -59,7 +59,7 @@ class ConvBnArgs(C.Structure):
 EXPORTS = ['senas_version', 'senas_last_error', 'senas_device_check', 'senas_graph_create', 'senas_graph_destroy',
            'senas_graph_plan', 'senas_graph_forward', 'senas_graph_backward', 'senas_avgpool_forward',
            'senas_avgpool_backward', 'senas_launch_count', 'senas_set_lanes', 'senas_set_slot', 'senas_set_defer', 'senas_flush', 'senas_set_ds_fused', 'senas_set_z_bfloat', 'senas_set_gather_mma', 'senas_comm_unique_id', 'senas_comm_init',
-           'senas_comm_allreduce', 'senas_comm_destroy', 'senas_sgd_clip_step', 'senas_adam_step', 'senas_mix_forward',
+           'senas_comm_allreduce', 'senas_comm_destroy', 'senas_sgd_clip_step', 'senas_adam_step', 'senas_dice_ce_forward', 'senas_dice_ce_backward', 'senas_mix_forward',
            'senas_mix_backward', 'senas_mix_dx', 'senas_convbn_workspace', 'senas_convbn_forward', 'senas_convbn_backward',
            'senas_profile',
            'senas_profile_dump']
@@ -93,6 +93,10 @@ def bind(path):
     lib.senas_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.senas_comm_destroy.argtypes = [C.c_void_p]
     lib.senas_flush.argtypes = [C.c_void_p]
+    lib.senas_dice_ce_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.senas_dice_ce_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.senas_convbn_workspace.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.senas_convbn_forward.argtypes = [C.POINTER(ConvBnArgs)]
     lib.senas_convbn_backward.argtypes = [C.POINTER(ConvBnArgs)]

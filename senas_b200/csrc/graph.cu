@@ -1923,6 +1923,36 @@ extern "C" int senas_adam_step(float *param, const float *grad, float *exp_avg, 
                eps, wd);
   return check_cuda("adam step");
 }
+extern "C" int senas_dice_ce_forward(const float *logits, const int64_t *target, int32_t B, int32_t C, int64_t HW, int64_t sn,
+                                     int64_t sc, int64_t sp, float ce_scale, float smooth, float *loss, float *coef,
+                                     float *scratch, void *stream) {
+  if (!logits || !target || !loss || !coef || !scratch || B < 1 || HW < 1 || C < 1 || C > kLossMaxC)
+    SENAS_FAIL("dice_ce forward: bad arguments (1 <= classes <= %d)", kLossMaxC);
+  LossArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = logits, a.target = target, a.sn = sn, a.sc = sc, a.sp = sp, a.HW = HW, a.B = B, a.C = C, a.partials = scratch;
+  const int blocks = (int)std::min<int64_t>(kLossBlocks, ((int64_t)B * HW + 255) / 256);
+  SENAS_TAG("loss_fwd", 0, (double)B * HW * (4.0 * C + 8.0));
+  SENAS_LAUNCH(loss_fwd_kernel, dim3(blocks), dim3(256), 0, stream, a);
+  SENAS_TAG("reduce", 0, 0);
+  SENAS_LAUNCH(loss_final_kernel, dim3(1), dim3(32), 0, stream, (const float *)scratch, blocks, C, (float)((double)B * HW), ce_scale,
+               smooth, loss, coef);
+  return check_cuda("dice_ce forward");
+}
+extern "C" int senas_dice_ce_backward(const float *logits, const int64_t *target, int32_t B, int32_t C, int64_t HW, int64_t sn,
+                                      int64_t sc, int64_t sp, const float *coef, const float *grad_loss, float *grad_logits,
+                                      void *stream) {
+  if (!logits || !target || !coef || !grad_loss || !grad_logits || B < 1 || HW < 1 || C < 1 || C > kLossMaxC)
+    SENAS_FAIL("dice_ce backward: bad arguments");
+  LossArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = logits, a.target = target, a.sn = sn, a.sc = sc, a.sp = sp, a.HW = HW, a.B = B, a.C = C;
+  a.coef = coef, a.gout = grad_loss, a.dlogits = grad_logits;
+  const int blocks = (int)std::min<int64_t>(4 * kLossBlocks, ((int64_t)B * HW + 255) / 256);
+  SENAS_TAG("loss_bwd", 0, (double)B * HW * (8.0 * C + 8.0));
+  SENAS_LAUNCH(loss_bwd_kernel, dim3(blocks), dim3(256), 0, stream, a);
+  return check_cuda("dice_ce backward");
+}
 extern "C" int senas_mix_forward(const float *a, int64_t a_ld, const float *b, int64_t b_ld, const float *w, float *out,
                                  int64_t out_ld, int32_t c0, int32_t C, int64_t npix, void *stream) {
   if (!a || !out || (b && !w) || C < 4 || (C & 3) || (c0 & 3) || (a_ld & 3) || (b_ld & 3) || (out_ld & 3) || npix < 1)

@@ -188,3 +188,114 @@ __global__ void __launch_bounds__(256) mix_dx_kernel(MixDxArgs q) {
   }
   st4(q.out + pix * q.C + c, v);
 }
+
+// ---- f4: dice + cross-entropy segmentation loss (SegmentationLosses('dice_ce'), utils/loss/loss.py:45-70,124-159) -------
+//   loss = mean_pixels CE(logits, target) * ce_scale + 1 - mean_{c >= 1} (2 tp_c + s) / (2 tp_c + fp_c + fn_c + s + 1e-8)
+//   tp_c = sum p_c [t = c],  fp_c = sum p_c [t != c],  fn_c = sum (1 - p_c) [t = c],  p = softmax(logits) over the classes
+// forward: one sweep (softmax, CE term and the 3C soft counts per block, fixed-order reduction) + a one-block finalize
+// that also leaves the coefficients backward needs; backward: one sweep that recomputes the softmax.  ~15 elementwise /
+// reduction launches of the PyTorch expression -> 3.  logits: element offset = n * sn + c * sc + pixel * sp.
+constexpr int kLossMaxC = 8, kLossBlocks = 296;
+struct LossArgs {
+  const float *logits;
+  const int64_t *target;  // [B][HW]
+  int64_t sn, sc, sp, HW;
+  int32_t B, C;
+  float *partials;        // forward: [kLossBlocks][3C + 1]
+  const float *coef;      // backward: [3C + 1] = ktp[C], kfp[C], kfn[C], ce weight
+  const float *gout;      // backward: upstream gradient (device scalar)
+  float *dlogits;         // backward: same strides as logits
+};
+SENAS_DEVFN float loss_softmax(const LossArgs &a, int64_t i, float *p, int *t) {  // returns -log p[t] (log-sum-exp form)
+  const int64_t n = i / a.HW, px = i - n * a.HW;
+  const float *l = a.logits + n * a.sn + px * a.sp;
+  float m = -3.4e38f;
+#pragma unroll
+  for (int c = 0; c < kLossMaxC; ++c)
+    if (c < a.C) p[c] = l[c * a.sc], m = fmaxf(m, p[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kLossMaxC; ++c)
+    if (c < a.C) p[c] = expf(p[c] - m), s += p[c];
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < kLossMaxC; ++c)
+    if (c < a.C) p[c] *= inv;
+  *t = (int)a.target[i];
+  return (m + logf(s)) - l[(int64_t)(*t) * a.sc];
+}
+__global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a) {
+  __shared__ float s_w[8][3 * kLossMaxC + 1];
+  float acc[3 * kLossMaxC + 1];
+#pragma unroll
+  for (int j = 0; j < 3 * kLossMaxC + 1; ++j) acc[j] = 0.f;
+  const int64_t total = (int64_t)a.B * a.HW;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    float p[kLossMaxC];
+    int t;
+    acc[3 * kLossMaxC] += loss_softmax(a, i, p, &t);
+#pragma unroll
+    for (int c = 0; c < kLossMaxC; ++c)
+      if (c < a.C) {
+        const bool hit = t == c;
+        acc[c] += hit ? p[c] : 0.f, acc[kLossMaxC + c] += hit ? 0.f : p[c], acc[2 * kLossMaxC + c] += hit ? 1.f - p[c] : 0.f;
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 3 * kLossMaxC + 1; ++j) {
+    const float v = warp_sum(acc[j]);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * kLossMaxC + 1) {
+    float r = 0.f;
+    for (int w = 0; w < 8; ++w) r += s_w[w][threadIdx.x];
+    a.partials[(int64_t)blockIdx.x * (3 * kLossMaxC + 1) + threadIdx.x] = r;
+  }
+}
+// out[0] = loss; coef[0:C) = ktp, [C:2C) = kfp, [2C:3C) = kfn (d loss / d tp_c ...), coef[3C] = CE weight per pixel
+__global__ void __launch_bounds__(32) loss_final_kernel(const float *partials, int nblk, int C, float npix, float ce_scale,
+                                                        float smooth, float *out, float *coef) {
+  __shared__ float s[3 * kLossMaxC + 1];
+  if (threadIdx.x < 3 * kLossMaxC + 1) {
+    float r = 0.f;
+    for (int b = 0; b < nblk; ++b) r += partials[(int64_t)b * (3 * kLossMaxC + 1) + threadIdx.x];
+    s[threadIdx.x] = r;
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    float dsum = 0.f;
+    const float k = C > 1 ? 1.f / (float)(C - 1) : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float tp = s[c], fp = s[kLossMaxC + c], fn = s[2 * kLossMaxC + c];
+      const float N = 2.f * tp + smooth, D = 2.f * tp + fp + fn + smooth + 1e-8f;
+      if (c >= 1) dsum += N / D;
+      coef[c] = c >= 1 ? -k * 2.f * (D - N) / (D * D) : 0.f;
+      coef[C + c] = c >= 1 ? k * N / (D * D) : 0.f;
+      coef[2 * C + c] = c >= 1 ? k * N / (D * D) : 0.f;
+    }
+    coef[3 * C] = ce_scale / npix;
+    out[0] = s[3 * kLossMaxC] * ce_scale / npix + 1.f - k * dsum;
+  }
+}
+__global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a) {
+  const int64_t total = (int64_t)a.B * a.HW;
+  const float go = a.gout[0], cew = a.coef[3 * a.C];
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    float p[kLossMaxC], gp[kLossMaxC];
+    int t;
+    loss_softmax(a, i, p, &t);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLossMaxC; ++c)
+      if (c < a.C) {
+        gp[c] = t == c ? a.coef[c] - a.coef[2 * a.C + c] : a.coef[a.C + c];  // d loss / d p_c (fn = sum (1 - p) [t = c])
+        dot += gp[c] * p[c];
+      }
+    const int64_t n = i / a.HW, px = i - n * a.HW;
+    float *d = a.dlogits + n * a.sn + px * a.sp;
+#pragma unroll
+    for (int c = 0; c < kLossMaxC; ++c)
+      if (c < a.C) d[c * a.sc] = go * (p[c] * (gp[c] - dot) + cew * (p[c] - (t == c ? 1.f : 0.f)));
+  }
+}

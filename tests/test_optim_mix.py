@@ -411,3 +411,39 @@ def test_arch_grads_only_step_equals_full_backward_step():
                 ulp = 2 * 1.1920929e-07 * v.abs().max().item()
                 worst = max(worst, max((upd1 - upd0).abs().max().item() - ulp, 0.0) / s)
     assert worst <= 5e-3, worst
+
+
+# ------------------------------------------------------------------------------------------------- row f4: the loss
+def _loss_case(lib, dev, B, C, H, W, channels_last):
+    """senas_dice_ce_forward/backward (through the autograd wrapper) against the PyTorch expression of senas_b200.loss
+    (itself checked against the reference's SegmentationLosses('dice_ce') in tests/test_oracle_golden.py)."""
+    from senas_b200 import loss as L
+    torch.manual_seed(B * 100 + C)
+    logits = (torch.randn(B, C, H, W) * 3).to(dev)
+    if channels_last:
+        logits = logits.contiguous(memory_format=torch.channels_last)
+    target = torch.randint(0, C, (B, H, W)).to(dev)
+    a = logits.clone().requires_grad_(True)
+    L.fused_loss[0] = False
+    try:
+        want = L.DiceCrossEntropyLoss()(a, target)
+    finally:
+        L.fused_loss[0] = True
+    (want * 1.7).backward()
+    b = logits.clone().requires_grad_(True)
+    got = L._DiceCEFn.apply(b, target, 1e-5, lib)
+    (got * 1.7).backward()
+    assert abs(got.item() - want.item()) <= 2e-6 * abs(want.item()), (got.item(), want.item())
+    assert torch.allclose(b.grad, a.grad, rtol=1e-4, atol=1e-6 * a.grad.abs().max().item()), (b.grad - a.grad).abs().max().item()
+
+
+@pytest.mark.parametrize('B,C,H,W,cl', [(2, 2, 16, 16, True), (1, 2, 5, 7, False), (3, 5, 9, 4, True), (2, 8, 3, 3, False)])
+def test_dice_ce_loss_emulated(emu, B, C, H, W, cl):
+    _loss_case(emu, 'cpu', B, C, H, W, cl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,C,H,W,cl', [(16, 2, 256, 256, True), (4, 2, 64, 64, False), (2, 5, 33, 17, True)])
+def test_dice_ce_loss_gpu(B, C, H, W, cl):
+    from senas_b200 import _lib
+    _loss_case(_lib.get(), 'cuda', B, C, H, W, cl)
