@@ -772,6 +772,10 @@ static void launch_gather(GatherArgs &a, const Geo &g, int B, void *stream, bool
 // bound by its serial stage -> sync -> MMA -> store structure, not by the FMA pipe), and the extra TF32 rounding on the node
 // edges flipped a near-tie of the fixed-seed genotype gate.  Opt in with SENAS_GATHER_MMA=1 / senas_set_gather_mma(1).
 static int g_gather_mma = env_flag("SENAS_GATHER_MMA", 0);
+// bf16 mode: weight gradient of the 8 -> 8 node edges as mma.sync TF32 (conv_wgrad_mma8_kernel) instead of the fp32
+// CUDA-core kernel.  A parameter gradient (a sum over all pixels): the TF32 rounding of its operands averages out and no
+// forward value or ReLU decision depends on it.
+static int g_wgrad_mma = env_flag("SENAS_WGRAD_MMA", 1);
 static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream, bool mma = false) {
   const int nph = g.taps.nphase, pix = gather_pix(NC, g.si, a.base_w);
   mma = mma && g_gather_mma;
@@ -1378,6 +1382,17 @@ static int backward_edge(BwdCall &c, int e) {
     SENAS_LAUNCH(kern, dim3(nblk), dim3(TL::THREADS), smem, st, a);                                          \
   }
           const int si_ = geo.si, so_ = geo.so;
+          if (C == 8 && t.k == 5 && si_ == 1 && so_ == 1 && geo.taps.n == kWmTaps && (c.d->reserved & 1) && g_wgrad_mma) {
+            // bf16 mode: the 8 -> 8 node edges' weight gradient on the tensor cores (mma.sync TF32, pixels = GEMM-K)
+            a.tiles_x = cdiv(a.base_w, kWmTW), a.tiles_y = cdiv(a.base_h, kWmTH);
+            nblk = std::min(a.tiles_x * a.tiles_y * B, kPersistBlocks);
+            const int XR = kWmTH + geo.taps.max_dy - geo.taps.min_dy, XC = kWmTW + geo.taps.max_dx - geo.taps.min_dx;
+            const size_t smem = (size_t)(XR * XC * 8 + kWmTH * kWmTW * 8 + 4 * kWmTaps * 64) * sizeof(float);
+            auto kern = conv_wgrad_mma8_kernel;
+            allow_smem(kern, smem);
+            SENAS_TAG("conv_wgrad.n8", 2.0 * B * a.base_h * a.base_w * T * 8 * 8, 4.0 * B * (ep.in_h * ep.in_w * 8 + HW * 16));
+            SENAS_LAUNCH(kern, dim3(nblk), dim3(kWmThreads), smem, st, a);
+          } else
           if (C == 32 && t.k == 5 && si_ == 1 && so_ == 1) SENAS_WGRAD2(32, 5, 1, 1)
           else if (C == 32 && t.k == 5 && si_ == 2 && so_ == 1) SENAS_WGRAD2(32, 5, 2, 1)
           else if (C == 32 && t.k == 5 && si_ == 1 && so_ == 2) SENAS_WGRAD2(32, 5, 1, 2)

@@ -2039,6 +2039,104 @@ __global__ void __launch_bounds__(32 * K) conv_wgrad2_kernel(WgradArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the 8 -> 8 node-edge convolutions (dil_2 / dil_3_conv_5, stride 1) on the tensor cores: warp-level
+// mma.sync m16n8k8 TF32 with the PIXELS as GEMM-K (bf16 mode; conv_wgrad2_kernel<8, 5, 1, 1> is the exact fp32 version and
+// is bound by its shared-memory reads: ncu, round 2, L1 83 % / FMA 29 %).  Two taps share one MMA:
+//   A (16 x 8, row = (tap pair member, ci), k = pixel)   a0 = x[q0][px t][ci g]   a1 = x[q1][px t][ci g]
+//                                                        a2 = x[q0][px t + 4][g]  a3 = x[q1][px t + 4][g]
+//   B ( 8 x 8, k = pixel, n = co)                        b0 = dy[px t][co g]      b1 = dy[px t + 4][co g]
+//   D (16 x 8)   d0, d1 = dW[q0][ci g][co 2t, 2t + 1]    d2, d3 = dW[q1][ci g][co 2t, 2t + 1]
+// (g = lane >> 2, t = lane & 3), i.e. 13 MMAs + 54 conflict-free LDS per 8 pixels for all 25 taps, against 25 x 8 x 8
+// FMAs + 27 LDS per pixel.  Same tile (8 x 16 output pixels, x tile with halo and dy = A gm + B y + C staged once), same
+// persistent grid and the same partial layout [block][tap][ci][co] as conv_wgrad2_kernel, so wgrad_reduce_kernel follows
+// unchanged.  Operands are rounded to TF32 when staged (2e-2 gate of the mode).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWmTH = 8, kWmTW = 16, kWmThreads = 128, kWmTaps = 25;
+__global__ void __launch_bounds__(kWmThreads) conv_wgrad_mma8_kernel(WgradArgs a) {
+  SENAS_DYN_SMEM(float, smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int span_y = a.taps.max_dy - a.taps.min_dy, span_x = a.taps.max_dx - a.taps.min_dx;
+  const int XR = kWmTH + span_y, XC = kWmTW + span_x;
+  float *s_x = smem;                             // [XR][XC][8]
+  float *s_dy = s_x + XR * XC * 8;               // [TH * TW][8]
+  float *s_red = s_dy + kWmTH * kWmTW * 8;       // [4 warps][25 * 64]
+  int off[kWmTaps + 1];
+#pragma unroll
+  for (int q = 0; q < kWmTaps + 1; ++q)
+    off[q] = q < a.taps.n ? ((a.taps.dy[q] - a.taps.min_dy) * XC + (a.taps.dx[q] - a.taps.min_dx)) * 8 : 0;
+  float acc[(kWmTaps + 1) / 2][4];
+#pragma unroll
+  for (int p = 0; p < (kWmTaps + 1) / 2; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+  const int tiles = a.tiles_x * a.tiles_y, total = tiles * a.batch;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int n = item / tiles, tile = item - n * tiles;
+    const int by0 = (tile / a.tiles_x) * kWmTH, bx0 = (tile % a.tiles_x) * kWmTW;
+    const float *gmn = a.gm + (int64_t)n * a.o_h * a.o_w * 8;
+    const float *yn = a.y + (int64_t)n * a.o_h * a.o_w * a.y_ld;
+    const float *xn = a.x + (int64_t)n * a.x_h * a.x_w * a.x_ld;
+    __syncthreads();
+    const int gy0 = by0 + a.taps.min_dy, gx0 = bx0 + a.taps.min_dx;
+    for (int i = tid; i < XR * XC * 2; i += kWmThreads) {
+      const int q = i & 1, pxl = i >> 1;
+      const int r = pxl / XC, c = pxl - r * XC;
+      const int gy = gy0 + r, gx = gx0 + c;
+      float4 v = f4zero();
+      if (gy >= 0 && gy < a.x_h && gx >= 0 && gx < a.x_w) v = ld4(xn + ((int64_t)gy * a.x_w + gx) * a.x_ld + q * 4);
+      st4(s_x + (int64_t)pxl * 8 + q * 4, make_float4(senas_tf32(v.x), senas_tf32(v.y), senas_tf32(v.z), senas_tf32(v.w)));
+    }
+    for (int i = tid; i < kWmTH * kWmTW * 2; i += kWmThreads) {
+      const int q = i & 1, pxl = i >> 1;
+      const int r = pxl / kWmTW, c = pxl - r * kWmTW;
+      const int oy = by0 + r, ox = bx0 + c;
+      float4 v = f4zero();
+      if (oy < a.o_h && ox < a.o_w) {
+        const int64_t pix = (int64_t)oy * a.o_w + ox;
+        const float4 gv = ld4(gmn + pix * 8 + q * 4), yv = ld4(yn + pix * a.y_ld + q * 4);
+        const float *A = a.coefA + n * 8 + q * 4, *B = a.coefB + n * 8 + q * 4, *C = a.coefC + n * 8 + q * 4;
+        v.x = A[0] * gv.x + B[0] * yv.x + C[0], v.y = A[1] * gv.y + B[1] * yv.y + C[1];
+        v.z = A[2] * gv.z + B[2] * yv.z + C[2], v.w = A[3] * gv.w + B[3] * yv.w + C[3];
+      }
+      st4(s_dy + (int64_t)pxl * 8 + q * 4, make_float4(senas_tf32(v.x), senas_tf32(v.y), senas_tf32(v.z), senas_tf32(v.w)));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = 2 * warp + rr;
+#pragma unroll
+      for (int ks = 0; ks < kWmTW / 8; ++ks) {
+        const float *dyp = s_dy + (row * kWmTW + ks * 8) * 8 + g;
+        const float bf[2] = {dyp[t * 8], dyp[(t + 4) * 8]};
+        const float *xb = s_x + (row * XC + ks * 8) * 8 + g;
+#pragma unroll
+        for (int p = 0; p < (kWmTaps + 1) / 2; ++p) {
+          const int q0 = 2 * p, q1 = 2 * p + 1;
+          float af[4];
+          af[0] = xb[off[q0] + t * 8], af[2] = xb[off[q0] + (t + 4) * 8];
+          if (q1 < kWmTaps) af[1] = xb[off[q1] + t * 8], af[3] = xb[off[q1] + (t + 4) * 8];
+          else af[1] = af[3] = 0.f;
+          senas_mma_tf32(acc[p], af, bf);
+        }
+      }
+    }
+  }
+  __syncthreads();  // (tiles done: the staging area is not read any more; s_red is its own region)
+#pragma unroll
+  for (int p = 0; p < (kWmTaps + 1) / 2; ++p) {
+    const int q0 = 2 * p, q1 = 2 * p + 1;
+    float *r0 = s_red + warp * (kWmTaps * 64) + (q0 * 8 + g) * 8 + 2 * t;
+    r0[0] = acc[p][0], r0[1] = acc[p][1];
+    if (q1 < kWmTaps) {
+      float *r1 = s_red + warp * (kWmTaps * 64) + (q1 * 8 + g) * 8 + 2 * t;
+      r1[0] = acc[p][2], r1[1] = acc[p][3];
+    }
+  }
+  __syncthreads();
+  float *out = a.partials + (int64_t)blockIdx.x * kWmTaps * 64;
+  for (int o = tid; o < kWmTaps * 64; o += kWmThreads)
+    out[o] = (s_red[o] + s_red[kWmTaps * 64 + o]) + (s_red[2 * kWmTaps * 64 + o] + s_red[3 * kWmTaps * 64 + o]);
+}
+
 // depthwise convolution with a sliding register window (stride-1 output grids: NORM / DOWN forward, NORM data
 // gradient).  thread = (channel, strip): the K x K input window of the thread's channel slides along x in registers,
 // K*SI global loads + 1 store per output instead of K*K loads (the first version was L1-bandwidth bound).

@@ -379,3 +379,20 @@ def test_gather_mma_indexing_emulated(emu, name):
         fused._flags['override'] = None
         emu.senas_set_gather_mma(0)
     assert emu.senas_launch_count() > n0
+
+
+@pytest.mark.parametrize('name', ['mixed_norm8', 'cell_up', 'cell_down'])
+def test_wgrad_mma_indexing_emulated(emu, name):
+    """bf16 mode (default on): the weight gradient of the 8 -> 8 node-edge convolutions through conv_wgrad_mma8_kernel
+    (mma.sync m16n8k8 TF32, pixels = GEMM-K, two taps per MMA).  The emulator evaluates the MMA from the fragment layouts in
+    exact arithmetic, so the golden fixtures hold at the fp32 gate: tap pairing, tile / halo indexing, the cross-warp fold
+    and the partial layout that wgrad_reduce_kernel consumes."""
+    from senas_b200 import fused
+    fused._flags['override'] = 1
+    try:
+        if name.startswith('mixed_'):
+            test_mixed_op_emulated(emu, name)
+        else:
+            test_cell_nodes_emulated(emu, name, name.split('_')[1])
+    finally:
+        fused._flags['override'] = None
