@@ -195,6 +195,8 @@ static int gather_pix(int NC, int si, int base_w);
 // (scripts/ubench/dwbench.cu) -- default 3.
 enum { DWL_WGRAD = 0, DWL_FWD = 2, DWL_DX = 4 };
 static int g_dw_lane = env_flag("SENAS_DW_LANE", 3);
+// (round 2: a variant of dw_multi_kernel that prefetches the next input row while the current one is consumed -- 150 registers,
+// 3 blocks per SM -- measured SLOWER in the step: dw_fwd 8.7 -> 9.6 ms, dw_dx 9.6 -> 11.1 ms, 88.1 -> 89.8 ms; removed.)
 static int dwl_tile_w(int C) { return C == 32 ? DwLane<32>::TILE_W : DwLane<8>::TILE_W; }
 static bool dw_lane_ok(int C, int w, int what) {
   return ((g_dw_lane >> what) & (C == 32 ? 1 : 2)) && 2 * w >= dwl_tile_w(C);
@@ -776,9 +778,14 @@ static int g_gather_mma = env_flag("SENAS_GATHER_MMA", 0);
 // CUDA-core kernel.  A parameter gradient (a sum over all pixels): the TF32 rounding of its operands averages out and no
 // forward value or ReLU decision depends on it.
 static int g_wgrad_mma = env_flag("SENAS_WGRAD_MMA", 1);
+// bf16 mode: data gradients of the non-tcgen05 convs through gather_mma_kernel.  Measured (r2k): the dgrad families drop
+// from 12.0 to 9.9 ms of kernel time per step, the step does not move (88.1 vs 87.5 ms, inside the run-to-run noise) -- OFF.
+static int g_dgrad_mma = env_flag("SENAS_DGRAD_MMA", 0);
 static int launch_gather_any(GatherArgs &a, const Geo &g, int KC, int NC, int B, void *stream, bool mma = false) {
   const int nph = g.taps.nphase, pix = gather_pix(NC, g.si, a.base_w);
-  mma = mma && g_gather_mma;
+  // forward (a.partials != nullptr: statistics epilogue) only with the opt-in; data gradients (no forward value, no ReLU
+  // decision depends on them: the TF32 rounding stays inside the 2e-2 gate of the mode) also with SENAS_DGRAD_MMA
+  mma = mma && (g_gather_mma || (g_dgrad_mma && a.partials == nullptr));
 #define SENAS_GATHER(KC_, NC_, NPH_)                                                       \
   if (KC == KC_ && NC == NC_ && nph == NPH_) {                                             \
     if (pix == 4 && NC_ == 8) launch_gather<KC_, NC_, NPH_, (NC_ == 8 ? 4 : 2)>(a, g, B, stream, mma); \
