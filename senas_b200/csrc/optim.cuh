@@ -221,8 +221,13 @@ SENAS_DEVFN float loss_softmax(const LossArgs &a, int64_t i, float *p, int *t) {
 #pragma unroll
   for (int c = 0; c < kLossMaxC; ++c)
     if (c < a.C) p[c] *= inv;
-  *t = (int)a.target[i];
-  return (m + logf(s)) - l[(int64_t)(*t) * a.sc];
+  const int64_t tv = a.target[i];
+  if (tv < 0 || tv >= a.C) {  // not a class id: the pixel matches no class (no out-of-bounds read; PyTorch would assert)
+    *t = -1;
+    return 0.f;
+  }
+  *t = (int)tv;
+  return (m + logf(s)) - l[tv * a.sc];
 }
 __global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a) {
   __shared__ float s_w[8][3 * kLossMaxC + 1];

@@ -18,6 +18,10 @@ no packing copy, and in data-parallel runs the slice is all-reduced in place whi
 rates live in device scalars: a scheduler (CosineAnnealingLR, search_arc.py:296) takes effect on the next replay of the
 captured step without re-capturing it.  The torch optimizers stay the owners of the hyper-parameters and their
 ``state_dict()`` keeps working: their per-parameter state entries are views of the arenas (``publish_state``).
+
+Lifetime: the arenas belong to this object and the parameters alias them -- build it after the model is on its device
+and do not move the model (``.to()`` / ``.cuda()``) afterwards (a moved Cell drops its fused graph and with it the
+``grad_buffer`` binding; ``check_direct`` reports that, GraphedSearchStep raises during its warm-up).
 """
 import ctypes as C
 
