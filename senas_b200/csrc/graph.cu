@@ -1496,6 +1496,9 @@ static int backward_edge(BwdCall &c, int e) {
         sums1 = tmp + (int64_t)B * nblk_cc * 10 * C, coef1 = sums1 + 12 * C;
         a.bn1_coef = coef1;
         SENAS_TAG("pw_bwd_stats", 4.0 * B * HW * C * 8, 4.0 * B * HW * (C + 16));
+        // (round 2: a version with du = dy.W and dW += dy^T.a as mma.sync TF32 -- 16 pixels per warp step, z read in the D and
+        // the B fragment layout -- was correct (emulator + GPU suite) and SLOWER: 11.9 vs 10.6 ms per step; it trades FMAs for
+        // twice as many narrow load instructions and the sweep is bound by those.  Removed.)
         if (C == 32) {  // (2 / 3 / 4 pixel steps in flight measured the same under the 128-register cap: 2)
           auto kern = pw_bwd_q_kernel<32, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);

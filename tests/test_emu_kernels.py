@@ -395,3 +395,13 @@ def test_wgrad_mma_indexing_emulated(emu, name):
             test_cell_nodes_emulated(emu, name, name.split('_')[1])
     finally:
         fused._flags['override'] = None
+
+
+def test_mma_backward_kernels_ragged_emulated(emu):
+    """The MMA weight-gradient kernel on a ragged up cell (3 x 10 x 18: partial tiles) against the oracle."""
+    from senas_b200 import fused
+    fused._flags['override'] = 1
+    try:
+        test_cell_ragged_emulated(emu, 'up', 3, 10, 18)
+    finally:
+        fused._flags['override'] = None
