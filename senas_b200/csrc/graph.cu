@@ -1462,13 +1462,10 @@ static int backward_edge(BwdCall &c, int e) {
           for (int q = 0; q < nk; ++q) {
             const int k2 = ks[q];
             float *base = tmp + q * per, *sums = base + (int64_t)B * nb * 10 * C;
-            SENAS_TAG("reduce", 0, 0);
-            SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)base, sums,
-                         nb * B, 10 * C);
-            SENAS_TAG("pw_bfin", 0, 0);
-            SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums, C, (float)B * (float)HW,
-                         da.it[q].g1, da.it[q].istd1, sums + 12 * C, gp + ed.grad_off[k2][1], gp + ed.grad_off[k2][2],
-                         gp + ed.grad_off[k2][6]);
+            SENAS_TAG("reduce", 0, 0);  // fold + BN1-backward finalize in one launch
+            SENAS_LAUNCH(pw_reduce_fin_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st,
+                         (const float *)base, nb * B, C, (float)B * (float)HW, da.it[q].g1, da.it[q].istd1, sums + 12 * C,
+                         gp + ed.grad_off[k2][1], gp + ed.grad_off[k2][2], gp + ed.grad_off[k2][6]);
           }
           SENAS_TAG("ds_bwd_dz", 2.0 * px * (taps * C + 16.0 * C * nk), 4.0 * px * (C + 16.0 * nk + (double)C * nk));
           if (C == 32) {
@@ -1506,12 +1503,10 @@ static int backward_edge(BwdCall &c, int e) {
           auto kern = pw_bwd_q_kernel<8, 1>;
           SENAS_LAUNCH(kern, grid_cc, dim3(256), 0, st, a, px_pb, c.a->training);
         }
-        SENAS_TAG("reduce", 0, 0);
-        SENAS_LAUNCH(rows_reduce_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st, (const float *)tmp, sums1,
-                     (int)(nblk_cc * B), 10 * C);
-        SENAS_TAG("pw_bfin", 0, 0);
-        SENAS_LAUNCH(pw_bfin_kernel, dim3(1), dim3(128), 0, st, (const float *)sums1, C, (float)B * (float)HW, a.g1,
-                     a.istd1, coef1, gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
+        SENAS_TAG("reduce", 0, 0);  // fold + BN1-backward finalize in one launch
+        SENAS_LAUNCH(pw_reduce_fin_kernel, dim3(cdiv(10 * C, kRowsReduceCols), 1), dim3(kRowsReduceThreads), 0, st,
+                     (const float *)tmp, (int)(nblk_cc * B), C, (float)B * (float)HW, a.g1, a.istd1, coef1,
+                     gp + ed.grad_off[k][1], gp + ed.grad_off[k][2], gp + ed.grad_off[k][6]);
         SENAS_TAG("pw_bwd_dz", 2.0 * B * HW * C * 8, 4.0 * B * HW * (2 * C + 16));
         if (C == 32) {
           auto kern = pw_bwd_q_kernel<32, 2>;

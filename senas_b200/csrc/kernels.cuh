@@ -611,7 +611,8 @@ SENAS_DEVFN float block_rows_sum(const float *src, int rows, int V, int col) {
 // (ncu, round 2: 15 us at 2048 rows x 320 columns, long-scoreboard stalls 50 per issue -- pure load latency).
 // Fixed order: lane r sums rows r, r+128, ... in four interleaved chains; lanes combined 16 at a time, then 8.
 constexpr int kRowsReduceCols = 8, kRowsReduceLanes = 128, kRowsReduceThreads = kRowsReduceCols * kRowsReduceLanes;
-__global__ void __launch_bounds__(kRowsReduceThreads) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
+// column sums of one block: valid in threads < kRowsReduceCols (column blockIdx.x * 8 + threadIdx.x)
+SENAS_DEVFN float rows_reduce_block(const float *src, int rows, int V) {
   __shared__ float s_rr[kRowsReduceLanes][kRowsReduceCols + 1];
   __shared__ float s_r2[8][kRowsReduceCols + 1];
   constexpr int L = kRowsReduceLanes;
@@ -634,10 +635,34 @@ __global__ void __launch_bounds__(kRowsReduceThreads) rows_reduce_kernel(const f
     s_r2[g][c] = t;
   }
   __syncthreads();
-  if (threadIdx.x < kRowsReduceCols && col < V) {
-    float t = 0.f;
+  float t = 0.f;
+  if (threadIdx.x < kRowsReduceCols)
     for (int g = 0; g < 8; ++g) t += s_r2[g][threadIdx.x];
-    dst[(int64_t)blockIdx.y * V + col] = t;
+  return t;
+}
+__global__ void __launch_bounds__(kRowsReduceThreads) rows_reduce_kernel(const float *src, float *dst, int rows, int V) {
+  const float t = rows_reduce_block(src, rows, V);
+  const int col = blockIdx.x * kRowsReduceCols + threadIdx.x;
+  if (threadIdx.x < kRowsReduceCols && col < V) dst[(int64_t)blockIdx.y * V + col] = t;
+}
+// The pass-1 fold of the dep-sep pointwise backward WITH its finalize (every output of pw_bfin_kernel depends on its own
+// column sum only): sums [10C] = (sum du | sum du zhat | dW_pw) -> d beta1, d gamma1, dW_pw and the BN1-backward coefficients
+// [3][C] in one launch; 540 launches per search step fewer on the candidates' backward chains (round 2).  grid = (ceil(10C / 8), 1)
+__global__ void __launch_bounds__(kRowsReduceThreads) pw_reduce_fin_kernel(const float *src, int rows, int C, float M, const float *g1,
+                                                                           const float *istd1, float *coef /*[3][C]*/, float *g_gamma1,
+                                                                           float *g_beta1, float *g_wpw) {
+  const float s = rows_reduce_block(src, rows, 10 * C);
+  const int i = blockIdx.x * kRowsReduceCols + threadIdx.x;
+  if (threadIdx.x >= kRowsReduceCols || i >= 10 * C) return;
+  if (i < C) {
+    g_beta1[i] = s;
+    coef[C + i] = s / M;
+    coef[i] = g1[i] * istd1[i];
+  } else if (i < 2 * C) {
+    g_gamma1[i - C] = s;
+    coef[2 * C + i - C] = s / M;
+  } else {
+    g_wpw[i - 2 * C] = s;
   }
 }
 
@@ -1555,24 +1580,7 @@ __global__ void __launch_bounds__(128) pw_bwd_stats_kernel(PwBwdArgs a) {
   if (tid < C) out[tid] = sacc0, out[C + tid] = sacc1;
 }
 
-// BN1 backward finalize (one block) on the already reduced pass-1 sums [10C]: d gamma1 / d beta1 / dW_pw, coefficients
-__global__ void __launch_bounds__(128) pw_bfin_kernel(const float *sums, int C, float M, const float *g1, const float *istd1,
-                                                      float *coef /*[3][C]*/, float *g_gamma1, float *g_beta1, float *g_wpw) {
-  const int V = 10 * C;
-  for (int i = threadIdx.x; i < V; i += 128) {
-    const float s = sums[i];
-    if (i < C) {
-      g_beta1[i] = s;
-      coef[C + i] = s / M;
-      coef[i] = g1[i] * istd1[i];
-    } else if (i < 2 * C) {
-      g_gamma1[i - C] = s;
-      coef[2 * C + i - C] = s / M;
-    } else {
-      g_wpw[i - 2 * C] = s;
-    }
-  }
-}
+// (BN1 backward finalize: fused into the fold, pw_reduce_fin_kernel)
 
 // pass 2: dz = a1 * (du - dbeta1/M - zhat * dgamma1/M), in place over z
 template <int C>

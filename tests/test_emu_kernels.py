@@ -360,7 +360,7 @@ def test_fused_depsep_recompute_emulated(emu, name):
         emu.senas_set_ds_fused(0)
 
 
-@pytest.mark.parametrize('name', ['mixed_norm8', 'mixed_down32', 'mixed_down32_odd', 'mixed_up32', 'cell_up'])
+@pytest.mark.parametrize('name', ['mixed_norm8', 'mixed_down32', 'mixed_down32_odd', 'mixed_up32'])
 def test_gather_mma_indexing_emulated(emu, name):
     """Opt-in (senas_set_gather_mma): bf16 mode routes every convolution that is not on the tcgen05 path through
     gather_mma_kernel (mma.sync m16n8k8 TF32).  The emulator evaluates the MMA from the documented fragment layouts in exact arithmetic (no TF32 rounding),
