@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+cd $GRAFT_REPO_ROOT
+O=gpurun_out
+python -m pytest tests -m gpu -q > $O/r2o_tests_all.log 2>&1; echo "all_rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r2o_smoke.log 2>&1; echo "smoke_rc=$?"
+timeout 900 python bench.py > $O/r2o_bench_default.json 2> $O/r2o_bench_default.err; echo "bench_rc=$?"
+echo done

@@ -69,6 +69,7 @@ class SenasSearch(nn.Module):
     # the small latency-bound cells hide under the large one in the captured graph.  Same operations on the same data:
     # results do not depend on the setting.
     concurrent_cells = False
+    down_side_streams = os.environ.get('SENAS_DOWN_STREAMS', '1') != '0'  # (only with concurrent_cells)
     fused_mix = os.environ.get('SENAS_NO_MIX', '0') != '1'  # gamma mix + concat through libsenas_b200 (row f3); False: torch.lerp / torch.cat
     gamma_rows_sum_to_one = False  # set by NAS (which softmaxes gamma); a direct caller may pass any gamma
 
@@ -89,10 +90,27 @@ class SenasSearch(nn.Module):
         # j = depth-2 .. 0 outside and i inside while overwriting cell_out[i + j]; cell (i, j) reads cell_out[j .. i+j-1]
         # = out[0..i-1][j] and cell_out[i + j] = out[i-1][j+1], which the level-by-level walk below provides unchanged.
         out = [[self.stem1(s0)]]
+        side = self.concurrent_cells and x.is_cuda
         for j in range(1, depth):
             prev = s0 if j == 1 else out[0][-2]
+            if side and j >= 2 and self.down_side_streams:
+                # The down path is a strict chain in forward, but in BACKWARD the small down cells (32^2 and below: ~300
+                # latency-bound launches each) only wait for the small up cells of their own column; on the caller's stream
+                # they would queue behind the 128^2 cell of level 1.  A stream of their own (joined at once in forward)
+                # lets autograd run their backward beside it.
+                cur = torch.cuda.current_stream(x.device)
+                st = self._cell_stream(100 + j, x.device)
+                st.wait_stream(cur)
+                fused.set_slot(100 + j)
+                try:
+                    with torch.cuda.stream(st):
+                        o = self.blocks[0][j](prev, out[0][-1], alpha_dn_nm, alpha_dn, beta_dn)
+                finally:
+                    fused.set_slot(0)
+                cur.wait_stream(st)
+                out[0].append(o)
+                continue
             out[0].append(self.blocks[0][j](prev, out[0][-1], alpha_dn_nm, alpha_dn, beta_dn))
-        side = self.concurrent_cells and x.is_cuda
         for i in range(1, depth):
             cur = torch.cuda.current_stream(x.device) if side else None
             row, joins = [], []
