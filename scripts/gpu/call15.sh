@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+cd $GRAFT_REPO_ROOT
+O=gpurun_out
+python -m pytest tests/test_gpu_parity_r2.py tests/test_optim_mix.py -m gpu -q -k "graphed or fused_search or arch_grads or genotype" > $O/r2p_tests.log 2>&1; echo "tests_rc=$?"
+timeout 600 python bench.py --no-cpu --no-ref-gpu --no-fp32-line > $O/r2p_bench_ds1.json 2> $O/r2p_bench_ds1.err
+SENAS_DOWN_STREAMS=0 timeout 600 python bench.py --no-cpu --no-ref-gpu --no-fp32-line > $O/r2p_bench_ds0.json 2> $O/r2p_bench_ds0.err
+echo done

@@ -89,15 +89,17 @@ class SenasSearch(nn.Module):
         # out[i][j]: output of cell (i, j); row 0 is the down path.  The reference (senas_search.py:87-107) walks
         # j = depth-2 .. 0 outside and i inside while overwriting cell_out[i + j]; cell (i, j) reads cell_out[j .. i+j-1]
         # = out[0..i-1][j] and cell_out[i + j] = out[i-1][j+1], which the level-by-level walk below provides unchanged.
-        out = [[self.stem1(s0)]]
         side = self.concurrent_cells and x.is_cuda
+        out = [[self.stem1(s0)]]
         for j in range(1, depth):
             prev = s0 if j == 1 else out[0][-2]
             if side and j >= 2 and self.down_side_streams:
                 # The down path is a strict chain in forward, but in BACKWARD the small down cells (32^2 and below: ~300
                 # latency-bound launches each) only wait for the small up cells of their own column; on the caller's stream
                 # they would queue behind the 128^2 cell of level 1.  A stream of their own (joined at once in forward)
-                # lets autograd run their backward beside it.
+                # lets autograd run their backward beside it: 86.9 -> 84.8 ms per step.  (A fully dependency-driven
+                # schedule -- every cell waiting only for the events of its own inputs, so that the forward down path
+                # also overlaps with column 0 -- measured the same, 84.9 vs 84.8 ms, and was not kept.)
                 cur = torch.cuda.current_stream(x.device)
                 st = self._cell_stream(100 + j, x.device)
                 st.wait_stream(cur)
