@@ -68,6 +68,10 @@ class GraphedSearchStep:
         self.arch = [p for g in a_opt.param_groups for p in g['params']]
         dev = self.params[0].device
         self.overlap = bool(overlap) and comm is not None and self.world > 1
+        if self.overlap and self.defer_wgrad:
+            # the per-cell all-reduce is ordered after the cell's backward through the CALLER's stream; deferred weight-gradient
+            # lanes are not joined to it yet -- the two options exclude each other
+            self.defer_wgrad = False
         # opt-in: the architecture step asks autograd for the alpha / beta / gamma gradients only.  The reference's arch
         # step (search/senas_search.py Architecture.step: loss.backward()) also produces every weight gradient and
         # search_arc.py:271 zeroes them before any use; with this flag they are never computed (torch.autograd.grad on
