@@ -262,6 +262,7 @@ def _convbn_on_tensor_cores(x, conv, norm):
 
 
 import os as _os
+stem_convbn = [_os.environ.get('SENAS_STEM_CONVBN', '0') == '1']  # stem1's BasicBlock through the same op (bf16 mode)
 fused_convbn = [_os.environ.get('SENAS_NO_CONVBN', '0') != '1']  # switch (A/B runs, tests): False keeps cuDNN / ATen for the Shrink / Rectify blocks in every mode
 
 
@@ -359,6 +360,12 @@ class BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
 
     def forward(self, x):
+        if stem_convbn[0] and _convbn_on_tensor_cores(x, self.conv1, self.bn1) and _convbn_on_tensor_cores(x, self.conv2, self.bn2):
+            # the same library op as the Shrink / Rectify blocks: conv1 + bn1, then ReLU (folded into the bf16 cast and the
+            # data-gradient epilogue) + conv2 + bn2; the residual add stays a PyTorch kernel
+            h = _ConvBnFn.apply(x, self.conv1.weight, self.bn1.weight, self.bn1.bias, self.bn1, False)
+            out = _ConvBnFn.apply(h, self.conv2.weight, self.bn2.weight, self.bn2.bias, self.bn2, True)
+            return out + x
         out = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
         out += x
         return out

@@ -447,3 +447,47 @@ def test_dice_ce_loss_emulated(emu, B, C, H, W, cl):
 def test_dice_ce_loss_gpu(B, C, H, W, cl):
     from senas_b200 import _lib
     _loss_case(_lib.get(), 'cuda', B, C, H, W, cl)
+
+
+@pytest.mark.gpu
+def test_stem_basic_block_through_convbn_vs_pytorch():
+    """stem1's BasicBlock (utils/operations.py:235-268: conv3x3 + BN + ReLU + conv3x3 + BN + residual) through two
+    senas_convbn_* calls (ops.stem_convbn; bf16 mode) against the same module evaluated by PyTorch in fp32."""
+    import senas_b200
+    from senas_b200 import ops
+    senas_b200.exact_fp32()
+    dev = 'cuda'
+    torch.manual_seed(7)
+    blk = ops.BasicBlock(32, 32).to(dev)
+    blk.apply(senas_b200.weights_init)
+    with torch.no_grad():
+        for conv in (blk.conv1, blk.conv2):
+            conv.weight.copy_(conv.weight.bfloat16().float())
+    ref = copy.deepcopy(blk)
+    x = torch.randn(4, 32, 128, 128, device=dev).bfloat16().float().contiguous(memory_format=torch.channels_last)
+    gout = torch.randn(4, 32, 128, 128, device=dev).contiguous(memory_format=torch.channels_last)
+    xr = x.clone().requires_grad_(True)
+    senas_b200.set_conv_mode('fp32')
+    want = ref(xr)
+    want.backward(gout)
+    old = ops.stem_convbn[0]
+    ops.stem_convbn[0] = True
+    senas_b200.set_conv_mode('bf16')
+    try:
+        xg = x.clone().requires_grad_(True)
+        n0 = senas_b200._lib.get().senas_launch_count()
+        got = blk(xg)
+        got.backward(gout)
+        torch.cuda.synchronize()
+        assert senas_b200._lib.get().senas_launch_count() - n0 >= 20
+    finally:
+        ops.stem_convbn[0] = old
+        senas_b200.set_conv_mode('fp32')
+
+    def rel(a, b):
+        return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+    # the second conv reads relu(bn1(.)), which is NOT bf16-representable: forward at the 2e-2 gate of the mode
+    assert rel(got, want.detach()) <= 2e-2
+    assert rel(xg.grad, xr.grad) <= 2e-2
+    for n, p in blk.named_parameters():
+        assert rel(p.grad, dict(ref.named_parameters())[n].grad) <= 2e-2, n
