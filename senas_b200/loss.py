@@ -11,6 +11,14 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 fused_loss = [True]  # CUDA, <= 8 classes, no process group: libsenas_b200's dice_ce kernels
 
 
@@ -33,8 +41,10 @@ class _DiceCEFn(torch.autograd.Function):
         coef = torch.empty(3 * C + 1, dtype=torch.float32, device=dev)
         scratch = torch.empty(296 * 25, dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream if logits.is_cuda else 0
-        _lib.check(lib, lib.senas_dice_ce_forward(logits.data_ptr(), target.data_ptr(), B, C, HW, st[0], st[1], st[3], 1.0,
-                                                  float(smooth), loss.data_ptr(), coef.data_ptr(), scratch.data_ptr(), stream))
+        with (torch.cuda.device(dev) if logits.is_cuda else _NullCtx()):  # the library launches on the current device
+            _lib.check(lib, lib.senas_dice_ce_forward(logits.data_ptr(), target.data_ptr(), B, C, HW, st[0], st[1], st[3], 1.0,
+                                                      float(smooth), loss.data_ptr(), coef.data_ptr(), scratch.data_ptr(),
+                                                      stream))
         ctx.save_for_backward(logits, target, coef)
         ctx.lib, ctx.geo = lib, (B, C, HW, st[0], st[1], st[3])
         return loss
@@ -49,8 +59,9 @@ class _DiceCEFn(torch.autograd.Function):
             raise RuntimeError('senas_b200: dice_ce backward needs dense logits')
         g = g.float().contiguous()
         stream = torch.cuda.current_stream(logits.device).cuda_stream if logits.is_cuda else 0
-        _lib.check(ctx.lib, ctx.lib.senas_dice_ce_backward(logits.data_ptr(), target.data_ptr(), B, C, HW, sn, sc, sp,
-                                                           coef.data_ptr(), g.data_ptr(), d.data_ptr(), stream))
+        with (torch.cuda.device(logits.device) if logits.is_cuda else _NullCtx()):
+            _lib.check(ctx.lib, ctx.lib.senas_dice_ce_backward(logits.data_ptr(), target.data_ptr(), B, C, HW, sn, sc, sp,
+                                                               coef.data_ptr(), g.data_ptr(), d.data_ptr(), stream))
         return d, None, None, None
 
 

@@ -34,6 +34,14 @@ def _pad4(n):
     return (n + 3) & ~3
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class FusedSearchOptim:
     def __init__(self, model, w_opt, a_opt, grad_clip=5.0, lib=None):
         from .fused import GraphRunner  # noqa: F401  (runner discovery below)
@@ -180,8 +188,16 @@ class FusedSearchOptim:
                     return False
         return True
 
+    def _guard(self):
+        """Kernels launch on the CURRENT device: make it the arenas' (a model on cuda:1 while cuda:0 is current)."""
+        return torch.cuda.device(self.flat_p.device) if self.flat_p.is_cuda else _NullCtx()
+
     def adam_step(self):
         g = self.a_opt.param_groups[0]
+        with self._guard():
+            self._adam_step(g)
+
+    def _adam_step(self, g):
         _lib.check(self.lib, self.lib.senas_adam_step(
             self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.adam_avg.data_ptr(), self.adam_sq.data_ptr(),
             self.adam_t.data_ptr(), self.n_arch, self.lr_a.data_ptr(), float(g['betas'][0]), float(g['betas'][1]),
@@ -189,6 +205,10 @@ class FusedSearchOptim:
 
     def sgd_step(self):
         g = self.w_opt.param_groups[0]
+        with self._guard():
+            self._sgd_step(g)
+
+    def _sgd_step(self, g):
         _lib.check(self.lib, self.lib.senas_sgd_clip_step(
             self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.n, self.lr_w.data_ptr(),
             float(g['momentum']), float(g['weight_decay']), self.grad_clip, self.scratch.data_ptr(), self.norm.data_ptr(),
