@@ -87,11 +87,11 @@ class GraphedSearchStep:
             self.fopt = FusedSearchOptim(model, w_opt, a_opt, grad_clip)
             self.params = self.fopt.params
             self._comm_stream = torch.cuda.Stream() if self.overlap else None
+            self.all_views = [self.fopt.grad_views[id(p)] for p in self.params]
             if self.segmented:
                 self.bucket_arch = self.fopt.flat_g[:self.fopt.n_arch]
                 self.bucket_all = self.fopt.flat_g
                 self.n_rest = self.fopt.n_rest
-                self.all_views = [self.fopt.grad_views[id(p)] for p in self.params]
         elif self.segmented:
             self.bucket_arch = torch.zeros(sum(p.numel() for p in self.arch), device=dev)
             self.bucket_all = torch.zeros(sum(p.numel() for p in self.params), device=dev)
