@@ -139,3 +139,20 @@ def test_unsupported_configurations_fail_at_construction():
         with pytest.raises(NotImplementedError, match='candidate lists'):
             OPS[name](32, 8, OpType.NORM, 0)
     senas_b200.NAS(1, 32, 2, depth=3, meta_node_num=3, use_sharing=False, double_down_channel=False)  # supported
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the contract's reference arm: the unmodified reference on the host cores) prints ONE JSON
+    line with the agreed keys; run here on a tiny sample (2 x 1x64x64, one step)."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--size', '64', '--batch', '2',
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'search_step_images_per_sec' and d['unit'] == 'images/s'
+    assert d['higher_is_better'] is True and d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 1
+    assert d['cpu_baseline']['kind'] == 'reference' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'unmodified reference' in d['cpu_baseline']['sample']
